@@ -1,0 +1,85 @@
+"""Generate tests/golden/*.np[yz] by running the UNMODIFIED reference (oracle/_ref).
+
+Run once in the build container (needs /root/reference to have been compiled by
+`make -C oracle ref`):   python tests/golden/make_golden.py
+The outputs are committed; the GPU box only ever reads the committed files.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.oracle import LAYOUT, Ref  # noqa: E402
+from hand_tracking_samples_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+STRIDE = 4099  # prime stride for sampling the two 4.7M-element FC weight tensors
+
+
+def sample(params):
+    d = {}
+    for k, (off, n) in LAYOUT.items():
+        v = params[off:off + n]
+        d[k] = v[::STRIDE].copy() if n > 100000 else v.copy()
+    return d
+
+
+def main():
+    r = Ref()
+    r.init()
+    p0 = r.save()
+    meta = {"init_sha256": hashlib.sha256(p0.tobytes()).hexdigest(),
+            "known": {"conv1.W[0]": float(p0[0]), "conv2.W[0]": float(p0[416]),
+                      "fc1.W[0]": float(p0[16864]), "fc2.W[0]": float(p0[4737504])},
+            "stride": STRIDE}
+
+    crops = np.concatenate([synth.uniform_crops(2, 1234), synth.depthlike_crops(2, 1234),
+                            np.zeros((1, 4096), np.float32), np.ones((1, 4096), np.float32)])
+    labels = synth.heatmap_labels(crops.shape[0], 4321)
+    np.save(os.path.join(OUT, "crops.npy"), crops)
+    np.save(os.path.join(OUT, "labels.npy"), labels)
+
+    # Eval with Init() weights
+    np.save(os.path.join(OUT, "eval_init.npy"), r.eval(crops))
+    tr = r.forward_trace(crops[0])
+    np.savez_compressed(os.path.join(OUT, "trace_crop0.npz"), pool1=tr[3], pool2=tr[6], fc1=tr[8], logits=tr[9])
+
+    # Eval with fc2.W x30 ("peaky" softmax, SURVEY.md section 4 fixture ii)
+    pk = p0.copy()
+    off, n = LAYOUT["fc2.W"]
+    pk[off:off + n] *= 30.0
+    r.load(pk)
+    np.save(os.path.join(OUT, "eval_peaky.npy"), r.eval(crops))
+
+    # per-sample gradients at Init() weights
+    r.load(p0)
+    gs = {}
+    mses = []
+    for i in range(crops.shape[0]):
+        g, m = r.grad_sample(crops[i], labels[i])
+        mses.append(m)
+        for k, v in sample(g).items():
+            gs["%d/%s" % (i, k)] = v
+    gs["mse"] = np.array(mses, np.float32)
+    np.savez_compressed(os.path.join(OUT, "grads_init.npz"), **gs)
+
+    # 24 sequential reference Train steps (cycling the 6 crops), alpha as train-cnn.cpp:160
+    r.load(p0)
+    xs = np.concatenate([crops] * 4)
+    ts = np.concatenate([labels] * 4)
+    mse = r.train_seq(xs, ts, 0.001)
+    p1 = r.save()
+    meta["train24_sha256"] = hashlib.sha256(p1.tobytes()).hexdigest()
+    np.savez_compressed(os.path.join(OUT, "train24.npz"), mse=mse, **sample(p1))
+    np.save(os.path.join(OUT, "eval_train24.npy"), r.eval(crops))
+
+    json.dump(meta, open(os.path.join(OUT, "meta.json"), "w"), indent=1)
+    print(json.dumps(meta, indent=1))
+
+
+if __name__ == "__main__":
+    main()
