@@ -1,0 +1,87 @@
+"""ctypes binding of include/handposedd.h (libhandposedd.so, built in-tree by _build.py).
+
+This is the only route from Python into the product: there is no PyTorch or NumPy
+implementation of the path behind it, so a missing library or a missing GPU is a hard error.
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+HP_OK = 0
+PRECISION_FP32 = 0
+PRECISION_TENSOR = 1
+N_IN = 4096
+N_OUT = 2304
+N_PARAMS = 9458400
+CNNB_BYTES = 37833600
+
+# every symbol include/handposedd.h declares
+SYMBOLS = [
+    "hp_create", "hp_create_handposedd", "hp_retain", "hp_destroy", "hp_init_xavier", "hp_load_cnnb",
+    "hp_save_cnnb", "hp_load_cnnb_file", "hp_save_cnnb_file", "hp_eval_batch", "hp_eval_batch_device",
+    "hp_train_batch", "hp_train_batch_device", "hp_grad_batch_device", "hp_get_grads", "hp_device_ptrs",
+    "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_shutdown", "hp_launch_count",
+    "hp_peek", "hp_last_error", "hp_version",
+]
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("in_dims", C.c_int * 3), ("w_dims", C.c_int * 4),
+                ("out_dims", C.c_int * 3), ("n_spans", C.c_int), ("spans", C.POINTER(C.c_int))]
+
+
+class HpError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("handposedd status %d: %s" % (status, msg))
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    """Load (building if stale and nvcc is present) libhandposedd.so.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path) or _build._stale():
+        if os.path.exists(_build.nvcc()):
+            _build.build()
+    if not os.path.exists(path):
+        raise FileNotFoundError(path + ": the CUDA library is not built (python -m hand_tracking_samples_b200._build)")
+    L = C.CDLL(path)
+    vp, i64, fp = C.c_void_p, C.c_int64, C.c_float
+    L.hp_create.argtypes = [C.POINTER(LayerDesc), C.c_int, C.c_int, C.POINTER(vp)]
+    L.hp_create_handposedd.argtypes = [C.c_int, C.POINTER(vp)]
+    L.hp_retain.argtypes = [vp]
+    L.hp_destroy.argtypes = [vp]
+    L.hp_init_xavier.argtypes = [vp]
+    L.hp_load_cnnb.argtypes = [vp, vp, C.c_size_t]
+    L.hp_save_cnnb.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.hp_load_cnnb_file.argtypes = [vp, C.c_char_p]
+    L.hp_save_cnnb_file.argtypes = [vp, C.c_char_p]
+    L.hp_eval_batch.argtypes = [vp, vp, i64, vp, C.c_int]
+    L.hp_eval_batch_device.argtypes = [vp, vp, i64, vp, C.c_int, vp]
+    L.hp_train_batch.argtypes = [vp, vp, vp, i64, fp, vp, C.c_int]
+    L.hp_train_batch_device.argtypes = [vp, vp, vp, i64, fp, vp, C.c_int, vp]
+    L.hp_grad_batch_device.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp]
+    L.hp_get_grads.argtypes = [vp, vp]
+    L.hp_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.hp_apply_grads_device.argtypes = [vp, fp, vp]
+    L.hp_dp_unique_id.argtypes = [vp]
+    L.hp_dp_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.hp_dp_shutdown.argtypes = [vp]
+    L.hp_launch_count.argtypes = [vp]
+    L.hp_launch_count.restype = i64
+    L.hp_peek.argtypes = [vp, C.c_int, i64, vp]
+    L.hp_last_error.restype = C.c_char_p
+    L.hp_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != HP_OK:
+        raise HpError(status, lib().hp_last_error().decode())

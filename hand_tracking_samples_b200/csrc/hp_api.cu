@@ -1,0 +1,618 @@
+// hp_api.cu -- the C ABI of include/handposedd.h: net lifetime, the device-resident
+// weight store and its .cnnb (de)serialisation, CNN::Init, the batched Eval / Train
+// entry points (host-buffer variants stream through pinned staging buffers), and
+// NCCL data parallelism.  Kernels live in hp_fp32.cu and hp_tc.cu.
+//
+// Reference interfaces replaced: CNN::{Eval,Train,Init,loadb,saveb}
+// (third_party/cnn.h:550-593) and PoseInitializerCNN (include/handtrack.h:103-130).
+#include "../../include/handposedd.h"
+#include "hp_common.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+namespace hp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+constexpr int64_t FP32_CHUNK = 2048;   // crops per pass of the FP32 path (im2col workspace bound)
+constexpr int64_t STAGE_CHUNK = 8192;  // crops per host<->device staging chunk
+
+static std::mutex g_ref_mutex;
+
+template <class T>
+static int dev_alloc(T *&p, size_t count)
+{
+    if (p) { cudaFree(p); p = nullptr; }
+    HP_CUDA_TRY(cudaMalloc((void **)&p, count * sizeof(T)));
+    return 0;
+}
+
+int ensure_workspace(Net &net, int64_t n)
+{
+    Workspace &w = net.ws;
+    if (n <= w.cap) return 0;
+    int64_t cap = std::max<int64_t>(n, std::min<int64_t>(FP32_CHUNK, std::max<int64_t>(2 * w.cap, 64)));
+    HP_CUDA_TRY(cudaStreamSynchronize(net.stream));
+    int rc = 0;
+    rc |= dev_alloc(w.p1, cap * P1_N);
+    rc |= dev_alloc(w.idx1, cap * P1_N);
+    rc |= dev_alloc(w.col, cap * C2_POS * C2_KDIM);
+    rc |= dev_alloc(w.c2, cap * C2_POS * C2_CO);
+    rc |= dev_alloc(w.p2, cap * P2_N);
+    rc |= dev_alloc(w.idx2, cap * P2_N);
+    rc |= dev_alloc(w.h1, cap * FC1_OUT);
+    rc |= dev_alloc(w.logits, cap * N_OUT);
+    rc |= dev_alloc(w.y, cap * N_OUT);
+    rc |= dev_alloc(w.dlog, cap * N_OUT);
+    rc |= dev_alloc(w.da1, cap * FC1_OUT);
+    rc |= dev_alloc(w.g2, cap * P2_N);
+    rc |= dev_alloc(w.colgrad, cap * C2_POS * C2_KDIM);
+    rc |= dev_alloc(w.g1, cap * P1_N);
+    if (!w.partial) {
+        w.partial_floats = (size_t)128 * C2_CO * C2_KDIM;  // conv2 split-K partials dominate
+        rc |= dev_alloc(w.partial, w.partial_floats);
+    }
+    if (rc) return HP_ERR_CUDA;
+    w.cap = cap;
+    return 0;
+}
+
+static int ensure_staging(Net &net, int64_t n, bool pin_in, bool pin_out)
+{
+    if (n > net.stage_cap) {
+        HP_CUDA_TRY(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+            if (dev_alloc(net.dev_in[b], n * N_IN)) return HP_ERR_CUDA;
+            if (dev_alloc(net.dev_out[b], n * N_OUT)) return HP_ERR_CUDA;
+        }
+        if (dev_alloc(net.dev_t, n * N_OUT)) return HP_ERR_CUDA;
+        if (dev_alloc(net.dev_mse, n)) return HP_ERR_CUDA;
+        net.stage_cap = n;
+    }
+    // pinned bounce buffers only when the caller's memory is pageable
+    if (pin_in && n > net.pin_in_cap) {
+        for (int b = 0; b < 2; b++) {
+            if (net.pin_in[b]) cudaFreeHost(net.pin_in[b]);
+            net.pin_in[b] = nullptr;
+            HP_CUDA_TRY(cudaMallocHost((void **)&net.pin_in[b], n * N_IN * sizeof(float)));
+        }
+        net.pin_in_cap = n;
+    }
+    if (pin_out && n > net.pin_out_cap) {
+        for (int b = 0; b < 2; b++) {
+            if (net.pin_out[b]) cudaFreeHost(net.pin_out[b]);
+            net.pin_out[b] = nullptr;
+            HP_CUDA_TRY(cudaMallocHost((void **)&net.pin_out[b], n * N_OUT * sizeof(float)));
+        }
+        net.pin_out_cap = n;
+    }
+    return 0;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// ---- CNN::Init (cnn.h:581-586; LConv::init :280-285; LFull::init :446-451) --------
+// std::default_random_engine (libstdc++) == minstd_rand0, default seed 1, ONE engine
+// shared by all layers; each weight draws one value through a fresh
+// uniform_real_distribution<float>(-r, r): generate_canonical<float,24> =
+// float(u - 1) / float(2147483646.0L), result = canon * (b - a) + a.
+static void xavier_host(std::vector<float> &p)
+{
+    std::fill(p.begin(), p.end(), 0.0f);
+    uint32_t state = 1u;
+    auto draw = [&](float a, float b) {
+        state = (uint32_t)(((uint64_t)state * 16807u) % 2147483647u);
+        float canon = (float)(state - 1u) / (float)2147483646.0L;
+        if (canon >= 1.0f) canon = nextafterf(1.0f, 0.0f);
+        return canon * (b - a) + a;
+    };
+    auto fill = [&](int off, int count, int fan) {
+        const float r = sqrtf(6.0f / fan);
+        for (int i = 0; i < count; i++) p[off + i] = draw(-r, r);
+    };
+    fill(OFF_C1W, 400, C1_K * C1_K * 1 + C1_K * C1_K * C1_CO);
+    fill(OFF_C2W, C2_CO * C2_KDIM, C2_K * C2_K * C2_CI + C2_K * C2_K * C2_CO);
+    fill(OFF_F1W, FC1_IN * FC1_OUT, FC1_IN + FC1_OUT);
+    fill(OFF_F2W, FC2_IN * FC2_OUT, FC2_IN + FC2_OUT);
+}
+
+// ---- NCCL, bound lazily so that inference has no NCCL dependency ---------------------
+struct Id128 { char b[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_bind()
+{
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { set_error("NCCL not found: %s", dlerror()); return HP_ERR_NCCL; }
+#define BIND(field, sym)                                                                  \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, sym);                                   \
+    if (!g_nccl.field) { set_error("NCCL symbol %s missing", sym); g_nccl.lib = nullptr; return HP_ERR_NCCL; }
+    BIND(GetUniqueId, "ncclGetUniqueId");
+    BIND(CommInitRank, "ncclCommInitRank");
+    BIND(AllReduce, "ncclAllReduce");
+    BIND(CommDestroy, "ncclCommDestroy");
+    BIND(GetErrorString, "ncclGetErrorString");
+    BIND(GroupStart, "ncclGroupStart");
+    BIND(GroupEnd, "ncclGroupEnd");
+#undef BIND
+    return 0;
+}
+#define HP_NCCL_TRY(expr)                                                               \
+    do {                                                                                \
+        int _r = (expr);                                                                \
+        if (_r != 0) { set_error("%s failed: %s", #expr, g_nccl.GetErrorString(_r)); return HP_ERR_NCCL; } \
+    } while (0)
+
+// all-reduce the three gradient buckets behind the backward pass, fc2 first
+static int dp_allreduce(Net &net, cudaStream_t s)
+{
+    if (net.world <= 1) return 0;
+    const int off[4] = {OFF_F2W, OFF_F1W, 0, 0};
+    const int end[4] = {N_PARAMS, OFF_F2W, OFF_F1W, 0};
+    for (int b = 0; b < 3; b++) {
+        HP_CUDA_TRY(cudaStreamWaitEvent(net.comm_stream, net.ev_bucket[b], 0));
+        HP_NCCL_TRY(g_nccl.AllReduce(net.grads + off[b], net.grads + off[b], (size_t)(end[b] - off[b]), /*ncclFloat32*/ 7,
+                                     /*ncclSum*/ 0, net.nccl_comm, net.comm_stream));
+    }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_comm, net.comm_stream));
+    HP_CUDA_TRY(cudaStreamWaitEvent(s, net.ev_comm, 0));
+    return 0;
+}
+
+static int check_precision(int precision)
+{
+    if (precision != HP_PRECISION_FP32 && precision != HP_PRECISION_TENSOR) {
+        set_error("unknown precision %d", precision);
+        return HP_ERR_INVALID;
+    }
+    return 0;
+}
+
+// forward over device buffers, chunked to the workspace
+static int eval_device(Net &net, const float *x, int64_t n, float *y, int precision, cudaStream_t s)
+{
+    if (precision == HP_PRECISION_TENSOR) {
+        if (net.tc_dirty) {
+            if (int rc = tc_refresh_weights(net, s)) return rc;
+        }
+        return tc_forward(net, x, n, y, s);
+    }
+    for (int64_t b = 0; b < n; b += FP32_CHUNK) {
+        const int64_t m = std::min<int64_t>(FP32_CHUNK, n - b);
+        if (int rc = ensure_workspace(net, m)) return rc;
+        if (int rc = fp32_forward(net, x + b * N_IN, m, y + b * N_OUT, false, s)) return rc;
+    }
+    net.last_n = std::min<int64_t>(n, FP32_CHUNK);
+    return 0;
+}
+
+static int grad_device(Net &net, const float *x, const float *t, int64_t n, float *mse, int precision, cudaStream_t s)
+{
+    if (precision == HP_PRECISION_TENSOR) {
+        set_error("tensor-core training path not built yet; use HP_PRECISION_FP32");
+        return HP_ERR_UNSUPPORTED;
+    }
+    for (int64_t b = 0; b < n; b += FP32_CHUNK) {
+        const int64_t m = std::min<int64_t>(FP32_CHUNK, n - b);
+        if (int rc = ensure_workspace(net, m)) return rc;
+        if (int rc = fp32_forward(net, x + b * N_IN, m, nullptr, true, s)) return rc;
+        if (int rc = fp32_backward(net, x + b * N_IN, t + b * N_OUT, m, mse ? mse + b : nullptr, b > 0, s)) return rc;
+    }
+    net.last_n = std::min<int64_t>(n, FP32_CHUNK);
+    return 0;
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+struct hp_net {
+    Net n;
+};
+
+static int check_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+        return HP_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (%d devices)", device, count); return HP_ERR_INVALID; }
+    cudaDeviceProp prop;
+    HP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this build only contains sm_100a code", device, prop.major, prop.minor);
+        return HP_ERR_NO_DEVICE;
+    }
+    return 0;
+}
+
+static bool is_handposedd(const hp_layer_desc *L, int n)
+{
+    if (n != 11 || !L) return false;
+    auto conv = [](const hp_layer_desc &d, int ix, int iy, int iz, int kx, int ky, int ci, int co, int ox, int oy, int oz) {
+        return d.kind == HP_LAYER_CONV && d.in_dims[0] == ix && d.in_dims[1] == iy && d.in_dims[2] == iz && d.w_dims[0] == kx &&
+               d.w_dims[1] == ky && d.w_dims[2] == ci && d.w_dims[3] == co && d.out_dims[0] == ox && d.out_dims[1] == oy && d.out_dims[2] == oz;
+    };
+    auto pool = [](const hp_layer_desc &d, int x, int y, int z) {
+        return d.kind == HP_LAYER_MAXPOOL && d.in_dims[0] == x && d.in_dims[1] == y && d.in_dims[2] == z;
+    };
+    auto full = [](const hp_layer_desc &d, int i, int o) { return d.kind == HP_LAYER_FULL && d.in_dims[0] == i && d.out_dims[0] == o; };
+    auto act = [](const hp_layer_desc &d, int nn) { return d.kind == HP_LAYER_TANH && d.in_dims[0] == nn; };
+    if (!conv(L[0], 64, 64, 1, 5, 5, 1, 16, 60, 60, 16)) return false;
+    if (!act(L[1], 57600) || !pool(L[2], 60, 60, 16) || !pool(L[3], 30, 30, 16)) return false;
+    if (!conv(L[4], 15, 15, 16, 4, 4, 16, 64, 12, 12, 64)) return false;
+    if (!act(L[5], 9216) || !pool(L[6], 12, 12, 64)) return false;
+    if (!full(L[7], 2304, 2048) || !act(L[8], 2048) || !full(L[9], 2048, 2304)) return false;
+    if (L[10].kind != HP_LAYER_SOFTMAX_CHUNKED || L[10].n_spans != 24 || !L[10].spans) return false;
+    for (int i = 0; i < 24; i++)
+        if (L[10].spans[i] != (i < 8 ? 256 : 16)) return false;
+    return true;
+}
+
+extern "C" {
+
+int hp_create_handposedd(int device, hp_net **out)
+{
+    if (!out) { set_error("out is NULL"); return HP_ERR_INVALID; }
+    *out = nullptr;
+    if (int rc = check_device(device)) return rc;
+    HP_CUDA_TRY(cudaSetDevice(device));
+    hp_net *h = new hp_net;
+    Net &n = h->n;
+    n.device = device;
+    HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.stream, cudaStreamNonBlocking));
+    HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.comm_stream, cudaStreamNonBlocking));
+    HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.d2h_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_in[b], cudaEventDisableTiming));
+        HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_out[b], cudaEventDisableTiming));
+        HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_comp[b], cudaEventDisableTiming));
+    }
+    for (int b = 0; b < 3; b++) HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_bucket[b], cudaEventDisableTiming));
+    HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_comm, cudaEventDisableTiming));
+    HP_CUDA_TRY(cudaMalloc((void **)&n.params, (size_t)N_PARAMS * sizeof(float)));
+    HP_CUDA_TRY(cudaMalloc((void **)&n.grads, (size_t)N_PARAMS * sizeof(float)));
+    HP_CUDA_TRY(cudaMemset(n.params, 0, (size_t)N_PARAMS * sizeof(float)));
+    HP_CUDA_TRY(cudaMemset(n.grads, 0, (size_t)N_PARAMS * sizeof(float)));
+    if (int rc = tc_init(n)) return rc;
+    *out = h;
+    return HP_OK;
+}
+
+int hp_create(const hp_layer_desc *layers, int n_layers, int device, hp_net **out)
+{
+    if (!is_handposedd(layers, n_layers)) {
+        set_error("layer list is not handposedd (include/handtrack.h:108-118); no kernels for it");
+        if (out) *out = nullptr;
+        return HP_ERR_UNSUPPORTED;
+    }
+    return hp_create_handposedd(device, out);
+}
+
+int hp_retain(hp_net *net)
+{
+    if (!net) { set_error("net is NULL"); return HP_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(g_ref_mutex);
+    net->n.refcount++;
+    return HP_OK;
+}
+
+int hp_destroy(hp_net *net)
+{
+    if (!net) return HP_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_ref_mutex);
+        if (--net->n.refcount > 0) return HP_OK;
+    }
+    Net &n = net->n;
+    cudaSetDevice(n.device);
+    cudaDeviceSynchronize();
+    if (n.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n.nccl_comm);
+    tc_destroy(n);
+    Workspace &w = n.ws;
+    void *bufs[] = {n.params, n.grads, w.p1, w.idx1, w.col, w.c2, w.p2, w.idx2, w.h1, w.logits, w.y, w.dlog, w.da1, w.g2, w.colgrad,
+                    w.g1, w.partial, w.p2_bf, w.h1_bf, n.dev_in[0], n.dev_in[1], n.dev_out[0], n.dev_out[1], n.dev_t, n.dev_mse};
+    for (void *p : bufs)
+        if (p) cudaFree(p);
+    for (int b = 0; b < 2; b++) {
+        if (n.pin_in[b]) cudaFreeHost(n.pin_in[b]);
+        if (n.pin_out[b]) cudaFreeHost(n.pin_out[b]);
+        if (n.ev_in[b]) cudaEventDestroy(n.ev_in[b]);
+        if (n.ev_out[b]) cudaEventDestroy(n.ev_out[b]);
+        if (n.ev_comp[b]) cudaEventDestroy(n.ev_comp[b]);
+    }
+    for (int b = 0; b < 3; b++)
+        if (n.ev_bucket[b]) cudaEventDestroy(n.ev_bucket[b]);
+    if (n.ev_comm) cudaEventDestroy(n.ev_comm);
+    if (n.stream) cudaStreamDestroy(n.stream);
+    if (n.comm_stream) cudaStreamDestroy(n.comm_stream);
+    if (n.d2h_stream) cudaStreamDestroy(n.d2h_stream);
+    delete net;
+    return HP_OK;
+}
+
+int hp_init_xavier(hp_net *net)
+{
+    if (!net) { set_error("net is NULL"); return HP_ERR_INVALID; }
+    std::vector<float> p(N_PARAMS);
+    xavier_host(p);
+    return hp_load_cnnb(net, p.data(), p.size() * sizeof(float));
+}
+
+int hp_load_cnnb(hp_net *net, const void *bytes, size_t n_bytes)
+{
+    if (!net || (!bytes && n_bytes)) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &n = net->n;
+    HP_CUDA_TRY(cudaSetDevice(n.device));
+    size_t take = std::min<size_t>(n_bytes, (size_t)HP_CNNB_BYTES);
+    // like loadvb's istream::read (cnn.h:97) a short stream fills a prefix; a float torn by
+    // the end of the stream is dropped here rather than half-written
+    take -= take % sizeof(float);
+    HP_CUDA_TRY(cudaStreamSynchronize(n.stream));
+    if (take) HP_CUDA_TRY(cudaMemcpy(n.params, bytes, take, cudaMemcpyHostToDevice));
+    n.tc_dirty = true;
+    return HP_OK;
+}
+
+int hp_save_cnnb(const hp_net *net, void *bytes, size_t capacity, size_t *n_written)
+{
+    if (!net || !bytes) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (capacity < (size_t)HP_CNNB_BYTES) { set_error("buffer too small: need %d bytes", HP_CNNB_BYTES); return HP_ERR_IO; }
+    const Net &n = net->n;
+    HP_CUDA_TRY(cudaSetDevice(n.device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    HP_CUDA_TRY(cudaMemcpy(bytes, n.params, (size_t)HP_CNNB_BYTES, cudaMemcpyDeviceToHost));
+    if (n_written) *n_written = (size_t)HP_CNNB_BYTES;
+    return HP_OK;
+}
+
+int hp_load_cnnb_file(hp_net *net, const char *path)
+{
+    if (!net || !path) { set_error("bad argument"); return HP_ERR_INVALID; }
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error("cannot open %s", path); return HP_ERR_IO; }
+    std::vector<char> buf((size_t)HP_CNNB_BYTES);
+    size_t got = fread(buf.data(), 1, buf.size(), f);
+    fclose(f);
+    return hp_load_cnnb(net, buf.data(), got);
+}
+
+int hp_save_cnnb_file(const hp_net *net, const char *path)
+{
+    if (!net || !path) { set_error("bad argument"); return HP_ERR_INVALID; }
+    std::vector<char> buf((size_t)HP_CNNB_BYTES);
+    size_t nw = 0;
+    if (int rc = hp_save_cnnb(net, buf.data(), buf.size(), &nw)) return rc;
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("cannot open %s for writing", path); return HP_ERR_IO; }
+    size_t put = fwrite(buf.data(), 1, nw, f);
+    fclose(f);
+    if (put != nw) { set_error("short write to %s", path); return HP_ERR_IO; }
+    return HP_OK;
+}
+
+int hp_eval_batch_device(hp_net *net, const float *x_dev, int64_t n, float *y_dev, int precision, void *stream)
+{
+    if (!net || n < 0 || (n && (!x_dev || !y_dev))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return eval_device(net->n, x_dev, n, y_dev, precision, (cudaStream_t)stream);
+}
+
+// HOST buffers: chunks flow  host --H2D--> dev_in[b] --kernels--> dev_out[b] --D2H--> host  with
+// two buffers per direction so that the copies of chunk c+1 / c-1 overlap the compute of chunk c.
+int hp_eval_batch(hp_net *net, const float *x, int64_t n, float *y, int precision)
+{
+    if (!net || n < 0 || (n && (!x || !y))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    const int64_t chunk = std::min<int64_t>(n, STAGE_CHUNK);
+    const bool pin_x = is_pinned_host(x), pin_y = is_pinned_host(y);
+    if (int rc = ensure_staging(N, chunk, !pin_x, !pin_y)) return rc;
+    cudaStream_t s = N.stream, h2d = N.comm_stream, d2h = N.d2h_stream;
+    const int nc = (int)((n + chunk - 1) / chunk);
+    // wait until chunk c is back on the host (and bounce it into pageable y)
+    auto retire = [&](int c) -> int {
+        const int b = c & 1;
+        const int64_t m = std::min<int64_t>(chunk, n - (int64_t)c * chunk);
+        HP_CUDA_TRY(cudaEventSynchronize(N.ev_out[b]));
+        if (!pin_y) memcpy(y + (int64_t)c * chunk * N_OUT, N.pin_out[b], (size_t)m * N_OUT * sizeof(float));
+        return 0;
+    };
+    for (int c = 0; c < nc; c++) {
+        const int b = c & 1;
+        const int64_t m = std::min<int64_t>(chunk, n - (int64_t)c * chunk);
+        if (c >= 2)  // buffer pair b is reused: chunk c-2 must be fully out first
+            if (int rc = retire(c - 2)) return rc;
+        const float *src = x + (int64_t)c * chunk * N_IN;
+        if (!pin_x) {
+            memcpy(N.pin_in[b], src, (size_t)m * N_IN * sizeof(float));
+            src = N.pin_in[b];
+        }
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[b], src, (size_t)m * N_IN * sizeof(float), cudaMemcpyHostToDevice, h2d));
+        HP_CUDA_TRY(cudaEventRecord(N.ev_in[b], h2d));
+        HP_CUDA_TRY(cudaStreamWaitEvent(s, N.ev_in[b], 0));
+        if (int rc = eval_device(N, N.dev_in[b], m, N.dev_out[b], precision, s)) return rc;
+        HP_CUDA_TRY(cudaEventRecord(N.ev_comp[b], s));
+        HP_CUDA_TRY(cudaStreamWaitEvent(d2h, N.ev_comp[b], 0));
+        float *dst = pin_y ? y + (int64_t)c * chunk * N_OUT : N.pin_out[b];
+        HP_CUDA_TRY(cudaMemcpyAsync(dst, N.dev_out[b], (size_t)m * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, d2h));
+        HP_CUDA_TRY(cudaEventRecord(N.ev_out[b], d2h));
+    }
+    for (int c = std::max(0, nc - 2); c < nc; c++)
+        if (int rc = retire(c)) return rc;
+    return HP_OK;
+}
+
+int hp_grad_batch_device(hp_net *net, const float *x_dev, const float *t_dev, int64_t n, float *mse_dev, int precision, void *stream)
+{
+    if (!net || n <= 0 || !x_dev || !t_dev) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return grad_device(net->n, x_dev, t_dev, n, mse_dev, precision, (cudaStream_t)stream);
+}
+
+int hp_apply_grads_device(hp_net *net, float alpha, void *stream)
+{
+    if (!net) { set_error("net is NULL"); return HP_ERR_INVALID; }
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return sgd_apply(net->n, alpha, (cudaStream_t)stream);
+}
+
+int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, int64_t n, float alpha, float *mse_dev, int precision,
+                          void *stream)
+{
+    if (!net || n < 0 || (n && (!x_dev || !t_dev))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = grad_device(N, x_dev, t_dev, n, mse_dev, precision, s)) return rc;
+    if (int rc = dp_allreduce(N, s)) return rc;
+    return sgd_apply(N, alpha, s);
+}
+
+int hp_train_batch(hp_net *net, const float *x, const float *t, int64_t n, float alpha, float *mse_out, int precision)
+{
+    if (!net || n < 0 || (n && (!x || !t))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    if (int rc = ensure_staging(N, n, false, false)) return rc;
+    cudaStream_t s = N.stream;
+    HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[0], x, (size_t)n * N_IN * sizeof(float), cudaMemcpyHostToDevice, s));
+    HP_CUDA_TRY(cudaMemcpyAsync(N.dev_t, t, (size_t)n * N_OUT * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (int rc = hp_train_batch_device(net, N.dev_in[0], N.dev_t, n, alpha, N.dev_mse, precision, s)) return rc;
+    if (mse_out) HP_CUDA_TRY(cudaMemcpyAsync(mse_out, N.dev_mse, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HP_CUDA_TRY(cudaStreamSynchronize(s));
+    return HP_OK;
+}
+
+int hp_get_grads(const hp_net *net, float *grads_host)
+{
+    if (!net || !grads_host) { set_error("bad argument"); return HP_ERR_INVALID; }
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    HP_CUDA_TRY(cudaMemcpy(grads_host, net->n.grads, (size_t)N_PARAMS * sizeof(float), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+int hp_device_ptrs(hp_net *net, float **params_dev, float **grads_dev)
+{
+    if (!net) { set_error("net is NULL"); return HP_ERR_INVALID; }
+    if (params_dev) *params_dev = net->n.params;
+    if (grads_dev) *grads_dev = net->n.grads;
+    net->n.tc_dirty = true;  // the caller may write the weights through this pointer
+    return HP_OK;
+}
+
+int hp_dp_unique_id(void *id128)
+{
+    if (!id128) { set_error("id128 is NULL"); return HP_ERR_INVALID; }
+    if (int rc = nccl_bind()) return rc;
+    HP_NCCL_TRY(g_nccl.GetUniqueId(id128));
+    return HP_OK;
+}
+
+int hp_dp_init(hp_net *net, const void *id128, int rank, int world)
+{
+    if (!net || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = nccl_bind()) return rc;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    Id128 id;
+    memcpy(id.b, id128, 128);
+    HP_NCCL_TRY(g_nccl.CommInitRank(&N.nccl_comm, world, id, rank));
+    N.rank = rank;
+    N.world = world;
+    return HP_OK;
+}
+
+int hp_dp_shutdown(hp_net *net)
+{
+    if (!net) return HP_OK;
+    Net &N = net->n;
+    if (N.nccl_comm) {
+        cudaSetDevice(N.device);
+        cudaDeviceSynchronize();
+        g_nccl.CommDestroy(N.nccl_comm);
+        N.nccl_comm = nullptr;
+    }
+    N.world = 1;
+    N.rank = 0;
+    return HP_OK;
+}
+
+int64_t hp_launch_count(const hp_net *net) { return net ? net->n.launches : 0; }
+
+int hp_peek(hp_net *net, int which, int64_t n, float *out_host)
+{
+    if (!net || !out_host || n <= 0) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    if (n > N.ws.cap) { set_error("peek beyond workspace (%lld > %lld)", (long long)n, (long long)N.ws.cap); return HP_ERR_INVALID; }
+    const float *src = nullptr;
+    size_t len = 0;
+    switch (which) {
+    case 3: src = N.ws.p1; len = P1_N; break;
+    case 6: src = N.ws.p2; len = P2_N; break;
+    case 8: src = N.ws.h1; len = FC1_OUT; break;
+    case 9: src = N.ws.logits; len = N_OUT; break;
+    case 109: src = N.ws.dlog; len = N_OUT; break;
+    case 107: src = N.ws.da1; len = FC1_OUT; break;
+    case 106: src = N.ws.g2; len = P2_N; break;
+    case 103: src = N.ws.g1; len = P1_N; break;
+    default: set_error("unknown intermediate %d", which); return HP_ERR_INVALID;
+    }
+    HP_CUDA_TRY(cudaMemcpy(out_host, src, (size_t)n * len * sizeof(float), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+const char *hp_last_error(void) { return g_err; }
+const char *hp_version(void) { return "handposedd-b200 0.1 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// hp_common.cuh -- geometry of the handposedd net, the device weight store and
+// the per-net workspace shared by the FP32 and tensor-core kernel files.
+//
+// Reference: IntelRealSense/hand_tracking_samples include/handtrack.h:108-118
+// (layer list) and third_party/cnn.h (layer arithmetic).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace hp {
+
+// ---- geometry (include/handtrack.h:108-118) --------------------------------
+constexpr int IN_W = 64, IN_H = 64, N_IN = 4096;
+constexpr int C1_K = 5, C1_CO = 16, C1_W = 60, C1_H = 60;
+constexpr int P1_W = 15, P1_H = 15, P1_N = C1_CO * P1_W * P1_H;   // 3600: after the two 2x2 pools
+constexpr int C2_K = 4, C2_CI = 16, C2_CO = 64, C2_W = 12, C2_H = 12, C2_POS = C2_W * C2_H;  // 144
+constexpr int C2_KDIM = C2_CI * C2_K * C2_K;                      // 256
+constexpr int P2_W = 6, P2_H = 6, P2_N = C2_CO * P2_W * P2_H;     // 2304
+constexpr int FC1_IN = 2304, FC1_OUT = 2048, FC2_IN = 2048, FC2_OUT = 2304;
+constexpr int N_OUT = 2304;
+constexpr int N_BIG_SPANS = 8, BIG_SPAN = 256, N_SMALL_SPANS = 16, SMALL_SPAN = 16;
+
+// ---- .cnnb float offsets (cnn.h:97-98,288-289,454-455,590-593) --------------
+constexpr int OFF_C1W = 0;
+constexpr int OFF_C1B = 400;
+constexpr int OFF_C2W = 416;
+constexpr int OFF_C2B = 16800;
+constexpr int OFF_F1W = 16864;
+constexpr int OFF_F1B = 4735456;
+constexpr int OFF_F2W = 4737504;
+constexpr int OFF_F2B = 9456096;
+constexpr int N_PARAMS = 9458400;
+
+// ---- workspace: activations kept between forward and backward ---------------
+struct Workspace {
+    int64_t cap = 0;          // crops this workspace can hold
+    // forward (FP32 path; CHW planar like the reference unless noted)
+    float *p1 = nullptr;      // [cap][16][15][15] tanh(conv1) after both pools
+    uint8_t *idx1 = nullptr;  // [cap][3600] winning offset oy*4+ox inside the 4x4 window (hierarchical tie-break)
+    float *col = nullptr;     // [cap*144][256] im2col of p1, k = (ci,ky,kx)
+    float *c2 = nullptr;      // [cap*144][64] conv2 pre-activation; reused as dense dL/dc2 in backward
+    float *p2 = nullptr;      // [cap][2304] tanh(conv2) pooled, index x + 6*y + 36*c (the reference's flatten)
+    uint8_t *idx2 = nullptr;  // [cap][2304] winning offset oy*2+ox inside the 2x2 window
+    float *h1 = nullptr;      // [cap][2048] tanh(fc1)
+    float *logits = nullptr;  // [cap][2304]
+    float *y = nullptr;       // [cap][2304] softmax output (training forward)
+    // backward
+    float *dlog = nullptr;    // [cap][2304] dL/dlogits
+    float *da1 = nullptr;     // [cap][2048] dL/d(fc1 pre-activation)
+    float *g2 = nullptr;      // [cap][2304] dL/d(conv2 pre-activation) at the pool winners
+    float *colgrad = nullptr; // [cap*144][256]
+    float *g1 = nullptr;      // [cap][3600] dL/d(conv1 pre-activation) at the pool winners
+    float *partial = nullptr; // split-K / column-sum partials
+    size_t partial_floats = 0;
+    // tensor-core path (bf16 activations)
+    __nv_bfloat16 *p2_bf = nullptr;  // [cap][2304]
+    __nv_bfloat16 *h1_bf = nullptr;  // [cap][2048]
+};
+
+// error plumbing (hp_api.cu)
+void set_error(const char *fmt, ...);
+#define HP_CUDA_TRY(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            hp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                          __LINE__);                                                        \
+            return 3; /* HP_ERR_CUDA */                                                     \
+        }                                                                                   \
+    } while (0)
+
+// TanH::f, cnn.h:31: (exp(2t)-1)/(exp(2t)+1) -- NOT tanhf: NaN above ~44.4 and
+// cancellation near 0 are part of the reference's results (SURVEY.md 8a note 2).
+__device__ __forceinline__ float tanh_ref(float t)
+{
+    float e = expf(2.0f * t);
+    return (e - 1.0f) / (e + 1.0f);
+}
+// std::max(a,b) == (a<b)?b:a (cnn.h:146): only differs from fmaxf for NaN.
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+
+// ---- FP32 path launchers (hp_fp32.cu); all return an hp_status ---------------
+struct Net;
+int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool training, cudaStream_t s);
+int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *mse, bool accumulate,
+                  cudaStream_t s);
+int sgd_apply(Net &net, float alpha, cudaStream_t s);
+// ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
+int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);
+int tc_refresh_weights(Net &net, cudaStream_t s);
+int tc_init(Net &net);
+void tc_destroy(Net &net);
+
+struct TcState;  // opaque: tensor maps + bf16 shadow weights (hp_tc.cu)
+
+struct Net {
+    int refcount = 1;
+    int device = 0;
+    cudaStream_t stream = nullptr;        // internal stream for the HOST-buffer entry points
+    cudaStream_t comm_stream = nullptr;   // gradient all-reduce stream (H2D copy stream of the host-buffer Eval)
+    cudaStream_t d2h_stream = nullptr;    // D2H copy stream of the host-buffer Eval
+    float *params = nullptr;              // FP32 master weights, .cnnb order
+    float *grads = nullptr;               // FP32 gradient sums, .cnnb order
+    Workspace ws;
+    TcState *tc = nullptr;
+    bool tc_dirty = true;                 // bf16 shadows stale w.r.t. params
+    // pinned staging for HOST entry points
+    float *pin_in[2] = {nullptr, nullptr};
+    float *pin_out[2] = {nullptr, nullptr};
+    float *dev_in[2] = {nullptr, nullptr};
+    float *dev_out[2] = {nullptr, nullptr};
+    float *dev_t = nullptr, *dev_mse = nullptr;
+    int64_t stage_cap = 0, pin_in_cap = 0, pin_out_cap = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_bucket[3] = {nullptr, nullptr, nullptr},
+                ev_comm = nullptr;
+    // data parallelism
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    int64_t launches = 0;
+    int64_t last_n = 0;
+};
+
+int ensure_workspace(Net &net, int64_t n);
+
+}  // namespace hp

@@ -1,0 +1,656 @@
+// hp_fp32.cu -- the FP32 (FFMA) variant of the handposedd hot path: the "exact
+// comparison" arm of BASELINE.json's north_star.  Same arithmetic as the
+// reference's third_party/cnn.h (bias first, then products accumulated in
+// ascending-k order, the reference's exp-based tanh, unshifted softmax, first
+// strict maximum in the pools) with FMA contraction as the only deliberate
+// difference; parity bound 1e-5 max-normalised (tests/test_gpu_parity.py).
+//
+// Kernels
+//   conv1_fwd_fp32      LConv 5x5 (cnn.h:205) + TanH (cnn.h:31,460) + 2x LMaxPool (cnn.h:141), fused
+//   im2col_p1 + sgemm   LConv 4x4 16->64 (cnn.h:205) as [n*144 x 256] x [256 x 64]
+//   tanh_pool2          TanH + LMaxPool (cnn.h:141)
+//   sgemm<..>           LFull forward / backward / update contractions (cnn.h:405,430,438)
+//   softmax_*           LSoftMaxChunked forward/backward (cnn.h:497,512) + Train's loss (cnn.h:566-569)
+//   scatter_e2, col2im_g1, conv1_wgrad   LMaxPool::backward (cnn.h:149), TanH::df (cnn.h:32),
+//                       LConv::backward / update (cnn.h:258,269)
+//   sgd_kernel          the W -= alpha*g epilogue of every update()
+#include "hp_common.cuh"
+
+namespace hp {
+
+#define LAUNCH_CHECK(net)                                   \
+    do {                                                    \
+        (net).launches++;                                   \
+        HP_CUDA_TRY(cudaGetLastError());                    \
+    } while (0)
+
+// ============================================================================
+// conv1 5x5 (1->16) + tanh + pool 2x2 + pool 2x2, one crop per CTA.
+// Thread p < 225 owns one pooled pixel: it holds the 8x8 input patch in
+// registers and produces the 4x4 window of conv outputs for each channel.
+// tanh is applied to all 16 window values BEFORE the pools (the reference's
+// order) so that the hierarchical first-strict-maximum tie-break of two stacked
+// LMaxPool::backward calls (cnn.h:157-161) is evaluated on post-tanh values.
+// ============================================================================
+__device__ __forceinline__ void pool4(float a00, float a10, float a01, float a11, float &val, int &arg)
+{
+    // forward value: cnn.h:146 chain; winner: cnn.h:157-161 (first strict max, scan (0,0),(1,0),(0,1),(1,1))
+    val = std_max(std_max(std_max(a00, a10), a01), a11);
+    float cur = a00;
+    arg = 0;
+    if (a10 > cur) { cur = a10; arg = 1; }
+    if (a01 > cur) { cur = a01; arg = 2; }
+    if (a11 > cur) { cur = a11; arg = 3; }
+}
+
+__global__ void __launch_bounds__(256) conv1_fwd_fp32(const float *__restrict__ x, const float *__restrict__ params,
+                                                      float *__restrict__ p1, uint8_t *__restrict__ idx1)
+{
+    __shared__ __align__(16) float img[N_IN];
+    __shared__ float w[400];
+    __shared__ float b[16];
+    const int64_t crop = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float4 *src = reinterpret_cast<const float4 *>(x + crop * N_IN);
+#pragma unroll
+    for (int i = 0; i < 4; i++) reinterpret_cast<float4 *>(img)[tid + 256 * i] = src[tid + 256 * i];
+    for (int i = tid; i < 400; i += 256) w[i] = params[OFF_C1W + i];
+    if (tid < 16) b[tid] = params[OFF_C1B + tid];
+    __syncthreads();
+    if (tid >= P1_W * P1_H) return;
+    const int py = tid / P1_W, px = tid % P1_W;
+
+    float patch[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        float4 lo = *reinterpret_cast<const float4 *>(&img[(4 * py + r) * IN_W + 4 * px]);
+        float4 hi = *reinterpret_cast<const float4 *>(&img[(4 * py + r) * IN_W + 4 * px + 4]);
+        patch[r][0] = lo.x; patch[r][1] = lo.y; patch[r][2] = lo.z; patch[r][3] = lo.w;
+        patch[r][4] = hi.x; patch[r][5] = hi.y; patch[r][6] = hi.z; patch[r][7] = hi.w;
+    }
+    for (int co = 0; co < C1_CO; co++) {
+        float acc[4][4];
+        const float bias = b[co];
+#pragma unroll
+        for (int oy = 0; oy < 4; oy++)
+#pragma unroll
+            for (int ox = 0; ox < 4; ox++) acc[oy][ox] = bias;
+        // reference accumulation order: ky outer, kx inner (cnn.h:223)
+#pragma unroll
+        for (int ky = 0; ky < 5; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 5; kx++) {
+                const float wv = w[co * 25 + ky * 5 + kx];
+#pragma unroll
+                for (int oy = 0; oy < 4; oy++)
+#pragma unroll
+                    for (int ox = 0; ox < 4; ox++) acc[oy][ox] = fmaf(patch[oy + ky][ox + kx], wv, acc[oy][ox]);
+            }
+#pragma unroll
+        for (int oy = 0; oy < 4; oy++)
+#pragma unroll
+            for (int ox = 0; ox < 4; ox++) acc[oy][ox] = tanh_ref(acc[oy][ox]);
+        float v[4];
+        int a[4];
+#pragma unroll
+        for (int by = 0; by < 2; by++)
+#pragma unroll
+            for (int bx = 0; bx < 2; bx++)
+                pool4(acc[2 * by][2 * bx], acc[2 * by][2 * bx + 1], acc[2 * by + 1][2 * bx], acc[2 * by + 1][2 * bx + 1],
+                      v[by * 2 + bx], a[by * 2 + bx]);
+        float val;
+        int blk;
+        pool4(v[0], v[1], v[2], v[3], val, blk);
+        const int sub = a[blk];
+        const int oy = 2 * (blk >> 1) + (sub >> 1), ox = 2 * (blk & 1) + (sub & 1);
+        p1[crop * P1_N + co * (P1_W * P1_H) + tid] = val;
+        idx1[crop * P1_N + co * (P1_W * P1_H) + tid] = (uint8_t)(oy * 4 + ox);
+    }
+}
+
+// im2col of the pooled conv1 stage: col[(n*144+pos)][k], k = ci*16 + ky*4 + kx.
+__global__ void __launch_bounds__(256) im2col_p1(const float *__restrict__ p1, float *__restrict__ col)
+{
+    __shared__ float s[P1_N];
+    const int64_t crop = blockIdx.x;
+    for (int i = threadIdx.x; i < P1_N; i += 256) s[i] = p1[crop * P1_N + i];
+    __syncthreads();
+    float *dst = col + crop * (int64_t)(C2_POS * C2_KDIM);
+    for (int e = threadIdx.x; e < C2_POS * C2_KDIM; e += 256) {
+        const int pos = e >> 8, k = e & 255;
+        const int ci = k >> 4, ky = (k >> 2) & 3, kx = k & 3;
+        const int y = pos / C2_W, xx = pos % C2_W;
+        dst[e] = s[ci * (P1_W * P1_H) + (y + ky) * P1_W + xx + kx];
+    }
+}
+
+// tanh + 2x2 max-pool of conv2's pre-activations c2[(n*144+pos)][co]; writes the
+// reference's CHW flatten p2[n][x + 6y + 36c] and the winner offset.
+__global__ void __launch_bounds__(256) tanh_pool2(const float *__restrict__ c2, float *__restrict__ p2,
+                                                  uint8_t *__restrict__ idx2)
+{
+    __shared__ float sv[P2_N];
+    __shared__ uint8_t si[P2_N];
+    const int64_t crop = blockIdx.x;
+    const float *src = c2 + crop * (int64_t)(C2_POS * C2_CO);
+    for (int e = threadIdx.x; e < P2_N; e += 256) {
+        const int co = e & 63, pp = e >> 6;
+        const int py = pp / P2_W, px = pp % P2_W;
+        const int base = ((2 * py) * C2_W + 2 * px) * C2_CO + co;
+        float a00 = tanh_ref(src[base]);
+        float a10 = tanh_ref(src[base + C2_CO]);
+        float a01 = tanh_ref(src[base + C2_W * C2_CO]);
+        float a11 = tanh_ref(src[base + C2_W * C2_CO + C2_CO]);
+        float val;
+        int arg;
+        pool4(a00, a10, a01, a11, val, arg);
+        sv[co * 36 + pp] = val;
+        si[co * 36 + pp] = (uint8_t)arg;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < P2_N; e += 256) {
+        p2[crop * P2_N + e] = sv[e];
+        idx2[crop * P2_N + e] = si[e];
+    }
+}
+
+// ============================================================================
+// SGEMM  C[M x N] = A[M x K] * B[K x N]  (+ epilogue), FFMA, ascending-k sums.
+// 128 x BN x 16 tiles, 256 threads, 8 x (BN/16) register tile, double-buffered
+// shared memory with register prefetch.
+//   A_KC: A stored [M][K] (k contiguous)   else [K][M] (m contiguous)
+//   B_KC: B stored [N][K] (k contiguous)   else [K][N] (n contiguous)
+// ============================================================================
+enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_TANH = 2, EPI_DTANH = 3 };
+
+struct GemmArgs {
+    int M, N, K;
+    const float *A; int lda;
+    const float *B; int ldb;
+    float *C; int ldc;
+    const float *bias;   // EPI_BIAS*: accumulators start at bias[n] (LFull::forward: Y = B, cnn.h:407)
+    const float *H;      // EPI_DTANH: C = (1 - H*H) * acc (TanH::df on the layer OUTPUT, cnn.h:32,467)
+    int klen;            // split-K: block z handles k in [z*klen, min(K,(z+1)*klen)) and writes C + z*M*ldc
+    int accumulate;      // EPI_STORE: C += acc
+};
+
+template <int BN, bool A_KC, bool B_KC, int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g)
+{
+    constexpr int BM = 128, BK = 16, PAD = 4;
+    constexpr int TN = BN / 16;  // 8 or 4 columns per thread
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * g.klen;
+    const int kend = min(g.K, kbeg + g.klen);
+    float *C = g.C + (size_t)blockIdx.z * g.M * g.ldc;
+
+    float acc[8][TN];
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+        float bv = 0.f;
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_TANH) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4));
+            bv = (n < g.N) ? g.bias[n] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i][j] = bv;
+    }
+
+    float4 ra[2], rb[2];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int q = tid + 256 * r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A_KC) {
+                const int m = q >> 2, kq = q & 3;
+                if (m0 + m < g.M && k0 + kq * 4 < kend) v = *reinterpret_cast<const float4 *>(g.A + (size_t)(m0 + m) * g.lda + k0 + kq * 4);
+            } else {
+                const int k = q >> 5, mq = q & 31;
+                if (k0 + k < kend && m0 + mq * 4 < g.M) v = *reinterpret_cast<const float4 *>(g.A + (size_t)(k0 + k) * g.lda + m0 + mq * 4);
+            }
+            ra[r] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < (BN == 128 ? 2 : 1); r++) {
+            const int q = tid + 256 * r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (B_KC) {
+                const int n = q >> 2, kq = q & 3;
+                if (n0 + n < g.N && k0 + kq * 4 < kend) v = *reinterpret_cast<const float4 *>(g.B + (size_t)(n0 + n) * g.ldb + k0 + kq * 4);
+            } else {
+                const int k = q / (BN / 4), nq = q % (BN / 4);
+                if (k0 + k < kend && n0 + nq * 4 < g.N) v = *reinterpret_cast<const float4 *>(g.B + (size_t)(k0 + k) * g.ldb + n0 + nq * 4);
+            }
+            rb[r] = v;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int q = tid + 256 * r;
+            if (A_KC) {
+                const int m = q >> 2, kq = q & 3;
+                As[buf][kq * 4 + 0][m] = ra[r].x; As[buf][kq * 4 + 1][m] = ra[r].y;
+                As[buf][kq * 4 + 2][m] = ra[r].z; As[buf][kq * 4 + 3][m] = ra[r].w;
+            } else {
+                const int k = q >> 5, mq = q & 31;
+                *reinterpret_cast<float4 *>(&As[buf][k][mq * 4]) = ra[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < (BN == 128 ? 2 : 1); r++) {
+            const int q = tid + 256 * r;
+            if (B_KC) {
+                const int n = q >> 2, kq = q & 3;
+                Bs[buf][kq * 4 + 0][n] = rb[r].x; Bs[buf][kq * 4 + 1][n] = rb[r].y;
+                Bs[buf][kq * 4 + 2][n] = rb[r].z; Bs[buf][kq * 4 + 3][n] = rb[r].w;
+            } else {
+                const int k = q / (BN / 4), nq = q % (BN / 4);
+                *reinterpret_cast<float4 *>(&Bs[buf][k][nq * 4]) = rb[r];
+            }
+        }
+    };
+
+    const int nk = (kend - kbeg + BK - 1) / BK;
+    if (nk > 0) {
+        gload(kbeg);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int it = 0; it < nk; it++) {
+        const int buf = it & 1;
+        if (it + 1 < nk) gload(kbeg + (it + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float a[8], b[TN];
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][64 + ty * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+            if (TN == 8) {
+                const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][BN / 2 + tx * 4]);
+                b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (it + 1 < nk) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int h = 0; h < TN / 4; h++) {
+            const int n = n0 + (h == 0 ? tx * 4 : BN / 2 + tx * 4);
+            if (n >= g.N) continue;
+            float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+            float *cp = C + (size_t)m * g.ldc + n;
+            if (EPI == EPI_BIAS_TANH) {
+                v.x = tanh_ref(v.x); v.y = tanh_ref(v.y); v.z = tanh_ref(v.z); v.w = tanh_ref(v.w);
+            } else if (EPI == EPI_DTANH) {
+                const float4 hv = *reinterpret_cast<const float4 *>(g.H + (size_t)m * g.ldc + n);
+                v.x = (1.0f - hv.x * hv.x) * v.x; v.y = (1.0f - hv.y * hv.y) * v.y;
+                v.z = (1.0f - hv.z * hv.z) * v.z; v.w = (1.0f - hv.w * hv.w) * v.w;
+            } else if (EPI == EPI_STORE && g.accumulate) {
+                const float4 o = *reinterpret_cast<const float4 *>(cp);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *reinterpret_cast<float4 *>(cp) = v;
+        }
+    }
+}
+
+template <int BN, bool A_KC, bool B_KC, int EPI>
+static int launch_sgemm(Net &net, const GemmArgs &g, int splits, cudaStream_t s)
+{
+    dim3 grid((g.N + BN - 1) / BN, (g.M + 127) / 128, splits);
+    sgemm_kernel<BN, A_KC, B_KC, EPI><<<grid, 256, 0, s>>>(g);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// dst[i] (+)= sum_s src[s*len + i], s ascending (deterministic).
+__global__ void reduce_partials(float *__restrict__ dst, const float *__restrict__ src, int S, int len, int accumulate)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    float a = accumulate ? dst[i] : 0.f;
+    for (int s = 0; s < S; s++) a += src[(size_t)s * len + i];
+    dst[i] = a;
+}
+
+// column sums of in[R][ncols] over a row slice: partial[gy][col]
+__global__ void __launch_bounds__(256) colsum_partial(const float *__restrict__ in, int64_t R, int ncols, float *__restrict__ partial)
+{
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    float a = 0.f;
+    if (col < ncols)
+        for (int64_t r = (int64_t)blockIdx.y * 8 + ry; r < R; r += (int64_t)gridDim.y * 8) a += in[r * ncols + col];
+    sm[ry][cx] = a;
+    __syncthreads();
+    if (ry == 0 && col < ncols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += sm[k][cx];
+        partial[(size_t)blockIdx.y * ncols + col] = t;
+    }
+}
+
+// ============================================================================
+// LSoftMaxChunked (cnn.h:497-526) + the loss of CNN::Train (cnn.h:566-569).
+// One CTA per crop: warp w reduces big span w (256 wide); the 16 small spans
+// (16 wide) are reduced inside 16-lane groups.  No max-subtraction, as in the
+// reference (overflows above 88.7 just like it).
+// ============================================================================
+template <bool TRAIN>
+__global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ logits, float *__restrict__ y,
+                                                      const float *__restrict__ t, float *__restrict__ dlog,
+                                                      float *__restrict__ mse)
+{
+    const int64_t crop = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *lg = logits + crop * N_OUT;
+    float ev[8], es;
+    // big span `warp`
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        ev[i] = expf(lg[warp * 256 + i * 32 + lane]);
+        sum += ev[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+    for (int i = 0; i < 8; i++) ev[i] = ev[i] / sum;
+    // small spans: element 2048 + tid, span = tid / 16
+    es = expf(lg[2048 + tid]);
+    float ssum = es;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    es = es / ssum;
+
+    if (y) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[crop * N_OUT + warp * 256 + i * 32 + lane] = ev[i];
+        y[crop * N_OUT + 2048 + tid] = es;
+    }
+    if (TRAIN) {
+        __shared__ float red[8];
+        const float *tt = t + crop * N_OUT;
+        float e[8], se = 0.f, dp = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            e[i] = ev[i] - tt[warp * 256 + i * 32 + lane];  // e = y - t (cnn.h:568)
+            se += e[i] * e[i];
+            dp += e[i] * ev[i];                             // cnn.h:519-520
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, o);
+#pragma unroll
+        for (int i = 0; i < 8; i++) dlog[crop * N_OUT + warp * 256 + i * 32 + lane] = ev[i] * (e[i] - dp);  // cnn.h:522
+        const float e2 = es - tt[2048 + tid];
+        se += e2 * e2;
+        float dp2 = e2 * es;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) dp2 += __shfl_xor_sync(0xffffffffu, dp2, o);
+        dlog[crop * N_OUT + 2048 + tid] = es * (e2 - dp2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        if (lane == 0) red[warp] = se;
+        __syncthreads();
+        if (tid == 0 && mse) {
+            float m = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) m += red[k];
+            mse[crop] = m / (float)N_OUT;  // cnn.h:569
+        }
+    }
+}
+
+// LMaxPool::backward (cnn.h:149-164) after TanH::df was folded into g2 by the fc1
+// dX epilogue: dense dL/dc2[(n*144+pos)][co] = g2 at the winner, 0 elsewhere.
+__global__ void __launch_bounds__(256) scatter_e2(const float *__restrict__ g2, const uint8_t *__restrict__ idx2,
+                                                  float *__restrict__ e2)
+{
+    __shared__ float sg[P2_N];
+    __shared__ uint8_t si[P2_N];
+    const int64_t crop = blockIdx.x;
+    for (int e = threadIdx.x; e < P2_N; e += 256) {
+        sg[e] = g2[crop * P2_N + e];
+        si[e] = idx2[crop * P2_N + e];
+    }
+    __syncthreads();
+    float *dst = e2 + crop * (int64_t)(C2_POS * C2_CO);
+    for (int e = threadIdx.x; e < C2_POS * C2_CO; e += 256) {
+        const int co = e & 63, pos = e >> 6;
+        const int y = pos / C2_W, xx = pos % C2_W;
+        const int pp = (y >> 1) * P2_W + (xx >> 1), off = (y & 1) * 2 + (xx & 1);
+        const int j = co * 36 + pp;
+        dst[e] = (si[j] == off) ? sg[j] : 0.f;
+    }
+}
+
+// col2im of dL/dcol (LConv::backward, cnn.h:258-268, as a gather) fused with the
+// two LMaxPool::backward + TanH::df of the conv1 stage: only the pool winners
+// carry gradient, so g1[n][ci][Y][X] = (1 - p1^2) * dL/dp1.
+__global__ void __launch_bounds__(256) col2im_g1(const float *__restrict__ colgrad, const float *__restrict__ p1,
+                                                 float *__restrict__ g1)
+{
+    const int64_t crop = blockIdx.x;
+    const float *cg = colgrad + crop * (int64_t)(C2_POS * C2_KDIM);
+    for (int e = threadIdx.x; e < P1_N; e += 256) {
+        const int ci = e / (P1_W * P1_H), r = e % (P1_W * P1_H);
+        const int Y = r / P1_W, X = r % P1_W;
+        float a = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 4; ky++) {
+            const int y = Y - ky;
+            if (y < 0 || y >= C2_H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; kx++) {
+                const int xx = X - kx;
+                if (xx < 0 || xx >= C2_W) continue;
+                a += cg[(y * C2_W + xx) * C2_KDIM + ci * 16 + ky * 4 + kx];
+            }
+        }
+        const float pv = p1[crop * P1_N + e];
+        g1[crop * P1_N + e] = (1.0f - pv * pv) * a;
+    }
+}
+
+// LConv::update for conv1 (cnn.h:269-279) restricted to the pool winners: every
+// other conv1 output has exactly zero gradient.  partial[block][co*25+tap],
+// partial[block][400+co] (bias); thread = (co, 16 sub-lanes over pooled pixels).
+__global__ void __launch_bounds__(256) conv1_wgrad(const float *__restrict__ x, const float *__restrict__ g1,
+                                                   const uint8_t *__restrict__ idx1, int64_t n, int per_block,
+                                                   float *__restrict__ partial)
+{
+    __shared__ __align__(16) float img[N_IN];
+    const int tid = threadIdx.x, co = tid >> 4, sub = tid & 15;
+    float acc[26];
+#pragma unroll
+    for (int k = 0; k < 26; k++) acc[k] = 0.f;
+    const int64_t b0 = (int64_t)blockIdx.x * per_block;
+    const int64_t b1 = (b0 + per_block < n) ? b0 + per_block : n;
+    for (int64_t crop = b0; crop < b1; crop++) {
+        __syncthreads();
+        const float4 *src = reinterpret_cast<const float4 *>(x + crop * N_IN);
+#pragma unroll
+        for (int i = 0; i < 4; i++) reinterpret_cast<float4 *>(img)[tid + 256 * i] = src[tid + 256 * i];
+        __syncthreads();
+        for (int pp = sub; pp < P1_W * P1_H; pp += 16) {
+            const float g = g1[crop * P1_N + co * 225 + pp];
+            const int id = idx1[crop * P1_N + co * 225 + pp];
+            const int py = pp / P1_W, px = pp % P1_W;
+            const float *ip = img + (4 * py + (id >> 2)) * IN_W + 4 * px + (id & 3);
+#pragma unroll
+            for (int ky = 0; ky < 5; ky++)
+#pragma unroll
+                for (int kx = 0; kx < 5; kx++) acc[ky * 5 + kx] = fmaf(ip[ky * IN_W + kx], g, acc[ky * 5 + kx]);
+            acc[25] += g;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 26; k++) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[k] = v;
+    }
+    if (sub == 0) {
+        float *dst = partial + (size_t)blockIdx.x * 416;
+#pragma unroll
+        for (int k = 0; k < 25; k++) dst[co * 25 + k] = acc[k];
+        dst[400 + co] = acc[25];
+    }
+}
+
+// W <- W - alpha * g over the flat .cnnb-ordered stores.
+__global__ void __launch_bounds__(256) sgd_kernel(float4 *__restrict__ p, const float4 *__restrict__ g, float alpha, int n4)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 w = p[i];
+        const float4 d = g[i];
+        w.x = fmaf(-alpha, d.x, w.x); w.y = fmaf(-alpha, d.y, w.y);
+        w.z = fmaf(-alpha, d.z, w.z); w.w = fmaf(-alpha, d.w, w.w);
+        p[i] = w;
+    }
+}
+
+// ============================================================================
+// host-side chains
+// ============================================================================
+int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool training, cudaStream_t s)
+{
+    Workspace &w = net.ws;
+    const float *P = net.params;
+    conv1_fwd_fp32<<<(unsigned)n, 256, 0, s>>>(x, P, w.p1, w.idx1);
+    LAUNCH_CHECK(net);
+    im2col_p1<<<(unsigned)n, 256, 0, s>>>(w.p1, w.col);
+    LAUNCH_CHECK(net);
+    {   // conv2: [n*144 x 256] x W2[64][256]^T + bias
+        GemmArgs g{(int)(n * C2_POS), C2_CO, C2_KDIM, w.col, C2_KDIM, P + OFF_C2W, C2_KDIM, w.c2, C2_CO, P + OFF_C2B, nullptr, C2_KDIM, 0};
+        if (int rc = launch_sgemm<64, true, true, EPI_BIAS>(net, g, 1, s)) return rc;
+    }
+    tanh_pool2<<<(unsigned)n, 256, 0, s>>>(w.c2, w.p2, w.idx2);
+    LAUNCH_CHECK(net);
+    {   // fc1 + tanh
+        GemmArgs g{(int)n, FC1_OUT, FC1_IN, w.p2, FC1_IN, P + OFF_F1W, FC1_OUT, w.h1, FC1_OUT, P + OFF_F1B, nullptr, FC1_IN, 0};
+        if (int rc = launch_sgemm<128, true, false, EPI_BIAS_TANH>(net, g, 1, s)) return rc;
+    }
+    {   // fc2 logits
+        GemmArgs g{(int)n, FC2_OUT, FC2_IN, w.h1, FC2_IN, P + OFF_F2W, FC2_OUT, w.logits, FC2_OUT, P + OFF_F2B, nullptr, FC2_IN, 0};
+        if (int rc = launch_sgemm<128, true, false, EPI_BIAS>(net, g, 1, s)) return rc;
+    }
+    if (!training) {
+        softmax_kernel<false><<<(unsigned)n, 256, 0, s>>>(w.logits, y_out, nullptr, nullptr, nullptr);
+        LAUNCH_CHECK(net);
+    }
+    return 0;
+}
+
+static int colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, bool accumulate, cudaStream_t s)
+{
+    int gy = (int)((R + 63) / 64);
+    if (gy > 64) gy = 64;
+    if (gy < 1) gy = 1;
+    dim3 grid((ncols + 31) / 32, gy);
+    colsum_partial<<<grid, 256, 0, s>>>(in, R, ncols, net.ws.partial);
+    LAUNCH_CHECK(net);
+    reduce_partials<<<(ncols + 255) / 256, 256, 0, s>>>(dst, net.ws.partial, gy, ncols, accumulate ? 1 : 0);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// Backward + weight-gradient sums into net.grads (W -= alpha*grads is sgd_apply).
+// Order fc2 -> fc1 -> conv2 -> conv1 so that the large FC buckets are ready first
+// for the data-parallel all-reduce (events ev_bucket[0..2]).
+int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *mse, bool accumulate, cudaStream_t s)
+{
+    Workspace &w = net.ws;
+    const float *P = net.params;
+    float *G = net.grads;
+    const int acc = accumulate ? 1 : 0;
+    softmax_kernel<true><<<(unsigned)n, 256, 0, s>>>(w.logits, w.y, t, w.dlog, mse);
+    LAUNCH_CHECK(net);
+    // ---- fc2: dB, dW = h1^T * dlog, dX = dlog * W2^T with tanh' of fc1's output
+    if (int rc = colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
+    {
+        GemmArgs g{FC2_IN, FC2_OUT, (int)n, w.h1, FC2_IN, w.dlog, FC2_OUT, G + OFF_F2W, FC2_OUT, nullptr, nullptr, (int)n, acc};
+        if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, 1, s)) return rc;
+    }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
+    {
+        GemmArgs g{(int)n, FC2_IN, FC2_OUT, w.dlog, FC2_OUT, P + OFF_F2W, FC2_OUT, w.da1, FC2_IN, nullptr, w.h1, FC2_OUT, 0};
+        if (int rc = launch_sgemm<128, true, true, EPI_DTANH>(net, g, 1, s)) return rc;
+    }
+    // ---- fc1
+    if (int rc = colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
+    {
+        GemmArgs g{FC1_IN, FC1_OUT, (int)n, w.p2, FC1_IN, w.da1, FC1_OUT, G + OFF_F1W, FC1_OUT, nullptr, nullptr, (int)n, acc};
+        if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, 1, s)) return rc;
+    }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
+    {
+        GemmArgs g{(int)n, FC1_IN, FC1_OUT, w.da1, FC1_OUT, P + OFF_F1W, FC1_OUT, w.g2, FC1_IN, nullptr, w.p2, FC1_OUT, 0};
+        if (int rc = launch_sgemm<128, true, true, EPI_DTANH>(net, g, 1, s)) return rc;
+    }
+    // ---- conv2: dense dL/dc2 (reuses w.c2), dB, dW (split-K over positions), dcol
+    scatter_e2<<<(unsigned)n, 256, 0, s>>>(w.g2, w.idx2, w.c2);
+    LAUNCH_CHECK(net);
+    const int64_t R = n * C2_POS;
+    if (int rc = colsum(net, w.c2, R, C2_CO, G + OFF_C2B, accumulate, s)) return rc;
+    {
+        int splits = (int)((R + 1151) / 1152);  // 8 crops per split
+        if (splits > 128) splits = 128;
+        int klen = (int)((R + splits - 1) / splits);
+        klen = (klen + 15) / 16 * 16;
+        splits = (int)((R + klen - 1) / klen);
+        GemmArgs g{C2_CO, C2_KDIM, (int)R, w.c2, C2_CO, w.col, C2_KDIM, w.partial, C2_KDIM, nullptr, nullptr, klen, 0};
+        if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, splits, s)) return rc;
+        reduce_partials<<<(C2_CO * C2_KDIM + 255) / 256, 256, 0, s>>>(G + OFF_C2W, w.partial, splits, C2_CO * C2_KDIM, acc);
+        LAUNCH_CHECK(net);
+    }
+    {
+        GemmArgs g{(int)R, C2_KDIM, C2_CO, w.c2, C2_CO, P + OFF_C2W, C2_KDIM, w.colgrad, C2_KDIM, nullptr, nullptr, C2_CO, 0};
+        if (int rc = launch_sgemm<128, true, false, EPI_STORE>(net, g, 1, s)) return rc;
+    }
+    col2im_g1<<<(unsigned)n, 256, 0, s>>>(w.colgrad, w.p1, w.g1);
+    LAUNCH_CHECK(net);
+    // ---- conv1 (no dX: CNN::Train never calls layer 0's backward, cnn.h:571)
+    {
+        int per_block = (int)((n + 147) / 148);
+        if (per_block < 1) per_block = 1;
+        int blocks = (int)((n + per_block - 1) / per_block);
+        conv1_wgrad<<<blocks, 256, 0, s>>>(x, w.g1, w.idx1, n, per_block, w.partial);
+        LAUNCH_CHECK(net);
+        reduce_partials<<<2, 256, 0, s>>>(G + OFF_C1W, w.partial, blocks, 416, acc);
+        LAUNCH_CHECK(net);
+    }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));
+    return 0;
+}
+
+int sgd_apply(Net &net, float alpha, cudaStream_t s)
+{
+    sgd_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<float4 *>(net.params), reinterpret_cast<const float4 *>(net.grads), alpha,
+                                       N_PARAMS / 4);
+    LAUNCH_CHECK(net);
+    net.tc_dirty = true;
+    return 0;
+}
+
+}  // namespace hp

@@ -1,0 +1,184 @@
+/*
+ * handposedd.h -- C ABI of the B200-native replacement for the CNN hot path of
+ * IntelRealSense/hand_tracking_samples (third_party/cnn.h, instantiated by
+ * include/handtrack.h:103-130 as "handposedd").
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no
+ * C++/torch types.  The cnn.h-compatible C++ class (include/handposedd/cnn.h)
+ * and the Python mirror (hand_tracking_samples_b200/cnn.py) are thin callers of
+ * these entry points.  Each entry point names the reference interface it
+ * replaces.  There is no CPU fallback: every compute entry point fails with
+ * HP_ERR_NO_DEVICE when no sm_100 device is usable.
+ *
+ * Threading: one hp_net is used by one host thread at a time (the reference has
+ * at most one Eval in flight, include/handtrack.h:755); distinct nets are
+ * independent.  hp_retain/hp_destroy are atomic.
+ *
+ * Layouts at the boundary are the reference's own:
+ *   crops   x[n][4096]  float32, row-major 64x64, one channel (NHWC == NCHW),
+ *           values as produced by include/handtrack.h:700 (nominally [0,1]);
+ *   outputs y[n][2304]  float32: 8 heatmaps of 16x16 then 16 heatmaps of 16
+ *           (spans of LSoftMaxChunked, include/handtrack.h:118);
+ *   labels  t[n][2304]  float32 (GatherHandExpectedCNN, include/handtrack.h:160);
+ *   weights the headerless little-endian float32 .cnnb stream of
+ *           CNN::saveb (cnn.h:591,288-289,454-455): 9,458,400 floats.
+ */
+#ifndef HANDPOSEDD_H
+#define HANDPOSEDD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define HP_API
+#else
+#define HP_API __attribute__((visibility("default")))
+#endif
+
+typedef struct hp_net hp_net;
+
+enum hp_status {
+    HP_OK = 0,
+    HP_ERR_INVALID = 1,     /* bad argument */
+    HP_ERR_UNSUPPORTED = 2, /* layer list is not one this build has kernels for */
+    HP_ERR_CUDA = 3,        /* a CUDA call failed; see hp_last_error() */
+    HP_ERR_IO = 4,          /* file could not be opened / short buffer */
+    HP_ERR_NCCL = 5,        /* NCCL unavailable or failed */
+    HP_ERR_NO_DEVICE = 6    /* no usable sm_100 device: there is no CPU fallback */
+};
+
+/* Arithmetic of the contraction layers (conv + FC). */
+enum hp_precision {
+    HP_PRECISION_FP32 = 0,  /* FFMA, reference summation order; parity bound 1e-5 */
+    HP_PRECISION_TENSOR = 1 /* tcgen05 BF16 operands, FP32 accumulate in TMEM; parity bound 1e-2 */
+};
+
+/* Layer descriptors mirror the constructors client code calls on the
+ * reference (cnn.h:139,203,403,459,496). */
+enum hp_layer_kind {
+    HP_LAYER_CONV = 1,            /* CNN::LConv(int3 indims, int4 dims, int3 outdims)   cnn.h:203 */
+    HP_LAYER_TANH = 2,            /* CNN::LActivation<TanH>(int n)                       cnn.h:459 */
+    HP_LAYER_MAXPOOL = 3,         /* CNN::LMaxPool(int3 indims)                          cnn.h:139 */
+    HP_LAYER_FULL = 4,            /* CNN::LFull(int in, int out)                         cnn.h:403 */
+    HP_LAYER_SOFTMAX_CHUNKED = 5  /* CNN::LSoftMaxChunked(std::vector<int> spans)        cnn.h:496 */
+};
+typedef struct hp_layer_desc {
+    int kind;
+    int in_dims[3];   /* x, y, z (z = channels); FULL: {in,0,0}; TANH: {n,0,0} */
+    int w_dims[4];    /* CONV: kx, ky, cin, cout */
+    int out_dims[3];  /* CONV: x, y, cout; FULL: {out,0,0} */
+    int n_spans;      /* SOFTMAX_CHUNKED */
+    const int *spans; /* SOFTMAX_CHUNKED */
+} hp_layer_desc;
+
+#define HP_N_IN 4096
+#define HP_N_OUT 2304
+#define HP_N_PARAMS 9458400
+#define HP_CNNB_BYTES 37833600
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+/* Replaces: the layer-list construction of PoseInitializerCNN
+ * (include/handtrack.h:107-118).  Accepts exactly the handposedd list (the only
+ * instantiation in the reference); anything else -> HP_ERR_UNSUPPORTED.
+ * Weights start at zero (CNN ctor, cnn.h:203,403); call hp_init_xavier or
+ * hp_load_cnnb next, as PoseInitializerCNN does. */
+HP_API int hp_create(const hp_layer_desc *layers, int n_layers, int device, hp_net **out);
+/* Convenience: the handposedd list without spelling it out. */
+HP_API int hp_create_handposedd(int device, hp_net **out);
+/* Replaces: CNN's by-value (shallow) copy semantics (include/handtrack.h:129,
+ * train-hand-pose-cnn/train-cnn.cpp:116): copies share one device weight store. */
+HP_API int hp_retain(hp_net *net);
+HP_API int hp_destroy(hp_net *net);
+
+/* ---- weights ------------------------------------------------------------- */
+
+/* Replaces: CNN::Init (cnn.h:581-586): Xavier-uniform from one
+ * std::default_random_engine (libstdc++: minstd_rand0, default seed) shared
+ * across layers; biases 0.  Bit-identical to the reference under libstdc++. */
+HP_API int hp_init_xavier(hp_net *net);
+/* Replaces: CNN::loadb(std::istream&) (cnn.h:590).  Like the reference's
+ * loadvb (cnn.h:97), a short buffer fills a prefix and leaves the tail of the
+ * weights unmodified; n_bytes beyond HP_CNNB_BYTES are ignored. */
+HP_API int hp_load_cnnb(hp_net *net, const void *bytes, size_t n_bytes);
+/* Replaces: CNN::saveb(std::ostream&) (cnn.h:591).  *n_written = HP_CNNB_BYTES. */
+HP_API int hp_save_cnnb(const hp_net *net, void *bytes, size_t capacity, size_t *n_written);
+/* Replaces: CNN::loadb(std::string) / CNN::saveb(std::string) (cnn.h:592-593).
+ * hp_load_cnnb_file returns HP_ERR_IO if the file cannot be opened (the C++
+ * wrapper keeps the reference's silent no-op by ignoring that status). */
+HP_API int hp_load_cnnb_file(hp_net *net, const char *path);
+HP_API int hp_save_cnnb_file(const hp_net *net, const char *path);
+
+/* ---- inference ----------------------------------------------------------- */
+
+/* Replaces: CNN::Eval (cnn.h:550-556), batched.  HOST buffers: x[n][4096] ->
+ * y[n][2304]; uploads/downloads run through pinned staging buffers on an
+ * internal stream, chunked and overlapped with compute; returns when y is
+ * complete.  n == 0 is a no-op. */
+HP_API int hp_eval_batch(hp_net *net, const float *x, int64_t n, float *y, int precision);
+/* Same with DEVICE buffers on the caller's CUDA stream (cudaStream_t passed as
+ * void*; NULL = the legacy default stream); asynchronous with respect to the
+ * host. */
+HP_API int hp_eval_batch_device(hp_net *net, const float *x_dev, int64_t n, float *y_dev,
+                                int precision, void *stream);
+
+/* ---- training ------------------------------------------------------------ */
+
+/* Replaces: CNN::Train (cnn.h:558-580), batched.  One optimiser step on a
+ * minibatch: all n samples see the same (pre-update) weights, and
+ *     W <- W - alpha * sum_b g_b
+ * where g_b is exactly what the reference's `update` (cnn.h:269-279, 438-445)
+ * applies per unit alpha for sample b.  n == 1 is the reference's step.
+ * mse_out (optional) receives the n per-sample values Train returns
+ * (sum e^2 / 2304, cnn.h:566-569).  HOST buffers. */
+HP_API int hp_train_batch(hp_net *net, const float *x, const float *t, int64_t n, float alpha,
+                          float *mse_out, int precision);
+/* DEVICE buffers, caller's stream.  With data parallelism enabled (hp_dp_init)
+ * the gradient sum is all-reduced over NCCL behind the backward pass before
+ * the update. */
+HP_API int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, int64_t n,
+                                 float alpha, float *mse_dev, int precision, void *stream);
+/* Forward + backward WITHOUT the update: leaves sum_b g_b in the net's
+ * gradient store (.cnnb order).  For gradient parity tests and custom
+ * optimisers.  DEVICE buffers. */
+HP_API int hp_grad_batch_device(hp_net *net, const float *x_dev, const float *t_dev, int64_t n,
+                                float *mse_dev, int precision, void *stream);
+/* Copy the gradient store (HP_N_PARAMS floats, .cnnb order) to a HOST buffer. */
+HP_API int hp_get_grads(const hp_net *net, float *grads_host);
+/* Device address of the weight / gradient stores (HP_N_PARAMS floats each). */
+HP_API int hp_device_ptrs(hp_net *net, float **params_dev, float **grads_dev);
+/* W <- W - alpha * grads (the SGD epilogue on its own).  DEVICE, caller's stream. */
+HP_API int hp_apply_grads_device(hp_net *net, float alpha, void *stream);
+
+/* ---- data parallelism (new; the reference is single-process) ------------ */
+
+/* 128-byte NCCL unique id for rank 0 to broadcast by any host-side channel. */
+HP_API int hp_dp_unique_id(void *id128);
+/* One process per GPU: join a communicator of `world` ranks.  Afterwards
+ * hp_train_batch_device all-reduces (sum) the 9,458,400-float gradient per
+ * step, bucketed fc2 | fc1 | conv, launched as each bucket's weight gradient
+ * finishes, and applies the identical update on every rank. */
+HP_API int hp_dp_init(hp_net *net, const void *id128, int rank, int world);
+HP_API int hp_dp_shutdown(hp_net *net);
+
+/* ---- diagnostics --------------------------------------------------------- */
+
+/* Number of kernels this library has launched on behalf of `net` so far. */
+HP_API int64_t hp_launch_count(const hp_net *net);
+/* Peek at an intermediate of the last forward/backward pass (tests only):
+ * which = 3 pooled conv1 stage [n][3600], 6 pooled conv2 stage [n][2304],
+ * 8 fc1+tanh [n][2048]; copies n*len floats to HOST. */
+HP_API int hp_peek(hp_net *net, int which, int64_t n, float *out_host);
+/* Message for the last non-OK status returned on this thread. */
+HP_API const char *hp_last_error(void);
+/* "handposedd-b200 <version> sm_100a" */
+HP_API const char *hp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANDPOSEDD_H */

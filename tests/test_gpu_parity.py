@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/handposedd.h), against
+the CPU oracle on the same seeded inputs, against the committed golden vectors produced by the
+unmodified reference, and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Metric: max-normalised error max|a-b|/max|b| per tensor.
+
+Bounds (BASELINE.json north_star): FP32 path <= 1e-5 on outputs and gradients; tensor-core
+path <= 1e-2 on outputs.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, maxnorm_err
+from hand_tracking_samples_b200 import cnn as hp
+from hand_tracking_samples_b200 import synth
+from oracle.oracle import LAYOUT, N_PARAMS, Oracle
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+TC_TOL = 1e-2
+META = json.load(open(os.path.join(GOLDEN, "meta.json")))
+STRIDE = META["stride"]
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def p0(orc):
+    return orc.init_xavier()
+
+
+@pytest.fixture()
+def net():
+    n = hp.PoseInitializerCNN("")
+    yield n
+    del n
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def peaky(p0):
+    pk = p0.copy()
+    off, n = LAYOUT["fc2.W"]
+    pk[off:off + n] *= 30.0
+    return pk
+
+
+# ---- weights: Init and .cnnb ---------------------------------------------------------------
+def test_init_is_bit_identical_to_reference(net, p0):
+    data = net.saveb()
+    assert len(data) == 37833600
+    assert hashlib.sha256(data).hexdigest() == META["init_sha256"]
+    assert np.array_equal(np.frombuffer(data, np.float32), p0)
+
+
+def test_cnnb_roundtrip_and_short_read(net, p0, tmp_path):
+    rng = np.random.default_rng(3)
+    w = rng.standard_normal(N_PARAMS).astype(np.float32)
+    net.set_params(w)
+    path = str(tmp_path / "a.cnnb")
+    net.saveb(path)
+    assert open(path, "rb").read() == w.tobytes()          # byte-identical file, reference layout
+    net.Init()
+    net.loadb(path)
+    assert net.saveb() == w.tobytes()
+    # short stream: prefix loaded, tail untouched (loadvb, cnn.h:97)
+    net.Init()
+    net.loadb(w.tobytes()[:1664 + 10])                      # conv1.W, conv1.B and 2.5 floats of conv2.W
+    got = np.frombuffer(net.saveb(), np.float32)
+    assert np.array_equal(got[:418], w[:418]) and np.array_equal(got[418:], p0[418:])
+    # missing file: silent no-op like CNN::loadb(std::string) (cnn.h:592)
+    before = net.saveb()
+    net.loadb(str(tmp_path / "does_not_exist.cnnb"))
+    assert net.saveb() == before
+
+
+def test_copies_share_the_weight_store(net, p0):
+    twin = net.copy()
+    net.set_params(p0 * 2)
+    assert np.array_equal(np.frombuffer(twin.saveb(), np.float32), p0 * 2)
+    del twin
+    assert np.array_equal(np.frombuffer(net.saveb(), np.float32), p0 * 2)   # still alive after one owner died
+
+
+# ---- Eval ----------------------------------------------------------------------------------
+def test_eval_fp32_matches_golden(net):
+    crops = golden("crops.npy")
+    got = net.eval_batch(crops)
+    want = golden("eval_init.npy")
+    for i in range(crops.shape[0]):
+        assert maxnorm_err(got[i], want[i]) <= FP32_TOL, i
+    assert maxnorm_err(net.Eval(crops[2]), want[2]) <= FP32_TOL     # the reference's own single-crop call
+
+
+def test_eval_fp32_peaky_and_trained_weights(net, p0):
+    crops = golden("crops.npy")
+    net.set_params(peaky(p0))
+    assert maxnorm_err(net.eval_batch(crops), golden("eval_peaky.npy")) <= FP32_TOL
+
+
+def test_eval_fp32_stage_by_stage(net, orc, p0):
+    crops = golden("crops.npy")
+    tr = golden("trace_crop0.npz")
+    net.eval_batch(crops[:1])
+    assert maxnorm_err(net.peek(3, 1, 3600)[0], tr["pool1"]) <= FP32_TOL      # conv1+tanh+pool+pool
+    assert maxnorm_err(net.peek(6, 1, 2304)[0], tr["pool2"]) <= FP32_TOL      # conv2+tanh+pool
+    assert maxnorm_err(net.peek(8, 1, 2048)[0], tr["fc1"]) <= FP32_TOL        # fc1+tanh
+    assert maxnorm_err(net.peek(9, 1, 2304)[0], tr["logits"]) <= FP32_TOL     # fc2
+
+
+def test_eval_fp32_vs_oracle_seeded_and_ragged(net, orc, p0):
+    x = np.concatenate([synth.uniform_crops(5, 11), synth.depthlike_crops(6, 12)])
+    want = orc.eval(p0, x)
+    got = net.eval_batch(x)
+    assert maxnorm_err(got, want) <= FP32_TOL
+    for n in (1, 2, 3, 7):                                   # ragged batch sizes give the same per-crop result
+        assert np.array_equal(net.eval_batch(x[:n]), got[:n])
+    assert net.eval_batch(np.zeros((0, 4096), np.float32)).shape == (0, 2304)    # empty batch
+
+
+def test_eval_nan_propagation_like_reference(net, orc, p0):
+    # TanH::f is NaN above ~44.4 (SURVEY.md 8a note 2); same crops must go NaN on both sides
+    x = np.stack([np.full(4096, 1e3, np.float32), np.zeros(4096, np.float32), np.full(4096, -1e3, np.float32)])
+    want = orc.eval(p0, x)
+    got = net.eval_batch(x)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert maxnorm_err(got[ok], want[ok]) <= FP32_TOL
+
+
+def test_eval_chunking_and_device_entry_agree(net):
+    import torch
+    n = 2048 + 517                                           # crosses the FP32 workspace chunk
+    x = synth.uniform_crops(n, 5)
+    y_host = net.eval_batch(x)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty((n, 2304), device="cuda")
+    net.eval_batch_device(xd.data_ptr(), n, yd.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(yd.cpu().numpy(), y_host)
+    xp = torch.from_numpy(x).pin_memory()                    # pinned host buffers take the zero-bounce route
+    yp = torch.empty((n, 2304)).pin_memory()
+    net.eval_batch(xp.numpy(), out=yp.numpy())
+    assert np.array_equal(yp.numpy(), y_host)
+    sums = y_host[:, :2048].reshape(n, 8, 256).sum(-1)
+    assert np.allclose(sums, 1.0, atol=1e-5)
+
+
+# ---- Train ---------------------------------------------------------------------------------
+def sample(params):
+    return {k: (params[off:off + n][::STRIDE] if n > 100000 else params[off:off + n]) for k, (off, n) in LAYOUT.items()}
+
+
+def grads_of(net, x, t):
+    import torch
+    xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+    td = torch.from_numpy(np.ascontiguousarray(t, np.float32)).cuda()
+    mse = torch.empty(xd.shape[0], device="cuda")
+    net.grad_batch_device(xd.data_ptr(), td.data_ptr(), xd.shape[0], mse.data_ptr(),
+                          stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return net.get_grads(), mse.cpu().numpy()
+
+
+def test_single_sample_gradients_match_golden(net):
+    crops, labels, gold = golden("crops.npy"), golden("labels.npy"), golden("grads_init.npz")
+    for i in range(crops.shape[0]):
+        g, mse = grads_of(net, crops[i:i + 1], labels[i:i + 1])
+        assert abs(mse[0] - gold["mse"][i]) <= 1e-5 * gold["mse"][i]
+        for k, v in sample(g).items():
+            assert maxnorm_err(v, gold["%d/%s" % (i, k)]) <= FP32_TOL, (i, k)
+
+
+def test_backward_stage_by_stage(net, orc, p0):
+    x, t = synth.depthlike_crops(1, 21), synth.heatmap_labels(1, 22)
+    g_want, _ = orc.grad_sample(p0, x[0], t[0])
+    g, _ = grads_of(net, x, t)
+    assert maxnorm_err(net.peek(109, 1, 2304)[0], orc.peek(109)) <= FP32_TOL   # softmax backward
+    assert maxnorm_err(net.peek(107, 1, 2048)[0], orc.peek(107)) <= FP32_TOL   # fc2 dX * tanh'
+    # winners-only forms: compare at the non-zero entries of the oracle's dense tensors
+    e4 = orc.peek(104).reshape(64, 12, 12)
+    g2 = net.peek(106, 1, 2304)[0].reshape(64, 6, 6)
+    assert maxnorm_err(g2, e4.reshape(64, 6, 2, 6, 2).transpose(0, 1, 3, 2, 4).reshape(64, 6, 6, 4).sum(-1)) <= FP32_TOL
+    e0 = orc.peek(100).reshape(16, 15, 4, 15, 4).transpose(0, 1, 3, 2, 4).reshape(16, 15, 15, 16).sum(-1)
+    assert maxnorm_err(net.peek(103, 1, 3600)[0].reshape(16, 15, 15), e0) <= FP32_TOL
+    for k, (off, n) in LAYOUT.items():
+        assert maxnorm_err(g[off:off + n], g_want[off:off + n]) <= FP32_TOL, k
+
+
+def test_minibatch_gradient_is_sum_of_reference_sample_gradients(net, orc, p0):
+    n = 9
+    x = np.concatenate([synth.depthlike_crops(5, 31), synth.uniform_crops(4, 32)])
+    t = synth.heatmap_labels(n, 33)
+    want, mse_want = orc.train_minibatch(p0.copy(), x, t, 0.001, apply=False)
+    g, mse = grads_of(net, x, t)
+    assert np.allclose(mse, mse_want, rtol=1e-5)
+    for k, (off, cnt) in LAYOUT.items():
+        assert maxnorm_err(g[off:off + cnt], want[off:off + cnt]) <= FP32_TOL, k
+
+
+def test_train_batch1_sequence_matches_golden(net):
+    # 24 sequential CNN::Train steps exactly as train-cnn.cpp:160 issues them (alpha = 0.001)
+    crops, labels, gold = golden("crops.npy"), golden("labels.npy"), golden("train24.npz")
+    xs, ts = np.concatenate([crops] * 4), np.concatenate([labels] * 4)
+    mse = np.array([net.Train(xs[i], ts[i], 0.001) for i in range(24)], np.float32)
+    assert np.allclose(mse, gold["mse"], rtol=2e-5)
+    for k, v in sample(net.get_params()).items():
+        assert maxnorm_err(v, gold[k]) <= FP32_TOL, k
+    assert maxnorm_err(net.eval_batch(crops), golden("eval_train24.npy")) <= FP32_TOL
+
+
+def test_minibatch_step_matches_oracle(net, orc, p0):
+    n = 6
+    x, t = synth.depthlike_crops(n, 41), synth.heatmap_labels(n, 42)
+    p = p0.copy()
+    _, mse_want = orc.train_minibatch(p, x, t, 0.001, apply=True)
+    mse = net.train_batch(x, t, 0.001)
+    assert np.allclose(mse, mse_want, rtol=1e-5)
+    got = net.get_params()
+    for k, (off, cnt) in LAYOUT.items():
+        assert maxnorm_err(got[off:off + cnt], p[off:off + cnt]) <= FP32_TOL, k
+    # update really is W - alpha * grads
+    assert np.abs(got - p0).max() > 0
+
+
+def test_train_chunked_batch_equals_unchunked_sum(net, p0):
+    # n above the workspace chunk accumulates gradients across chunks at frozen weights
+    n = 2048 + 64
+    x, t = synth.uniform_crops(n, 51), synth.heatmap_labels(64, 52)
+    t = np.concatenate([t] * 33)[:n]
+    g_all, _ = grads_of(net, x, t)
+    g_a, _ = grads_of(net, x[:2048], t[:2048])
+    g_b, _ = grads_of(net, x[2048:], t[2048:])
+    for k, (off, cnt) in LAYOUT.items():
+        assert maxnorm_err(g_all[off:off + cnt], (g_a + g_b)[off:off + cnt]) <= 2e-6, k
+
+
+# ---- tensor-core path ----------------------------------------------------------------------
+def test_eval_tensor_path_within_bound(net, orc, p0):
+    x = np.concatenate([golden("crops.npy"), synth.depthlike_crops(10, 61), synth.uniform_crops(10, 62)])
+    want = orc.eval(p0, x)
+    got = net.eval_batch(x, precision=hp.PRECISION_TENSOR)
+    for i in range(x.shape[0]):
+        assert maxnorm_err(got[i], want[i]) <= TC_TOL, i
+    net.set_params(peaky(p0))
+    want = orc.eval(peaky(p0), x[:6])
+    got = net.eval_batch(x[:6], precision=hp.PRECISION_TENSOR)
+    assert maxnorm_err(got, want) <= 5 * TC_TOL            # 30x logits amplify bf16 rounding; reported, looser
+
+
+def test_eval_tensor_path_ragged_and_against_fp32(net):
+    x = synth.depthlike_crops(300, 71)
+    y32 = net.eval_batch(x)
+    ytc = net.eval_batch(x, precision=hp.PRECISION_TENSOR)
+    assert maxnorm_err(ytc, y32) <= TC_TOL
+    for n in (1, 3, 127, 129, 257):
+        assert np.array_equal(net.eval_batch(x[:n], precision=hp.PRECISION_TENSOR), ytc[:n])
+
+
+# ---- full-size properties (BASELINE.json configs[1]: 65,536 crops) --------------------------
+def test_full_size_properties():
+    import torch
+    n = 65536
+    net = hp.PoseInitializerCNN("")
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.rand((n, 4096), device="cuda", generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    for prec, tol in ((hp.PRECISION_TENSOR, 2e-6), (hp.PRECISION_FP32, 2e-6)):
+        y = torch.empty((n, 2304), device="cuda")
+        net.eval_batch_device(x.data_ptr(), n, y.data_ptr(), precision=prec, stream=st)
+        torch.cuda.synchronize()
+        assert torch.isfinite(y).all()
+        sums = torch.cat([y[:, :2048].reshape(n, 8, 256).sum(-1), y[:, 2048:].reshape(n, 16, 16).sum(-1)], 1)
+        assert (sums - 1).abs().max().item() <= 1e-5        # 24 softmaxes per crop
+        # shard consistency: evaluating a slice == slicing the evaluation (the multi-GPU inference contract)
+        lo, hi = 3 * n // 8, 4 * n // 8
+        ys = torch.empty((hi - lo, 2304), device="cuda")
+        net.eval_batch_device(x[lo:hi].data_ptr(), hi - lo, ys.data_ptr(), precision=prec, stream=st)
+        torch.cuda.synchronize()
+        assert torch.equal(ys, y[lo:hi])
+        # determinism
+        y2 = torch.empty_like(y)
+        net.eval_batch_device(x.data_ptr(), n, y2.data_ptr(), precision=prec, stream=st)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y2)
