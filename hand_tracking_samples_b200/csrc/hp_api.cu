@@ -64,6 +64,7 @@ int ensure_workspace(Net &net, int64_t n)
     rc |= dev_alloc(w.g2, cap * P2_N);
     rc |= dev_alloc(w.colgrad, cap * C2_POS * C2_KDIM);
     rc |= dev_alloc(w.g1, cap * P1_N);
+    if (!w.w2p) rc |= dev_alloc(w.w2p, (size_t)C2_CO * C2_KDIM);
     if (!w.partial) {
         w.partial_floats = (size_t)128 * C2_CO * C2_KDIM;  // conv2 split-K partials dominate
         rc |= dev_alloc(w.partial, w.partial_floats);
@@ -349,7 +350,7 @@ int hp_destroy(hp_net *net)
     tc_destroy(n);
     Workspace &w = n.ws;
     void *bufs[] = {n.params, n.grads, w.p1, w.idx1, w.col, w.c2, w.p2, w.idx2, w.h1, w.logits, w.y, w.dlog, w.da1, w.g2, w.colgrad,
-                    w.g1, w.partial, w.p2_bf, w.h1_bf, n.dev_in[0], n.dev_in[1], n.dev_out[0], n.dev_out[1], n.dev_t, n.dev_mse};
+                    w.g1, w.partial, w.w2p, w.p2_bf, w.h1_bf, n.dev_in[0], n.dev_in[1], n.dev_out[0], n.dev_out[1], n.dev_t, n.dev_mse};
     for (void *p : bufs)
         if (p) cudaFree(p);
     for (int b = 0; b < 2; b++) {
@@ -606,6 +607,12 @@ int hp_peek(hp_net *net, int which, int64_t n, float *out_host)
     case 107: src = N.ws.da1; len = FC1_OUT; break;
     case 106: src = N.ws.g2; len = P2_N; break;
     case 103: src = N.ws.g1; len = P1_N; break;
+    case 203:  // pool winners of the conv1 stage, uint8 [n][3600] (bytes, not floats)
+        HP_CUDA_TRY(cudaMemcpy(out_host, N.ws.idx1, (size_t)n * P1_N, cudaMemcpyDeviceToHost));
+        return HP_OK;
+    case 206:  // pool winners of the conv2 stage, uint8 [n][2304]
+        HP_CUDA_TRY(cudaMemcpy(out_host, N.ws.idx2, (size_t)n * P2_N, cudaMemcpyDeviceToHost));
+        return HP_OK;
     default: set_error("unknown intermediate %d", which); return HP_ERR_INVALID;
     }
     HP_CUDA_TRY(cudaMemcpy(out_host, src, (size_t)n * len * sizeof(float), cudaMemcpyDeviceToHost));

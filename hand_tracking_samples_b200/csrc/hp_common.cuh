@@ -38,7 +38,8 @@ struct Workspace {
     // forward (FP32 path; CHW planar like the reference unless noted)
     float *p1 = nullptr;      // [cap][16][15][15] tanh(conv1) after both pools
     uint8_t *idx1 = nullptr;  // [cap][3600] winning offset oy*4+ox inside the 4x4 window (hierarchical tie-break)
-    float *col = nullptr;     // [cap*144][256] im2col of p1, k = (ci,ky,kx)
+    float *col = nullptr;     // [cap*144][256] im2col of p1, k = (ky*4+kx)*16+ci (the reference's accumulation order)
+    float *w2p = nullptr;     // [64][256] conv2.W permuted to that k order (refreshed every forward)
     float *c2 = nullptr;      // [cap*144][64] conv2 pre-activation; reused as dense dL/dc2 in backward
     float *p2 = nullptr;      // [cap][2304] tanh(conv2) pooled, index x + 6*y + 36*c (the reference's flatten)
     uint8_t *idx2 = nullptr;  // [cap][2304] winning offset oy*2+ox inside the 2x2 window
@@ -72,9 +73,14 @@ void set_error(const char *fmt, ...);
 
 // TanH::f, cnn.h:31: (exp(2t)-1)/(exp(2t)+1) -- NOT tanhf: NaN above ~44.4 and
 // cancellation near 0 are part of the reference's results (SURVEY.md 8a note 2).
+// The FP32 path evaluates exp through double precision, (float)exp((double)x): a
+// correctly rounded expf, which is what glibc's expf (<= 0.502 ULP) returns for all but a
+// ~0.4 % sliver of inputs.  CUDA's own expf (2 ULP) would break the reference's exact
+// post-tanh ties differently and so pick different max-pool winners in backward.
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float tanh_ref(float t)
 {
-    float e = expf(2.0f * t);
+    float e = exp_cr(2.0f * t);
     return (e - 1.0f) / (e + 1.0f);
 }
 // std::max(a,b) == (a<b)?b:a (cnn.h:146): only differs from fmaxf for NaN.

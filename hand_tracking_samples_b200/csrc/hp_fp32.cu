@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) conv1_fwd_fp32(const float *__restrict__ 
         for (int oy = 0; oy < 4; oy++)
 #pragma unroll
             for (int ox = 0; ox < 4; ox++) acc[oy][ox] = bias;
-        // reference accumulation order: ky outer, kx inner (cnn.h:223)
+        // reference accumulation order: ky outer, kx inner (cnn.h:223); separately rounded multiply
+        // and add (no FMA) so the pre-activations -- and with them the pool winners -- are
+        // bit-identical to the reference built with -ffp-contract=off
 #pragma unroll
         for (int ky = 0; ky < 5; ky++)
 #pragma unroll
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_fp32(const float *__restrict__ 
 #pragma unroll
                 for (int oy = 0; oy < 4; oy++)
 #pragma unroll
-                    for (int ox = 0; ox < 4; ox++) acc[oy][ox] = fmaf(patch[oy + ky][ox + kx], wv, acc[oy][ox]);
+                    for (int ox = 0; ox < 4; ox++) acc[oy][ox] = __fadd_rn(acc[oy][ox], __fmul_rn(patch[oy + ky][ox + kx], wv));
             }
 #pragma unroll
         for (int oy = 0; oy < 4; oy++)
@@ -108,7 +110,25 @@ __global__ void __launch_bounds__(256) conv1_fwd_fp32(const float *__restrict__ 
     }
 }
 
-// im2col of the pooled conv1 stage: col[(n*144+pos)][k], k = ci*16 + ky*4 + kx.
+// conv2.W [co][ci][ky][kx] -> w2p[co][(ky*4+kx)*16+ci]: the k order in which LConv::forward
+// accumulates one output element (taps outer, ci inner, cnn.h:223-225).
+__global__ void __launch_bounds__(256) permute_c2w(const float *__restrict__ w, float *__restrict__ w2p)
+{
+    const int co = blockIdx.x, k = threadIdx.x;
+    const int ci = k & 15, tap = k >> 4;
+    w2p[co * C2_KDIM + k] = w[co * C2_KDIM + ci * 16 + tap];
+}
+// dst (+)= sum_s partial[s][co][(tap)*16+ci] un-permuted back to .cnnb order [co][ci][tap]
+__global__ void __launch_bounds__(256) reduce_c2w(float *__restrict__ dst, const float *__restrict__ src, int S, int accumulate)
+{
+    const int co = blockIdx.x, k = threadIdx.x;
+    const int ci = k & 15, tap = k >> 4;
+    float a = accumulate ? dst[co * C2_KDIM + ci * 16 + tap] : 0.f;
+    for (int s = 0; s < S; s++) a += src[(size_t)s * (C2_CO * C2_KDIM) + co * C2_KDIM + k];
+    dst[co * C2_KDIM + ci * 16 + tap] = a;
+}
+
+// im2col of the pooled conv1 stage: col[(n*144+pos)][k], k = (ky*4 + kx)*16 + ci.
 __global__ void __launch_bounds__(256) im2col_p1(const float *__restrict__ p1, float *__restrict__ col)
 {
     __shared__ float s[P1_N];
@@ -118,7 +138,7 @@ __global__ void __launch_bounds__(256) im2col_p1(const float *__restrict__ p1, f
     float *dst = col + crop * (int64_t)(C2_POS * C2_KDIM);
     for (int e = threadIdx.x; e < C2_POS * C2_KDIM; e += 256) {
         const int pos = e >> 8, k = e & 255;
-        const int ci = k >> 4, ky = (k >> 2) & 3, kx = k & 3;
+        const int ci = k & 15, ky = k >> 6, kx = (k >> 4) & 3;
         const int y = pos / C2_W, xx = pos % C2_W;
         dst[e] = s[ci * (P1_W * P1_H) + (y + ky) * P1_W + xx + kx];
     }
@@ -174,7 +194,7 @@ struct GemmArgs {
     int accumulate;      // EPI_STORE: C += acc
 };
 
-template <int BN, bool A_KC, bool B_KC, int EPI>
+template <int BN, bool A_KC, bool B_KC, int EPI, bool NOFMA = false>
 __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g)
 {
     constexpr int BM = 128, BK = 16, PAD = 4;
@@ -280,7 +300,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g)
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
-                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < TN; j++)
+                    acc[i][j] = NOFMA ? __fadd_rn(acc[i][j], __fmul_rn(a[i], b[j])) : fmaf(a[i], b[j], acc[i][j]);
         }
         if (it + 1 < nk) sstore(buf ^ 1);
         __syncthreads();
@@ -311,11 +332,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g)
     }
 }
 
-template <int BN, bool A_KC, bool B_KC, int EPI>
+template <int BN, bool A_KC, bool B_KC, int EPI, bool NOFMA = false>
 static int launch_sgemm(Net &net, const GemmArgs &g, int splits, cudaStream_t s)
 {
     dim3 grid((g.N + BN - 1) / BN, (g.M + 127) / 128, splits);
-    sgemm_kernel<BN, A_KC, B_KC, EPI><<<grid, 256, 0, s>>>(g);
+    sgemm_kernel<BN, A_KC, B_KC, EPI, NOFMA><<<grid, 256, 0, s>>>(g);
     LAUNCH_CHECK(net);
     return 0;
 }
@@ -368,7 +389,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ 
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        ev[i] = expf(lg[warp * 256 + i * 32 + lane]);
+        ev[i] = exp_cr(lg[warp * 256 + i * 32 + lane]);
         sum += ev[i];
     }
 #pragma unroll
@@ -376,7 +397,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ 
 #pragma unroll
     for (int i = 0; i < 8; i++) ev[i] = ev[i] / sum;
     // small spans: element 2048 + tid, span = tid / 16
-    es = expf(lg[2048 + tid]);
+    es = exp_cr(lg[2048 + tid]);
     float ssum = es;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
@@ -463,7 +484,7 @@ __global__ void __launch_bounds__(256) col2im_g1(const float *__restrict__ colgr
             for (int kx = 0; kx < 4; kx++) {
                 const int xx = X - kx;
                 if (xx < 0 || xx >= C2_W) continue;
-                a += cg[(y * C2_W + xx) * C2_KDIM + ci * 16 + ky * 4 + kx];
+                a += cg[(y * C2_W + xx) * C2_KDIM + (ky * 4 + kx) * 16 + ci];
             }
         }
         const float pv = p1[crop * P1_N + e];
@@ -541,9 +562,11 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
     LAUNCH_CHECK(net);
     im2col_p1<<<(unsigned)n, 256, 0, s>>>(w.p1, w.col);
     LAUNCH_CHECK(net);
-    {   // conv2: [n*144 x 256] x W2[64][256]^T + bias
-        GemmArgs g{(int)(n * C2_POS), C2_CO, C2_KDIM, w.col, C2_KDIM, P + OFF_C2W, C2_KDIM, w.c2, C2_CO, P + OFF_C2B, nullptr, C2_KDIM, 0};
-        if (int rc = launch_sgemm<64, true, true, EPI_BIAS>(net, g, 1, s)) return rc;
+    permute_c2w<<<C2_CO, 256, 0, s>>>(P + OFF_C2W, w.w2p);
+    LAUNCH_CHECK(net);
+    {   // conv2: [n*144 x 256] x w2p[64][256]^T + bias, un-fused multiply-add in the reference's k order
+        GemmArgs g{(int)(n * C2_POS), C2_CO, C2_KDIM, w.col, C2_KDIM, w.w2p, C2_KDIM, w.c2, C2_CO, P + OFF_C2B, nullptr, C2_KDIM, 0};
+        if (int rc = launch_sgemm<64, true, true, EPI_BIAS, true>(net, g, 1, s)) return rc;
     }
     tanh_pool2<<<(unsigned)n, 256, 0, s>>>(w.c2, w.p2, w.idx2);
     LAUNCH_CHECK(net);
@@ -621,11 +644,11 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         splits = (int)((R + klen - 1) / klen);
         GemmArgs g{C2_CO, C2_KDIM, (int)R, w.c2, C2_CO, w.col, C2_KDIM, w.partial, C2_KDIM, nullptr, nullptr, klen, 0};
         if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, splits, s)) return rc;
-        reduce_partials<<<(C2_CO * C2_KDIM + 255) / 256, 256, 0, s>>>(G + OFF_C2W, w.partial, splits, C2_CO * C2_KDIM, acc);
+        reduce_c2w<<<C2_CO, 256, 0, s>>>(G + OFF_C2W, w.partial, splits, acc);
         LAUNCH_CHECK(net);
     }
     {
-        GemmArgs g{(int)R, C2_KDIM, C2_CO, w.c2, C2_CO, P + OFF_C2W, C2_KDIM, w.colgrad, C2_KDIM, nullptr, nullptr, C2_CO, 0};
+        GemmArgs g{(int)R, C2_KDIM, C2_CO, w.c2, C2_CO, w.w2p, C2_KDIM, w.colgrad, C2_KDIM, nullptr, nullptr, C2_CO, 0};
         if (int rc = launch_sgemm<128, true, false, EPI_STORE>(net, g, 1, s)) return rc;
     }
     col2im_g1<<<(unsigned)n, 256, 0, s>>>(w.colgrad, w.p1, w.g1);
