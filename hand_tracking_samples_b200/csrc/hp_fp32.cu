@@ -2,8 +2,10 @@
 // comparison" arm of BASELINE.json's north_star.  Same arithmetic as the
 // reference's third_party/cnn.h (bias first, then products accumulated in
 // ascending-k order, the reference's exp-based tanh, unshifted softmax, first
-// strict maximum in the pools) with FMA contraction as the only deliberate
-// difference; parity bound 1e-5 max-normalised (tests/test_gpu_parity.py).
+// strict maximum in the pools).  The conv stages use separately rounded multiply
+// and add plus a correctly rounded exp, so their outputs and pool winners are
+// bit-identical to the pinned reference; the FC contractions use FFMA, the only
+// deliberate difference.  Parity bound 1e-5 max-normalised (tests/test_gpu_parity.py).
 //
 // Kernels
 //   conv1_fwd_fp32      LConv 5x5 (cnn.h:205) + TanH (cnn.h:31,460) + 2x LMaxPool (cnn.h:141), fused
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256) im2col_p1(const float *__restrict__ p1, f
 // tanh + 2x2 max-pool of conv2's pre-activations c2[(n*144+pos)][co]; writes the
 // reference's CHW flatten p2[n][x + 6y + 36c] and the winner offset.
 __global__ void __launch_bounds__(256) tanh_pool2(const float *__restrict__ c2, float *__restrict__ p2,
-                                                  uint8_t *__restrict__ idx2)
+                                                  uint8_t *__restrict__ idx2, __nv_bfloat16 *__restrict__ p2_bf)
 {
     __shared__ float sv[P2_N];
     __shared__ uint8_t si[P2_N];
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(256) tanh_pool2(const float *__restrict__ c2, 
     for (int e = threadIdx.x; e < P2_N; e += 256) {
         p2[crop * P2_N + e] = sv[e];
         idx2[crop * P2_N + e] = si[e];
+        if (p2_bf) p2_bf[crop * P2_N + e] = __float2bfloat16_rn(sv[e]);
     }
 }
 
@@ -554,7 +557,8 @@ __global__ void __launch_bounds__(256) sgd_kernel(float4 *__restrict__ p, const 
 // ============================================================================
 // host-side chains
 // ============================================================================
-int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool training, cudaStream_t s)
+// conv1+tanh+pool+pool and conv2+tanh+pool; optionally also emits the features as bf16
+int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s)
 {
     Workspace &w = net.ws;
     const float *P = net.params;
@@ -568,8 +572,16 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
         GemmArgs g{(int)(n * C2_POS), C2_CO, C2_KDIM, w.col, C2_KDIM, w.w2p, C2_KDIM, w.c2, C2_CO, P + OFF_C2B, nullptr, C2_KDIM, 0};
         if (int rc = launch_sgemm<64, true, true, EPI_BIAS, true>(net, g, 1, s)) return rc;
     }
-    tanh_pool2<<<(unsigned)n, 256, 0, s>>>(w.c2, w.p2, w.idx2);
+    tanh_pool2<<<(unsigned)n, 256, 0, s>>>(w.c2, w.p2, w.idx2, p2_bf);
     LAUNCH_CHECK(net);
+    return 0;
+}
+
+int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool training, cudaStream_t s)
+{
+    Workspace &w = net.ws;
+    const float *P = net.params;
+    if (int rc = fp32_conv_stage(net, x, n, nullptr, s)) return rc;
     {   // fc1 + tanh
         GemmArgs g{(int)n, FC1_OUT, FC1_IN, w.p2, FC1_IN, P + OFF_F1W, FC1_OUT, w.h1, FC1_OUT, P + OFF_F1B, nullptr, FC1_IN, 0};
         if (int rc = launch_sgemm<128, true, false, EPI_BIAS_TANH>(net, g, 1, s)) return rc;
