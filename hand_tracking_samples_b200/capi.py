@@ -21,7 +21,7 @@ SYMBOLS = [
     "hp_create", "hp_create_handposedd", "hp_retain", "hp_destroy", "hp_init_xavier", "hp_load_cnnb",
     "hp_save_cnnb", "hp_load_cnnb_file", "hp_save_cnnb_file", "hp_eval_batch", "hp_eval_batch_device",
     "hp_train_batch", "hp_train_batch_device", "hp_grad_batch_device", "hp_get_grads", "hp_device_ptrs",
-    "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_shutdown", "hp_launch_count",
+    "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_shutdown", "hp_launch_count", "hp_profile", "hp_profile_read",
     "hp_peek", "hp_last_error", "hp_version",
 ]
 
@@ -75,6 +75,8 @@ def lib():
     L.hp_dp_shutdown.argtypes = [vp]
     L.hp_launch_count.argtypes = [vp]
     L.hp_launch_count.restype = i64
+    L.hp_profile.argtypes = [vp, C.c_int]
+    L.hp_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     L.hp_peek.argtypes = [vp, C.c_int, i64, vp]
     L.hp_last_error.restype = C.c_char_p
     L.hp_version.restype = C.c_char_p

@@ -177,6 +177,15 @@ class CNN:
         capi.check(self.L.hp_peek(self.h, which, n, out.ctypes.data))
         return out
 
+    def profile(self, enable):
+        capi.check(self.L.hp_profile(self.h, int(enable)))
+
+    def profile_read(self, n_stages=4):
+        ms = (C.c_double * n_stages)()
+        cnt = (C.c_int64 * n_stages)()
+        capi.check(self.L.hp_profile_read(self.h, n_stages, ms, cnt))
+        return list(ms), list(cnt)
+
     def launch_count(self):
         return int(self.L.hp_launch_count(self.h))
 

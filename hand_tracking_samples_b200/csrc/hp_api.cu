@@ -363,6 +363,10 @@ int hp_destroy(hp_net *net)
     for (int b = 0; b < 3; b++)
         if (n.ev_bucket[b]) cudaEventDestroy(n.ev_bucket[b]);
     if (n.ev_comm) cudaEventDestroy(n.ev_comm);
+    if (n.prof_ev) {
+        for (int i = 0; i < Net::PROF_MAX; i++) cudaEventDestroy(n.prof_ev[i]);
+        delete[] n.prof_ev;
+    }
     if (n.stream) cudaStreamDestroy(n.stream);
     if (n.comm_stream) cudaStreamDestroy(n.comm_stream);
     if (n.d2h_stream) cudaStreamDestroy(n.d2h_stream);
@@ -584,6 +588,38 @@ int hp_dp_shutdown(hp_net *net)
     }
     N.world = 1;
     N.rank = 0;
+    return HP_OK;
+}
+
+int hp_profile(hp_net *net, int enable)
+{
+    if (!net) { set_error("net is NULL"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    if (enable && !N.prof_ev) {
+        N.prof_ev = new cudaEvent_t[Net::PROF_MAX];
+        for (int i = 0; i < Net::PROF_MAX; i++) HP_CUDA_TRY(cudaEventCreate(&N.prof_ev[i]));
+    }
+    if (enable) N.prof_used = 0;
+    N.profiling = enable != 0;
+    return HP_OK;
+}
+
+int hp_profile_read(hp_net *net, int n_stages, double *total_ms, int64_t *intervals)
+{
+    if (!net || n_stages < 0 || !total_ms || !intervals) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < n_stages; i++) { total_ms[i] = 0; intervals[i] = 0; }
+    for (int i = 0; i + 1 < N.prof_used; i += 2) {
+        const int st = N.prof_stage[i / 2];
+        if (st < 0 || st >= n_stages) continue;
+        float ms = 0;
+        HP_CUDA_TRY(cudaEventElapsedTime(&ms, N.prof_ev[i], N.prof_ev[i + 1]));
+        total_ms[st] += ms;
+        intervals[st]++;
+    }
     return HP_OK;
 }
 

@@ -125,6 +125,32 @@ struct Net {
     int rank = 0, world = 1;
     int64_t launches = 0;
     int64_t last_n = 0;
+    // per-stage timing (hp_profile): a pool of events, (stage, begin, end) triples
+    bool profiling = false;
+    static constexpr int PROF_MAX = 8192;
+    cudaEvent_t *prof_ev = nullptr;
+    int prof_used = 0;            // events consumed
+    int prof_stage[PROF_MAX / 2]; // stage id of interval i = events (2i, 2i+1)
+};
+
+// record the begin/end of a stage on stream s when profiling is on
+struct StageTimer {
+    Net &net;
+    cudaStream_t s;
+    int slot = -1;
+    StageTimer(Net &n, int stage, cudaStream_t st) : net(n), s(st)
+    {
+        if (net.profiling && net.prof_used + 2 <= Net::PROF_MAX) {
+            slot = net.prof_used;
+            net.prof_used += 2;
+            net.prof_stage[slot / 2] = stage;
+            cudaEventRecord(net.prof_ev[slot], s);
+        }
+    }
+    ~StageTimer()
+    {
+        if (slot >= 0) cudaEventRecord(net.prof_ev[slot + 1], s);
+    }
 };
 
 int ensure_workspace(Net &net, int64_t n);

@@ -581,16 +581,22 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
 {
     Workspace &w = net.ws;
     const float *P = net.params;
-    if (int rc = fp32_conv_stage(net, x, n, nullptr, s)) return rc;
+    {
+        StageTimer st(net, 0, s);
+        if (int rc = fp32_conv_stage(net, x, n, nullptr, s)) return rc;
+    }
     {   // fc1 + tanh
+        StageTimer st(net, 1, s);
         GemmArgs g{(int)n, FC1_OUT, FC1_IN, w.p2, FC1_IN, P + OFF_F1W, FC1_OUT, w.h1, FC1_OUT, P + OFF_F1B, nullptr, FC1_IN, 0};
         if (int rc = launch_sgemm<128, true, false, EPI_BIAS_TANH>(net, g, 1, s)) return rc;
     }
     {   // fc2 logits
+        StageTimer st(net, 2, s);
         GemmArgs g{(int)n, FC2_OUT, FC2_IN, w.h1, FC2_IN, P + OFF_F2W, FC2_OUT, w.logits, FC2_OUT, P + OFF_F2B, nullptr, FC2_IN, 0};
         if (int rc = launch_sgemm<128, true, false, EPI_BIAS>(net, g, 1, s)) return rc;
     }
     if (!training) {
+        StageTimer st(net, 3, s);
         softmax_kernel<false><<<(unsigned)n, 256, 0, s>>>(w.logits, y_out, nullptr, nullptr, nullptr);
         LAUNCH_CHECK(net);
     }

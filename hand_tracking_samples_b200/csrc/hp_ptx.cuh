@@ -83,6 +83,24 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes multiple of 16)
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------
 template <uint32_t NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst)  // whole warp
@@ -154,6 +172,19 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr)
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// K-major operand WITHOUT swizzle ("interleave"): 8-row x 16-byte core matrices; row r,
+// 16-byte k-chunk c live at  start + (r%8)*16 + (r/8)*SBO + c*LBO.  With SBO = 128 the address is
+// linear in r, which lets a descriptor start at ANY 16-byte-aligned row: the convolutions use
+// this to express their im2col operands as shifted views of one shared-memory image.
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
     return d;
 }
 // Instruction descriptor, kind::f16: D = F32 (bits[4,6)=1), A = B = BF16 (bits[7,10)=1, [10,13)=1),

@@ -14,8 +14,8 @@
 //            fc2: + bias, exp, per-span sums and divide (LSoftMaxChunked::forward, cnn.h:497-511;
 //                 every 256-wide N tile is exactly one span of 256 or sixteen spans of 16)
 // The bound for this path is 1e-2 max-normalised against the reference (tests/test_gpu_parity.py).
-#include "hp_common.cuh"
 #include "hp_ptx.cuh"
+#include "hp_tc.cuh"
 
 #include <cuda.h>
 #include <stdio.h>
@@ -39,16 +39,6 @@ constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*ba
 constexpr int GEMM_THREADS = 256;
 
 enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1 };
-
-struct TcState {
-    __nv_bfloat16 *w1t = nullptr;  // [2048][2304] = fc1.W^T, k contiguous
-    __nv_bfloat16 *w2t = nullptr;  // [2304][2048] = fc2.W^T
-    __nv_bfloat16 *p2 = nullptr;   // [cap][2304] pooled conv2 stage (fc1 input)
-    __nv_bfloat16 *h1 = nullptr;   // [cap][2048] tanh(fc1)
-    int64_t cap = 0;
-    CUtensorMap tm_w1t, tm_w2t, tm_p2, tm_h1;
-    int num_sms = 148;
-};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -277,20 +267,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // fp32 W[K][N] (row-major, the .cnnb layout of LFull, cnn.h:417) -> bf16 Wt[N][K]
+// HWC: destination k' = pp*64 + co reads source row co*36 + pp (the conv kernel emits its features
+// pixel-major, the reference flattens channel-major: x + 6y + 36c).
+template <bool HWC>
 __global__ void __launch_bounds__(256) transpose_to_bf16(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wt, int K, int N)
 {
     __shared__ float tile[32][33];
     const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 4; i++) tile[ty + 8 * i][tx] = w[(size_t)(k0 + ty + 8 * i) * N + n0 + tx];
+    for (int i = 0; i < 4; i++) {
+        const int kd = k0 + ty + 8 * i;
+        const int ks = HWC ? (kd & 63) * 36 + (kd >> 6) : kd;
+        tile[ty + 8 * i][tx] = w[(size_t)ks * N + n0 + tx];
+    }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; i++) wt[(size_t)(n0 + ty + 8 * i) * K + k0 + tx] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
 }
 
-// hp_fp32.cu: conv1+tanh+pools and conv2+tanh+pool on FFMA, additionally emitting bf16 features
-int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
 
 int tc_init(Net &net)
 {
@@ -306,7 +301,7 @@ int tc_init(Net &net)
     if (int rc = make_map_bf16(&t->tm_w2t, t->w2t, FC2_OUT, FC2_IN, BN)) return rc;
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_SOFTMAX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    return 0;
+    return tc_conv_init(net);
 }
 
 void tc_destroy(Net &net)
@@ -315,6 +310,8 @@ void tc_destroy(Net &net)
     if (!t) return;
     if (t->w1t) cudaFree(t->w1t);
     if (t->w2t) cudaFree(t->w2t);
+    if (t->b1_img) cudaFree(t->b1_img);
+    if (t->b2_img) cudaFree(t->b2_img);
     if (t->p2) cudaFree(t->p2);
     if (t->h1) cudaFree(t->h1);
     delete t;
@@ -324,10 +321,11 @@ void tc_destroy(Net &net)
 int tc_refresh_weights(Net &net, cudaStream_t s)
 {
     TcState *t = net.tc;
-    transpose_to_bf16<<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, t->w1t, FC1_IN, FC1_OUT);
+    transpose_to_bf16<true><<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, t->w1t, FC1_IN, FC1_OUT);
     LAUNCH_CHECK(net);
-    transpose_to_bf16<<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, t->w2t, FC2_IN, FC2_OUT);
+    transpose_to_bf16<false><<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, t->w2t, FC2_IN, FC2_OUT);
     LAUNCH_CHECK(net);
+    if (int rc = tc_conv_refresh(net, s)) return rc;
     net.tc_dirty = false;
     return 0;
 }
@@ -359,13 +357,13 @@ int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s
         const int64_t m = (n - b < TC_CHUNK) ? n - b : TC_CHUNK;
         if (int rc = tc_ensure(net, m)) return rc;
         // conv stages (FFMA for now) -> bf16 features
-        for (int64_t c = 0; c < m; c += 2048) {
-            const int64_t mm = (m - c < 2048) ? m - c : 2048;
-            if (int rc = ensure_workspace(net, mm)) return rc;
-            if (int rc = fp32_conv_stage(net, x + (b + c) * N_IN, mm, t->p2 + c * FC1_IN, s)) return rc;
+        {
+            StageTimer st(net, 0, s);
+            if (int rc = tc_conv_stage(net, x + b * N_IN, m, t->p2, s)) return rc;
         }
         const int m_tiles = (int)((m + BM - 1) / BM);
         {
+            StageTimer st(net, 1, s);
             const int tiles = m_tiles * (FC1_OUT / BN);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
             tc_gemm_kernel<TC_EPI_TANH_BF16><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_p2, t->tm_w1t, net.params + OFF_F1B, t->h1, (int)m,
@@ -373,6 +371,7 @@ int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s
             LAUNCH_CHECK(net);
         }
         {
+            StageTimer st(net, 2, s);
             const int tiles = m_tiles * (FC2_OUT / BN);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
             tc_gemm_kernel<TC_EPI_SOFTMAX_F32><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_h1, t->tm_w2t, net.params + OFF_F2B,

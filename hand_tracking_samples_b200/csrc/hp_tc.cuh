@@ -1,0 +1,26 @@
+// hp_tc.cuh -- state shared by the tensor-core kernel files (hp_tc.cu: FC GEMMs, hp_tc_conv.cu: conv stages).
+#pragma once
+#include <cuda.h>
+#include "hp_common.cuh"
+
+namespace hp {
+
+struct TcState {
+    // bf16 shadows of the weights, in the layouts the MMAs consume (rebuilt by tc_refresh_weights)
+    __nv_bfloat16 *w1t = nullptr;  // [2048][2304] = fc1.W^T, k contiguous, k in HWC flatten order (pp*64+co)
+    __nv_bfloat16 *w2t = nullptr;  // [2304][2048] = fc2.W^T
+    uint8_t *b1_img = nullptr;     // 32 KB: conv1 as pooled-window GEMM, B operand [256 (pos,co)][64 (r,c)] bf16, 128B-swizzled image
+    uint8_t *b2_img = nullptr;     // 32 KB: conv2 taps, [16 taps][2 k-chunks][64 co][8 ci] bf16 (no-swizzle core matrices)
+    // activations
+    __nv_bfloat16 *p2 = nullptr;   // [cap][2304] pooled conv2 stage (fc1 input), HWC flatten
+    __nv_bfloat16 *h1 = nullptr;   // [cap][2048] tanh(fc1)
+    int64_t cap = 0;
+    CUtensorMap tm_w1t, tm_w2t, tm_p2, tm_h1;
+    int num_sms = 148;
+};
+
+int tc_conv_init(Net &net);
+int tc_conv_refresh(Net &net, cudaStream_t s);
+int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
+
+}  // namespace hp

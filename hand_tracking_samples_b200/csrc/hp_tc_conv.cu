@@ -1,0 +1,378 @@
+// hp_tc_conv.cu -- both convolution stages of handposedd on tcgen05 tensor cores, fused in one
+// persistent warp-specialised kernel:  fp32 crop -> [conv1 5x5 + 2x(2x2 max-pool) + tanh] ->
+// [conv2 4x4 + tanh + 2x2 max-pool] -> 2304 bf16 features (fc1's A operand).
+// Reference layers: LConv::forward (cnn.h:205-257), LActivation<TanH> (cnn.h:460), LMaxPool::forward
+// (cnn.h:141-148), instantiated at include/handtrack.h:108-114.
+//
+// Neither convolution materialises an im2col matrix.  Both A operands are *views* of one small
+// shared-memory image expressed through un-swizzled K-major UMMA descriptors, whose address is
+// linear in the row index when the 8-row stride (SBO) is 128 B or a multiple of the row pitch:
+//
+// conv1 as a "pooled-window GEMM".  Row m = pooled pixel (py,px) of the 15x15 grid that survives
+//   the two 2x2 pools; K = the 8x8 input patch at stride 4 that pixel depends on; N = 16 window
+//   positions x 16 channels (B is the 5x5 kernel embedded at offset (dy,dx) in the 8x8 patch).
+//   The 4x4 max-pool then happens inside one thread's registers (all 16 positions of a pooled
+//   pixel are columns of the same TMEM lane) and tanh is applied once per pooled value
+//   (max and the monotone tanh commute in the forward pass).  A[(py,px')][(r,c)] =
+//   img[4py+r][8px'+4e+c]: with the bf16 image stored twice (e = 0: as is, e = 1: shifted by 4
+//   pixels) a core matrix is 8 consecutive px' (16 B apart), SBO = 4 image rows, LBO = 1 image row.
+// conv2 as 16 shifted taps.  p1 is kept as two planes [pixel q][8 channels] (16 B per row); for
+//   tap (ky,kx) the A operand is the same plane pair starting ky*15+kx rows further down, K = 16
+//   input channels = one MMA.  Rows whose (y,x) fall outside the 12x12 valid outputs compute
+//   garbage that is never read.
+//
+// Warp roles (512 threads, 1 CTA/SM, crops strided over the grid):
+//   warp 0      loads the two 32 KB weight images with cp.async.bulk; allocates TMEM
+//   warp 1      MMA issuer: conv1(crop i+1) then conv2(crop i), software-pipelined by one crop
+//   warps 4-7   epilogue 1: TMEM -> running max over window positions -> +bias, tanh -> p1 planes (smem)
+//   warps 8-11  epilogue 2: TMEM -> bf16 staging -> 2x2 max, +bias, tanh -> global features
+//   warps 12-15 loader: fp32 crop from global -> two bf16 image copies in smem (double-buffered)
+#include "hp_ptx.cuh"
+#include "hp_tc.cuh"
+
+namespace hp {
+
+#define LAUNCH_CHECK(net)                \
+    do {                                 \
+        (net).launches++;                \
+        HP_CUDA_TRY(cudaGetLastError()); \
+    } while (0)
+
+namespace cv {
+constexpr int THREADS = 512;
+constexpr int IMG_COPY = 9216;                 // one bf16 image copy (8 KB) + slack for the pad rows' reads
+constexpr int IMG_BUF = 2 * IMG_COPY;          // aligned copy + copy shifted by 4 pixels
+constexpr int P1_ROWS = 304;                   // 225 pixels + tap-shift overhang of the second M tile
+constexpr int P1_PLANE = P1_ROWS * 16;         // 8 channels x bf16 per row
+constexpr int P1_BUF = 2 * P1_PLANE;
+constexpr int S_ROWS = 192;                    // conv2 pre-activations of rows q <= 176, 64 ch bf16 = 128 B
+constexpr int OFF_B1 = 0;                      // 32 KB, 1024-aligned (128B swizzle)
+constexpr int OFF_B2 = 32768;                  // 32 KB
+constexpr int OFF_IMG = 65536;                 // 2 x IMG_BUF
+constexpr int OFF_P1 = OFF_IMG + 2 * IMG_BUF;  // 2 x P1_BUF
+constexpr int OFF_S = OFF_P1 + 2 * P1_BUF;     // S_ROWS x 128
+constexpr int OFF_BIAS = OFF_S + S_ROWS * 128; // 16 + 64 floats
+constexpr int OFF_BAR = OFF_BIAS + 512;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+// TMEM columns
+constexpr int ACC1 = 0;    // two 128-column conv1 accumulators (window-position halves)
+constexpr int ACC2 = 256;  // two conv2 accumulator sets of 2 x 64 columns
+}  // namespace cv
+
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(cv::THREADS, 1)
+tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, const uint8_t *__restrict__ b2_img,
+               const float *__restrict__ params, __nv_bfloat16 *__restrict__ p2_out, int n)
+{
+    using namespace cv;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *bias1 = reinterpret_cast<float *>(smem + OFF_BIAS);
+    float *bias2 = bias1 + 16;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+    uint64_t *wgt_full = bars + 0;
+    uint64_t *img_full = bars + 1;    // [2]
+    uint64_t *img_empty = bars + 3;   // [2]
+    uint64_t *acc1_full = bars + 5;   // [2]
+    uint64_t *acc1_empty = bars + 7;  // [2]
+    uint64_t *p1_full = bars + 9;     // [2]
+    uint64_t *p1_empty = bars + 11;   // [2]
+    uint64_t *acc2_full = bars + 13;  // [2]
+    uint64_t *acc2_empty = bars + 15; // [2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_crops = (n > (int)blockIdx.x) ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(wgt_full, 1);
+        for (int b = 0; b < 2; b++) {
+            ptx::mbar_init(&img_full[b], 128);
+            ptx::mbar_init(&img_empty[b], 1);
+            ptx::mbar_init(&acc1_full[b], 1);
+            ptx::mbar_init(&acc1_empty[b], 4);
+            ptx::mbar_init(&p1_full[b], 4);
+            ptx::mbar_init(&p1_empty[b], 1);
+            ptx::mbar_init(&acc2_full[b], 1);
+            ptx::mbar_init(&acc2_empty[b], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    // zero the p1 planes once: the overhang rows (225..303) are read by the second conv2 M tile
+    for (int i = threadIdx.x; i < 2 * P1_BUF / 16; i += THREADS) reinterpret_cast<uint4 *>(smem + OFF_P1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 2 * IMG_BUF / 16; i += THREADS) reinterpret_cast<uint4 *>(smem + OFF_IMG)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 16) bias1[threadIdx.x] = params[OFF_C1B + threadIdx.x];
+    if (threadIdx.x >= 64 && threadIdx.x < 128) bias2[threadIdx.x - 64] = params[OFF_C2B + threadIdx.x - 64];
+    if (warp == 0) ptx::tmem_alloc<512>(tmem_ptr);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(wgt_full, 65536);
+            ptx::bulk_load_1d(smem + OFF_B1, b1_img, 32768, wgt_full);
+            ptx::bulk_load_1d(smem + OFF_B2, b2_img, 32768, wgt_full);
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = ptx::make_idesc_bf16(128, 128);
+            constexpr uint32_t idesc2 = ptx::make_idesc_bf16(128, 64);
+            ptx::mbar_wait(wgt_full, 0);
+            const uint32_t sB1 = ptx::smem_u32(smem + OFF_B1), sB2 = ptx::smem_u32(smem + OFF_B2);
+            auto conv2 = [&](int it) {
+                const int pb = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                ptx::mbar_wait(&p1_full[pb], ph);
+                ptx::mbar_wait(&acc2_empty[pb], ph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t sP = ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF);
+#pragma unroll 1
+                for (int mt = 0; mt < 2; mt++) {
+                    const uint32_t d = tmem_base + ACC2 + pb * 128 + mt * 64;
+#pragma unroll
+                    for (int tap = 0; tap < 16; tap++) {
+                        const int shift = (tap >> 2) * 15 + (tap & 3);
+                        const uint64_t ad = ptx::make_desc_nosw(sP + (mt * 128 + shift) * 16, P1_PLANE, 128);
+                        const uint64_t bd = ptx::make_desc_nosw(sB2 + tap * 2048, 1024, 128);
+                        ptx::umma_f16(d, ad, bd, idesc2, tap != 0);
+                    }
+                }
+                ptx::umma_commit(&acc2_full[pb]);
+                ptx::umma_commit(&p1_empty[pb]);
+            };
+            for (int it = 0; it < my_crops; it++) {
+                const int ib = it & 1;
+                ptx::mbar_wait(&img_full[ib], (it >> 1) & 1);
+                ptx::tc_fence_after();
+                const uint32_t sI = ptx::smem_u32(smem + OFF_IMG + ib * IMG_BUF);
+#pragma unroll 1
+                for (int g = 0; g < 4; g++) {
+                    const int e = g >> 1, half = g & 1;       // e: pooled-column parity (which image copy)
+                    const uint32_t u = (uint32_t)(it * 2 + e); // use count of accumulator `half`
+                    ptx::mbar_wait(&acc1_empty[half], (u & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d = tmem_base + ACC1 + half * 128;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint64_t ad = ptx::make_desc_nosw(sI + e * IMG_COPY + ks * 256, 128, 512);
+                        const uint64_t bd = ptx::make_desc_sw128(sB1 + half * 16384) + 2 * ks;
+                        ptx::umma_f16(d, ad, bd, idesc1, ks != 0);
+                    }
+                    ptx::umma_commit(&acc1_full[half]);
+                }
+                ptx::umma_commit(&img_empty[ib]);
+                if (it > 0) conv2(it - 1);
+            }
+            if (my_crops > 0) conv2(my_crops - 1);
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue 1: conv1 accumulators -> p1 planes =====================
+        const int ew = warp - 4;
+        const int m = ew * 32 + lane;           // row of the M tile: (py, px')
+        const int py = m >> 3, pxh = m & 7;
+        for (int it = 0; it < my_crops; it++) {
+            const int pb = it & 1;
+            uint8_t *planes = smem + OFF_P1 + pb * P1_BUF;
+            ptx::mbar_wait(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
+#pragma unroll 1
+            for (int e = 0; e < 2; e++) {
+                float mx[16];
+                const uint32_t u = (uint32_t)(it * 2 + e);
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+                    ptx::mbar_wait(&acc1_full[half], u & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC1 + half * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
+                        uint32_t r[32];
+                        ptx::tmem_ld32(ta + c * 32, r);
+                        ptx::tmem_ld_wait();
+                        if (half == 0 && c == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) mx[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) mx[j] = ptx::max3(mx[j], __uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+                        }
+                    }
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
+                }
+                const int px = 2 * pxh + e;
+                if (py < 15 && px < 15) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        pk[j] = pack_bf16(tanh_fast(mx[2 * j] + bias1[2 * j]), tanh_fast(mx[2 * j + 1] + bias1[2 * j + 1]));
+                    const int q = py * 15 + px;
+                    *reinterpret_cast<uint4 *>(planes + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4 *>(planes + P1_PLANE + q * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            ptx::fence_proxy_async();   // generic-proxy stores -> visible to the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ===================== epilogue 2: conv2 accumulators -> pooled features =====================
+        const int ew = warp - 8;
+        const int t128 = ew * 32 + lane;
+        uint8_t *S = smem + OFF_S;
+        for (int it = 0; it < my_crops; it++) {
+            const int pb = it & 1;
+            const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            ptx::mbar_wait(&acc2_full[pb], (it >> 1) & 1);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < 2; mt++) {
+                const int q = mt * 128 + t128;
+                const int yy = q / 15, xx = q - yy * 15;
+                const bool valid = (yy < 12) && (xx < 12);
+                const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC2 + pb * 128 + mt * 64;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(ta + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {   // 16-byte chunk index c*4+k, swizzled by the row to avoid bank conflicts
+                            const int chunk = c * 4 + k;
+                            *reinterpret_cast<uint4 *>(S + q * 128 + ((chunk ^ (q & 7)) << 4)) =
+                                make_uint4(pack_bf16(__uint_as_float(r[8 * k + 0]), __uint_as_float(r[8 * k + 1])),
+                                           pack_bf16(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3])),
+                                           pack_bf16(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
+                                           pack_bf16(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&acc2_empty[pb]);
+            ptx::named_bar_sync(1, 128);
+            // 36 pooled pixels x 8 chunks of 8 channels
+            for (int item = t128; item < 288; item += 128) {
+                const int pp = item >> 3, chunk = item & 7;
+                const int py = pp / 6, px = pp - py * 6;
+                const int q0 = (2 * py) * 15 + 2 * px;
+                auto ld = [&](int q) { return *reinterpret_cast<const uint4 *>(S + q * 128 + ((chunk ^ (q & 7)) << 4)); };
+                const uint4 a = ld(q0), b = ld(q0 + 1), c = ld(q0 + 15), d = ld(q0 + 16);
+                uint32_t o[4];
+                const uint32_t *pa = &a.x, *pb2 = &b.x, *pc = &c.x, *pd = &d.x;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const __nv_bfloat162 m01 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pa + k), *reinterpret_cast<const __nv_bfloat162 *>(pb2 + k));
+                    const __nv_bfloat162 m23 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pc + k), *reinterpret_cast<const __nv_bfloat162 *>(pd + k));
+                    const float2 f = __bfloat1622float2(__hmax2(m01, m23));
+                    const int co = chunk * 8 + 2 * k;
+                    o[k] = pack_bf16(tanh_fast(f.x + bias2[co]), tanh_fast(f.y + bias2[co + 1]));
+                }
+                *reinterpret_cast<uint4 *>(p2_out + crop * P2_N + pp * 64 + chunk * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            ptx::named_bar_sync(1, 128);
+        }
+    } else if (warp >= 12) {
+        // ===================== loader: fp32 crop -> two bf16 image copies =====================
+        const int t = threadIdx.x - 12 * 32;  // 0..127
+        for (int it = 0; it < my_crops; it++) {
+            const int ib = it & 1;
+            const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const float4 *src = reinterpret_cast<const float4 *>(x + crop * N_IN);
+            float4 v[4][3];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = t + 128 * k;  // 8-pixel chunk index
+                v[k][0] = __ldg(src + 2 * j);
+                v[k][1] = __ldg(src + 2 * j + 1);
+                v[k][2] = (j < 511) ? __ldg(src + 2 * j + 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            ptx::mbar_wait(&img_empty[ib], ((it >> 1) & 1) ^ 1);
+            uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = t + 128 * k;
+                const uint32_t lo0 = pack_bf16(v[k][0].x, v[k][0].y), lo1 = pack_bf16(v[k][0].z, v[k][0].w);
+                const uint32_t mi0 = pack_bf16(v[k][1].x, v[k][1].y), mi1 = pack_bf16(v[k][1].z, v[k][1].w);
+                const uint32_t hi0 = pack_bf16(v[k][2].x, v[k][2].y), hi1 = pack_bf16(v[k][2].z, v[k][2].w);
+                *reinterpret_cast<uint4 *>(img + j * 16) = make_uint4(lo0, lo1, mi0, mi1);             // pixels 8j .. 8j+7
+                *reinterpret_cast<uint4 *>(img + IMG_COPY + j * 16) = make_uint4(mi0, mi1, hi0, hi1);  // pixels 8j+4 .. 8j+11
+            }
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&img_full[ib]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// Build the two pre-laid-out weight images from the fp32 master weights.
+//  b1: row nrow = pos*16 + co (pos = dy*4+dx), 64 k = (r,c) of the 8x8 patch; value = w1[co][r-dy][c-dx]
+//      inside the 5x5 support, else 0; 128-byte rows, 16-byte chunk r stored at chunk (r ^ (nrow & 7)).
+//  b2: [tap][kchunk][co][8 ci] bf16 (16-byte rows): the un-swizzled K-major core-matrix order.
+__global__ void __launch_bounds__(256) build_conv_images(const float *__restrict__ params, uint8_t *__restrict__ b1, uint8_t *__restrict__ b2)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < 256 * 64) {
+        const int nrow = i >> 6, k = i & 63;
+        const int pos = nrow >> 4, co = nrow & 15, dy = pos >> 2, dx = pos & 3;
+        const int r = k >> 3, c = k & 7;
+        const int ky = r - dy, kx = c - dx;
+        const float v = (ky >= 0 && ky < 5 && kx >= 0 && kx < 5) ? params[OFF_C1W + co * 25 + ky * 5 + kx] : 0.f;
+        reinterpret_cast<__nv_bfloat16 *>(b1 + nrow * 128 + ((r ^ (nrow & 7)) << 4))[c] = __float2bfloat16_rn(v);
+    }
+    if (i < 16 * 2 * 64 * 8) {
+        const int ci8 = i & 7, co = (i >> 3) & 63, kc = (i >> 9) & 1, tap = i >> 10;
+        const int ci = kc * 8 + ci8;
+        reinterpret_cast<__nv_bfloat16 *>(b2)[i] = __float2bfloat16_rn(params[OFF_C2W + co * 256 + ci * 16 + tap]);
+    }
+}
+
+int tc_conv_init(Net &net)
+{
+    TcState *t = net.tc;
+    HP_CUDA_TRY(cudaMalloc((void **)&t->b1_img, 32768));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->b2_img, 32768));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
+    return 0;
+}
+
+int tc_conv_refresh(Net &net, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    build_conv_images<<<64, 256, 0, s>>>(net.params, t->b1_img, t->b2_img);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    const int grid = (int)(n < t->num_sms ? n : t->num_sms);
+    tc_conv_kernel<<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+}  // namespace hp

@@ -169,6 +169,13 @@ HP_API int hp_dp_shutdown(hp_net *net);
 
 /* Number of kernels this library has launched on behalf of `net` so far. */
 HP_API int64_t hp_launch_count(const hp_net *net);
+/* Per-stage device timing (CUDA events recorded on the caller's stream, read after a sync).
+ * hp_profile(net, 1) starts recording, hp_profile(net, 0) stops; hp_profile_read returns, for
+ * stage i < n_stages, the summed milliseconds and the number of intervals since recording
+ * started.  Stages of the tensor-core Eval: 0 conv stages, 1 fc1 GEMM, 2 fc2 GEMM + softmax;
+ * of the FP32 Eval: 0 conv stages, 1 fc1, 2 fc2, 3 softmax. */
+HP_API int hp_profile(hp_net *net, int enable);
+HP_API int hp_profile_read(hp_net *net, int n_stages, double *total_ms, int64_t *intervals);
 /* Peek at an intermediate of the last forward/backward pass (tests only):
  * which = 3 pooled conv1 stage [n][3600], 6 pooled conv2 stage [n][2304],
  * 8 fc1+tanh [n][2048]; copies n*len floats to HOST. */
