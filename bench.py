@@ -43,41 +43,66 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled DURING the timed region.  Uses NVML directly (about a
+    millisecond per sample, so even a 20 ms timed region gets samples); falls back to polling
+    nvidia-smi.  mark_begin()/mark_end() bracket the timed region; only samples inside count."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.t_begin, self.t_end = None, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.perf_counter(), float(sm), float(mx), int(rs)))
+                time.sleep(0.001)
+        except Exception:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            while not self.stop_flag:
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.rows.append((time.perf_counter(), float(out[0]), float(out[1]), int(out[2].strip(), 16)))
+                except Exception:
+                    pass
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def summary(self):
         self.stop_flag = True
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        sm.sort()
-        # median over the busier half of the samples = "under load"
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in self.rows if self.t_begin is not None and self.t_begin <= r[0] <= (self.t_end or 1e30)]
+        rows = inside or self.rows
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[3]
+        reasons = [name for name, bit in self.REASONS if bits & bit]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": rows[0][2] if rows else None, "reasons": reasons,
+                "samples": len(inside), "source": "nvml, sampled inside the timed region" if inside else "outside timed region"}
 
 
 def cpu_baseline_eval(sample_crops, threads):
@@ -130,7 +155,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="crops per GPU per step")
@@ -195,11 +220,13 @@ def main():
     net.profile(True)
     l0 = net.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for _ in range(K):
         net.eval_batch_device(x.data_ptr(), B, y.data_ptr(), precision=hp.PRECISION_TENSOR, stream=stream)
     e1.record()
     barrier()
+    sampler.mark_end()
     launches = net.launch_count() - l0
     stage_ms, stage_cnt = net.profile_read(3)
     net.profile(False)
