@@ -31,11 +31,12 @@ namespace hp {
 constexpr int64_t TC_CHUNK = 16384;  // crops per pass of the tensor-core path (activation workspace bound)
 
 // ---- GEMM tile configuration -----------------------------------------------------------
-constexpr int BM = 128, BN = 256, BK = 64, UK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;  // UMMA K = 16 bf16 per instruction
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES = BN * BK * 2;            // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_BYTES = 4096;                 // per-warp output staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by row
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 256;
 
 enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1 };
@@ -84,6 +85,13 @@ __device__ __forceinline__ float tanh_fast(float x)
     return y;
 }
 
+__device__ __forceinline__ float ex2_fast(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ============================================================================
 // C[M x N] = A[M x K] * Bt[N x K]^T  (+ fused epilogue); A, Bt bf16 K-major via TMA.
 // ============================================================================
@@ -94,7 +102,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint8_t *staging = smem + STAGES * STAGE_BYTES;  // [4 epilogue warps][2][STG_BYTES]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(staging + 8 * STG_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full = empty_bar + STAGES;   // [2]
     uint64_t *tmem_empty = tmem_full + 2;       // [2]
@@ -145,33 +154,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+        // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < num_kb; kb++) {
+                ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; kb++) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
+                if (ptx::elect_one()) {
                     const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t adesc = ptx::make_desc_sw128(sa);
                     const uint64_t bdesc = ptx::make_desc_sw128(sa + A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / UK; k++) {
-                        // advance 16 bf16 = 32 B along K inside the 128B-swizzled row: +2 in the >>4 address field
-                        ptx::umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    }
+                    // advance 16 bf16 = 32 B along K inside the 128B-swizzled row: +2 in the >>4 address field
+                    if (kb == 0) ptx::umma_f16_c<false>(tmem_d, adesc, bdesc, idesc);
+                    else ptx::umma_f16_c<true>(tmem_d, adesc, bdesc, idesc);
+                    ptx::umma_f16_c<true>(tmem_d, adesc + 2, bdesc + 2, idesc);
+                    ptx::umma_f16_c<true>(tmem_d, adesc + 4, bdesc + 4, idesc);
+                    ptx::umma_f16_c<true>(tmem_d, adesc + 6, bdesc + 6, idesc);
                     ptx::umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[as]);
                 }
-                ptx::umma_commit(&tmem_full[as]);
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -184,34 +195,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(&tmem_full[as], aphase);
             ptx::tc_fence_after();
-            const int row = m_blk * BM + ew * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
             const float *bptr = bias + n_blk * BN;
+            uint8_t *stg = staging + ew * 2 * STG_BYTES;
+            // stage one 32-row x 128-byte segment (this thread's row: 8 x 16 B) and write it out coalesced:
+            // each store instruction then covers 4 rows x 128 contiguous bytes instead of 32 scattered rows
+            auto flush = [&](int buf, const uint4 (&v)[8], uint8_t *gbase /*row 0 of this warp's tile, segment start*/, size_t row_pitch) {
+                uint8_t *sb = stg + buf * STG_BYTES;
+#pragma unroll
+                for (int q = 0; q < 8; q++) *reinterpret_cast<uint4 *>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) = v[q];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = i * 4 + (lane >> 3), cq = lane & 7;
+                    const uint4 val = *reinterpret_cast<const uint4 *>(sb + r * 128 + ((cq ^ (r & 7)) << 4));
+                    if (m_blk * BM + ew * 32 + r < M) *reinterpret_cast<uint4 *>(gbase + (size_t)r * row_pitch + cq * 16) = val;
+                }
+            };
             if (EPI == TC_EPI_TANH_BF16) {
-                __nv_bfloat16 *orow = reinterpret_cast<__nv_bfloat16 *>(out) + (size_t)row * N + n_blk * BN;
+                uint8_t *gtile = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 2;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
-                    uint32_t r[32];
-                    ptx::tmem_ld32(taddr + c * 32, r);
-                    ptx::tmem_ld_wait();
-                    uint32_t packed[16];
+                for (int c = 0; c < BN / 64; c++) {   // 64 columns = 128 B of bf16 per row
+                    uint4 v[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float2 bv = *reinterpret_cast<const float2 *>(bptr + c * 32 + j);
-                        const float v0 = tanh_fast(__uint_as_float(r[j]) + bv.x);
-                        const float v1 = tanh_fast(__uint_as_float(r[j + 1]) + bv.y);
-                        __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                        packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
-                    }
-                    if (row < M) {
+                    for (int h = 0; h < 2; h++) {
+                        uint32_t r[32];
+                        ptx::tmem_ld32(taddr + c * 64 + h * 32, r);
+                        ptx::tmem_ld_wait();
+                        uint32_t packed[16];
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            *reinterpret_cast<uint4 *>(orow + c * 32 + q * 8) =
-                                make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+                        for (int j = 0; j < 32; j += 2) {
+                            const float2 bv = *reinterpret_cast<const float2 *>(bptr + c * 64 + h * 32 + j);
+                            const float v0 = tanh_fast(__uint_as_float(r[j]) + bv.x);
+                            const float v1 = tanh_fast(__uint_as_float(r[j + 1]) + bv.y);
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+                            packed[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) v[h * 4 + q] = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
                     }
+                    flush(c & 1, v, gtile + c * 128, (size_t)N * 2);
                 }
             } else {
-                float *orow = reinterpret_cast<float *>(out) + (size_t)row * N + n_blk * BN;
+                uint8_t *gtile = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 4;
                 const bool big = (n_blk * BN) < N_BIG_SPANS * BIG_SPAN;  // one 256-wide span vs sixteen 16-wide spans
                 constexpr float LOG2E = 1.4426950408889634f;
                 float inv = 0.f;
@@ -223,18 +249,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ptx::tmem_ld32(taddr + c * 32, r);
                         ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; j++) sum += exp2f((__uint_as_float(r[j]) + bptr[c * 32 + j]) * LOG2E);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bv = *reinterpret_cast<const float4 *>(bptr + c * 32 + j);
+                            sum += ex2_fast((__uint_as_float(r[j]) + bv.x) * LOG2E) + ex2_fast((__uint_as_float(r[j + 1]) + bv.y) * LOG2E) +
+                                   ex2_fast((__uint_as_float(r[j + 2]) + bv.z) * LOG2E) + ex2_fast((__uint_as_float(r[j + 3]) + bv.w) * LOG2E);
+                        }
                     }
                     inv = 1.0f / sum;
                 }
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = 0; c < BN / 32; c++) {   // 32 columns = 128 B of fp32 per row
                     uint32_t r[32];
                     ptx::tmem_ld32(taddr + c * 32, r);
                     ptx::tmem_ld_wait();
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = exp2f((__uint_as_float(r[j]) + bptr[c * 32 + j]) * LOG2E);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(bptr + c * 32 + j);
+                        v[j] = ex2_fast((__uint_as_float(r[j]) + bv.x) * LOG2E);
+                        v[j + 1] = ex2_fast((__uint_as_float(r[j + 1]) + bv.y) * LOG2E);
+                        v[j + 2] = ex2_fast((__uint_as_float(r[j + 2]) + bv.z) * LOG2E);
+                        v[j + 3] = ex2_fast((__uint_as_float(r[j + 3]) + bv.w) * LOG2E);
+                    }
                     float i0 = inv, i1 = inv;
                     if (!big) {
                         float s0 = 0.f, s1 = 0.f;
@@ -243,14 +279,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         i0 = 1.0f / s0;
                         i1 = 1.0f / s1;
                     }
-                    if (row < M) {
+                    uint4 o[8];
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float sc = (q < 4) ? i0 : i1;
-                            *reinterpret_cast<float4 *>(orow + c * 32 + q * 4) =
-                                make_float4(v[q * 4] * sc, v[q * 4 + 1] * sc, v[q * 4 + 2] * sc, v[q * 4 + 3] * sc);
-                        }
+                    for (int q = 0; q < 8; q++) {
+                        const float sc = (q < 4) ? i0 : i1;
+                        o[q] = make_uint4(__float_as_uint(v[q * 4] * sc), __float_as_uint(v[q * 4 + 1] * sc), __float_as_uint(v[q * 4 + 2] * sc),
+                                          __float_as_uint(v[q * 4 + 3] * sc));
                     }
+                    flush(c & 1, o, gtile + c * 128, (size_t)N * 4);
                 }
             }
             ptx::tc_fence_before();

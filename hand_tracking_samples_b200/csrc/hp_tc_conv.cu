@@ -23,7 +23,9 @@
 //
 // Warp roles (512 threads, 1 CTA/SM, crops strided over the grid):
 //   warp 0      loads the two 32 KB weight images with cp.async.bulk; allocates TMEM
-//   warp 1      MMA issuer: conv1(crop i+1) then conv2(crop i), software-pipelined by one crop
+//   warp 1      conv1 MMA issuer (16 MMAs M128 N128 K16 per crop)
+//   warp 2      conv2 MMA issuer (32 MMAs M128 N64 K16 per crop); two issuers because at 32-64 tensor
+//               cycles per instruction a single issuing thread, not the tensor pipe, sets the pace
 //   warps 4-7   epilogue 1: TMEM -> running max over window positions -> +bias, tanh -> p1 planes (smem)
 //   warps 8-11  epilogue 2: TMEM -> bf16 staging -> 2x2 max, +bias, tanh -> global features
 //   warps 12-15 loader: fp32 crop from global -> two bf16 image copies in smem (double-buffered)
@@ -70,6 +72,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+
+#ifdef HP_CONV_TRACE
+__device__ long long g_conv_trace[64 * 1024];
+#define TRACE(role, it, ev)                                                                       \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && lane == 0 && (it) < 24) g_conv_trace[((role) * 24 + (it)) * 16 + (ev)] = clock64(); \
+    } while (0)
+#else
+#define TRACE(role, it, ev) do {} while (0)
+#endif
 
 __global__ void __launch_bounds__(cv::THREADS, 1)
 tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, const uint8_t *__restrict__ b2_img,
@@ -128,57 +140,73 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             ptx::bulk_load_1d(smem + OFF_B2, b2_img, 32768, wgt_full);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = ptx::make_idesc_bf16(128, 128);
-            constexpr uint32_t idesc2 = ptx::make_idesc_bf16(128, 64);
-            ptx::mbar_wait(wgt_full, 0);
-            const uint32_t sB1 = ptx::smem_u32(smem + OFF_B1), sB2 = ptx::smem_u32(smem + OFF_B2);
-            auto conv2 = [&](int it) {
-                const int pb = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                ptx::mbar_wait(&p1_full[pb], ph);
-                ptx::mbar_wait(&acc2_empty[pb], ph ^ 1);
+        // ===================== conv1 MMA issuer =====================
+        // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform
+        // registers; one elected lane issues.  16 MMAs per crop, fully unrolled.
+        constexpr uint32_t idesc1 = ptx::make_idesc_bf16(128, 128);
+        ptx::mbar_wait(wgt_full, 0);
+        const uint32_t sB1 = ptx::smem_u32(smem + OFF_B1);
+        const uint64_t bd0 = ptx::make_desc_sw128(sB1);
+        for (int it = 0; it < my_crops; it++) {
+            const int ib = it & 1;
+            TRACE(0, it, 0);
+            ptx::mbar_wait(&img_full[ib], (it >> 1) & 1);
+            ptx::tc_fence_after();
+            TRACE(0, it, 1);
+            const uint64_t ad0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_IMG + ib * IMG_BUF), 128, 512);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int e = g >> 1, half = g & 1;        // e: pooled-column parity (which image copy)
+                const uint32_t u = (uint32_t)(it * 2 + e);  // use count of accumulator `half`
+                ptx::mbar_wait(&acc1_empty[half], (u & 1) ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t sP = ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF);
-#pragma unroll 1
+                TRACE(0, it, 2 + 2 * g);
+                if (ptx::elect_one()) {
+                    const uint32_t d = tmem_base + ACC1 + half * 128;
+                    const uint64_t ad = ad0 + ((e * IMG_COPY) >> 4), bd = bd0 + ((half * 16384) >> 4);
+                    ptx::umma_f16_c<false>(d, ad, bd, idesc1);
+                    ptx::umma_f16_c<true>(d, ad + (256 >> 4), bd + 2, idesc1);
+                    ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
+                    ptx::umma_f16_c<true>(d, ad + (768 >> 4), bd + 6, idesc1);
+                    ptx::umma_commit(&acc1_full[half]);
+                    if (g == 3) ptx::umma_commit(&img_empty[ib]);
+                }
+                __syncwarp();
+                TRACE(0, it, 3 + 2 * g);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== conv2 MMA issuer: 2 M tiles x 16 taps per crop =====================
+        constexpr uint32_t idesc2 = ptx::make_idesc_bf16(128, 64);
+        ptx::mbar_wait(wgt_full, 0);
+        const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_B2), 1024, 128);
+        for (int it = 0; it < my_crops; it++) {
+            const int pb = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            TRACE(1, it, 0);
+            ptx::mbar_wait(&p1_full[pb], ph);
+            TRACE(1, it, 1);
+            ptx::mbar_wait(&acc2_empty[pb], ph ^ 1);
+            ptx::tc_fence_after();
+            TRACE(1, it, 2);
+            if (ptx::elect_one()) {
+                const uint64_t ad0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF), P1_PLANE, 128);
+#pragma unroll
                 for (int mt = 0; mt < 2; mt++) {
                     const uint32_t d = tmem_base + ACC2 + pb * 128 + mt * 64;
 #pragma unroll
                     for (int tap = 0; tap < 16; tap++) {
-                        const int shift = (tap >> 2) * 15 + (tap & 3);
-                        const uint64_t ad = ptx::make_desc_nosw(sP + (mt * 128 + shift) * 16, P1_PLANE, 128);
-                        const uint64_t bd = ptx::make_desc_nosw(sB2 + tap * 2048, 1024, 128);
-                        ptx::umma_f16(d, ad, bd, idesc2, tap != 0);
+                        const int shift = (tap >> 2) * 15 + (tap & 3);   // rows: ky*15 + kx
+                        const uint64_t ad = ad0 + (mt * 128 + shift), bd = bd0 + tap * (2048 >> 4);
+                        if (tap == 0) ptx::umma_f16_c<false>(d, ad, bd, idesc2);
+                        else ptx::umma_f16_c<true>(d, ad, bd, idesc2);
                     }
                 }
                 ptx::umma_commit(&acc2_full[pb]);
                 ptx::umma_commit(&p1_empty[pb]);
-            };
-            for (int it = 0; it < my_crops; it++) {
-                const int ib = it & 1;
-                ptx::mbar_wait(&img_full[ib], (it >> 1) & 1);
-                ptx::tc_fence_after();
-                const uint32_t sI = ptx::smem_u32(smem + OFF_IMG + ib * IMG_BUF);
-#pragma unroll 1
-                for (int g = 0; g < 4; g++) {
-                    const int e = g >> 1, half = g & 1;       // e: pooled-column parity (which image copy)
-                    const uint32_t u = (uint32_t)(it * 2 + e); // use count of accumulator `half`
-                    ptx::mbar_wait(&acc1_empty[half], (u & 1) ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t d = tmem_base + ACC1 + half * 128;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const uint64_t ad = ptx::make_desc_nosw(sI + e * IMG_COPY + ks * 256, 128, 512);
-                        const uint64_t bd = ptx::make_desc_sw128(sB1 + half * 16384) + 2 * ks;
-                        ptx::umma_f16(d, ad, bd, idesc1, ks != 0);
-                    }
-                    ptx::umma_commit(&acc1_full[half]);
-                }
-                ptx::umma_commit(&img_empty[ib]);
-                if (it > 0) conv2(it - 1);
             }
-            if (my_crops > 0) conv2(my_crops - 1);
+            __syncwarp();
+            TRACE(1, it, 3);
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue 1: conv1 accumulators -> p1 planes =====================
@@ -188,7 +216,9 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
         for (int it = 0; it < my_crops; it++) {
             const int pb = it & 1;
             uint8_t *planes = smem + OFF_P1 + pb * P1_BUF;
+            if (ew == 0) TRACE(2, it, 0);
             ptx::mbar_wait(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
+            if (ew == 0) TRACE(2, it, 1);
 #pragma unroll 1
             for (int e = 0; e < 2; e++) {
                 float mx[16];
@@ -197,6 +227,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                 for (int half = 0; half < 2; half++) {
                     ptx::mbar_wait(&acc1_full[half], u & 1);
                     ptx::tc_fence_after();
+                    if (ew == 0) TRACE(2, it, 2 + 2 * (e * 2 + half));
                     const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC1 + half * 128;
 #pragma unroll
                     for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
@@ -214,6 +245,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
+                    if (ew == 0) TRACE(2, it, 3 + 2 * (e * 2 + half));
                 }
                 const int px = 2 * pxh + e;
                 if (py < 15 && px < 15) {
@@ -229,6 +261,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             ptx::fence_proxy_async();   // generic-proxy stores -> visible to the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
+            if (ew == 0) TRACE(2, it, 10);
         }
     } else if (warp >= 8 && warp < 12) {
         // ===================== epilogue 2: conv2 accumulators -> pooled features =====================
@@ -238,8 +271,10 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
         for (int it = 0; it < my_crops; it++) {
             const int pb = it & 1;
             const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            if (ew == 0) TRACE(3, it, 0);
             ptx::mbar_wait(&acc2_full[pb], (it >> 1) & 1);
             ptx::tc_fence_after();
+            if (ew == 0) TRACE(3, it, 1);
 #pragma unroll 1
             for (int mt = 0; mt < 2; mt++) {
                 const int q = mt * 128 + t128;
@@ -267,6 +302,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&acc2_empty[pb]);
+            if (ew == 0) TRACE(3, it, 2);
             ptx::named_bar_sync(1, 128);
             // 36 pooled pixels x 8 chunks of 8 channels
             for (int item = t128; item < 288; item += 128) {
@@ -288,6 +324,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                 *reinterpret_cast<uint4 *>(p2_out + crop * P2_N + pp * 64 + chunk * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
             ptx::named_bar_sync(1, 128);
+            if (ew == 0) TRACE(3, it, 3);
         }
     } else if (warp >= 12) {
         // ===================== loader: fp32 crop -> two bf16 image copies =====================
@@ -304,7 +341,9 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                 v[k][1] = __ldg(src + 2 * j + 1);
                 v[k][2] = (j < 511) ? __ldg(src + 2 * j + 2) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (warp == 12) TRACE(4, it, 0);
             ptx::mbar_wait(&img_empty[ib], ((it >> 1) & 1) ^ 1);
+            if (warp == 12) TRACE(4, it, 1);
             uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -317,6 +356,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             }
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&img_full[ib]);
+            if (warp == 12) TRACE(4, it, 2);
         }
     }
     ptx::tc_fence_before();
@@ -348,6 +388,13 @@ __global__ void __launch_bounds__(256) build_conv_images(const float *__restrict
         reinterpret_cast<__nv_bfloat16 *>(b2)[i] = __float2bfloat16_rn(params[OFF_C2W + co * 256 + ci * 16 + tap]);
     }
 }
+
+#ifdef HP_CONV_TRACE
+extern "C" __attribute__((visibility("default"))) int hp_debug_conv_trace(long long *out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_conv_trace, sizeof(long long) * n);
+}
+#endif
 
 int tc_conv_init(Net &net)
 {
