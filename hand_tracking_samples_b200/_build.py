@@ -51,5 +51,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
+ROOT = os.path.dirname(HERE)
+DROPIN_BIN = os.path.join(ROOT, "tests", "_bin", "dropin_main")
+
+
+def build_dropin_test(reference_root="/root/reference"):
+    """g++-compile the C++ drop-in checks against include/handposedd/cnn.h (no CUDA needed to build):
+    tests/_bin/dropin_main (the PoseInitializerCNN call sequence, always) and tests/_bin/ht_dropin (the
+    reference's own include/handtrack.h compiled UNMODIFIED against the drop-in header, only where the
+    reference tree is present).  The binaries travel to the GPU box; the reference tree does not."""
+    os.makedirs(os.path.dirname(DROPIN_BIN), exist_ok=True)
+    common = ["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "include"), "-L" + HERE, "-lhandposedd",
+              "-Wl,-rpath,$ORIGIN/../../hand_tracking_samples_b200"]
+    subprocess.check_call(common[:4] + [os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-o", DROPIN_BIN] + common[4:])
+    out = [DROPIN_BIN]
+    if os.path.isdir(reference_root):
+        ht = os.path.join(ROOT, "tests", "_bin", "ht_dropin")
+        subprocess.check_call(common[:4] + ["-fpermissive", "-Wno-narrowing", "-w", "-I" + reference_root,
+                                            os.path.join(ROOT, "tests", "cpp", "handtrack_dropin.cpp"), "-o", ht] + common[4:] + ["-lpthread"])
+        out.append(ht)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
