@@ -7,6 +7,7 @@
 // (third_party/cnn.h:550-593) and PoseInitializerCNN (include/handtrack.h:103-130).
 #include "../../include/handposedd.h"
 #include "hp_common.cuh"
+#include "hp_tc.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -225,8 +226,12 @@ static int eval_device(Net &net, const float *x, int64_t n, float *y, int precis
 static int grad_device(Net &net, const float *x, const float *t, int64_t n, float *mse, int precision, cudaStream_t s)
 {
     if (precision == HP_PRECISION_TENSOR) {
-        set_error("tensor-core training path not built yet; use HP_PRECISION_FP32");
-        return HP_ERR_UNSUPPORTED;
+        for (int64_t b = 0; b < n; b += FP32_CHUNK) {
+            const int64_t m = std::min<int64_t>(FP32_CHUNK, n - b);
+            if (int rc = tc_train_grad(net, x + b * N_IN, t + b * N_OUT, m, mse ? mse + b : nullptr, b > 0, s)) return rc;
+        }
+        net.last_n = std::min<int64_t>(n, FP32_CHUNK);
+        return 0;
     }
     for (int64_t b = 0; b < n; b += FP32_CHUNK) {
         const int64_t m = std::min<int64_t>(FP32_CHUNK, n - b);

@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(256) tanh_pool2(const float *__restrict__ c2, 
     for (int e = threadIdx.x; e < P2_N; e += 256) {
         p2[crop * P2_N + e] = sv[e];
         idx2[crop * P2_N + e] = si[e];
-        if (p2_bf) p2_bf[crop * P2_N + e] = __float2bfloat16_rn(sv[e]);
+        // bf16 copy in HWC order (pp*64 + co), the feature order of the tensor-core fc1
+        if (p2_bf) p2_bf[crop * P2_N + e] = __float2bfloat16_rn(sv[(e & 63) * 36 + (e >> 6)]);
     }
 }
 
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ 
 
 // LMaxPool::backward (cnn.h:149-164) after TanH::df was folded into g2 by the fc1
 // dX epilogue: dense dL/dc2[(n*144+pos)][co] = g2 at the winner, 0 elsewhere.
+template <bool G2_HWC>
 __global__ void __launch_bounds__(256) scatter_e2(const float *__restrict__ g2, const uint8_t *__restrict__ idx2,
                                                   float *__restrict__ e2)
 {
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(256) scatter_e2(const float *__restrict__ g2, 
         const int y = pos / C2_W, xx = pos % C2_W;
         const int pp = (y >> 1) * P2_W + (xx >> 1), off = (y & 1) * 2 + (xx & 1);
         const int j = co * 36 + pp;
-        dst[e] = (si[j] == off) ? sg[j] : 0.f;
+        dst[e] = (si[j] == off) ? sg[G2_HWC ? pp * 64 + co : j] : 0.f;
     }
 }
 
@@ -616,6 +618,49 @@ static int colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, b
     return 0;
 }
 
+// conv2 and conv1 backward from g2 = dL/d(conv2 pre-activation) at the pool winners ([n][2304], CHW or HWC order)
+static int fp32_conv_backward_impl(Net &net, const float *x, int64_t n, const float *g2, bool g2_hwc, bool accumulate, cudaStream_t s)
+{
+    Workspace &w = net.ws;
+    float *G = net.grads;
+    const int acc = accumulate ? 1 : 0;
+    // ---- conv2: dense dL/dc2 (reuses w.c2), dB, dW (split-K over positions), dcol
+    if (g2_hwc) scatter_e2<true><<<(unsigned)n, 256, 0, s>>>(g2, w.idx2, w.c2);
+    else scatter_e2<false><<<(unsigned)n, 256, 0, s>>>(g2, w.idx2, w.c2);
+    LAUNCH_CHECK(net);
+    const int64_t R = n * C2_POS;
+    if (int rc = colsum(net, w.c2, R, C2_CO, G + OFF_C2B, accumulate, s)) return rc;
+    {
+        int splits = (int)((R + 1151) / 1152);  // 8 crops per split
+        if (splits > 128) splits = 128;
+        int klen = (int)((R + splits - 1) / splits);
+        klen = (klen + 15) / 16 * 16;
+        splits = (int)((R + klen - 1) / klen);
+        GemmArgs g{C2_CO, C2_KDIM, (int)R, w.c2, C2_CO, w.col, C2_KDIM, w.partial, C2_KDIM, nullptr, nullptr, klen, 0};
+        if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, splits, s)) return rc;
+        reduce_c2w<<<C2_CO, 256, 0, s>>>(G + OFF_C2W, w.partial, splits, acc);
+        LAUNCH_CHECK(net);
+    }
+    {
+        GemmArgs g{(int)R, C2_KDIM, C2_CO, w.c2, C2_CO, w.w2p, C2_KDIM, w.colgrad, C2_KDIM, nullptr, nullptr, C2_CO, 0};
+        if (int rc = launch_sgemm<128, true, false, EPI_STORE>(net, g, 1, s)) return rc;
+    }
+    col2im_g1<<<(unsigned)n, 256, 0, s>>>(w.colgrad, w.p1, w.g1);
+    LAUNCH_CHECK(net);
+    // ---- conv1 (no dX: CNN::Train never calls layer 0's backward, cnn.h:571)
+    {
+        int per_block = (int)((n + 147) / 148);
+        if (per_block < 1) per_block = 1;
+        int blocks = (int)((n + per_block - 1) / per_block);
+        conv1_wgrad<<<blocks, 256, 0, s>>>(x, w.g1, w.idx1, n, per_block, w.partial);
+        LAUNCH_CHECK(net);
+        reduce_partials<<<2, 256, 0, s>>>(G + OFF_C1W, w.partial, blocks, 416, acc);
+        LAUNCH_CHECK(net);
+    }
+    return 0;
+}
+
+
 // Backward + weight-gradient sums into net.grads (W -= alpha*grads is sgd_apply).
 // Order fc2 -> fc1 -> conv2 -> conv1 so that the large FC buckets are ready first
 // for the data-parallel all-reduce (events ev_bucket[0..2]).
@@ -649,40 +694,19 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         GemmArgs g{(int)n, FC1_IN, FC1_OUT, w.da1, FC1_OUT, P + OFF_F1W, FC1_OUT, w.g2, FC1_IN, nullptr, w.p2, FC1_OUT, 0};
         if (int rc = launch_sgemm<128, true, true, EPI_DTANH>(net, g, 1, s)) return rc;
     }
-    // ---- conv2: dense dL/dc2 (reuses w.c2), dB, dW (split-K over positions), dcol
-    scatter_e2<<<(unsigned)n, 256, 0, s>>>(w.g2, w.idx2, w.c2);
-    LAUNCH_CHECK(net);
-    const int64_t R = n * C2_POS;
-    if (int rc = colsum(net, w.c2, R, C2_CO, G + OFF_C2B, accumulate, s)) return rc;
-    {
-        int splits = (int)((R + 1151) / 1152);  // 8 crops per split
-        if (splits > 128) splits = 128;
-        int klen = (int)((R + splits - 1) / splits);
-        klen = (klen + 15) / 16 * 16;
-        splits = (int)((R + klen - 1) / klen);
-        GemmArgs g{C2_CO, C2_KDIM, (int)R, w.c2, C2_CO, w.col, C2_KDIM, w.partial, C2_KDIM, nullptr, nullptr, klen, 0};
-        if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, splits, s)) return rc;
-        reduce_c2w<<<C2_CO, 256, 0, s>>>(G + OFF_C2W, w.partial, splits, acc);
-        LAUNCH_CHECK(net);
-    }
-    {
-        GemmArgs g{(int)R, C2_KDIM, C2_CO, w.c2, C2_CO, w.w2p, C2_KDIM, w.colgrad, C2_KDIM, nullptr, nullptr, C2_CO, 0};
-        if (int rc = launch_sgemm<128, true, false, EPI_STORE>(net, g, 1, s)) return rc;
-    }
-    col2im_g1<<<(unsigned)n, 256, 0, s>>>(w.colgrad, w.p1, w.g1);
-    LAUNCH_CHECK(net);
-    // ---- conv1 (no dX: CNN::Train never calls layer 0's backward, cnn.h:571)
-    {
-        int per_block = (int)((n + 147) / 148);
-        if (per_block < 1) per_block = 1;
-        int blocks = (int)((n + per_block - 1) / per_block);
-        conv1_wgrad<<<blocks, 256, 0, s>>>(x, w.g1, w.idx1, n, per_block, w.partial);
-        LAUNCH_CHECK(net);
-        reduce_partials<<<2, 256, 0, s>>>(G + OFF_C1W, w.partial, blocks, 416, acc);
-        LAUNCH_CHECK(net);
-    }
+    if (int rc = fp32_conv_backward_impl(net, x, n, w.g2, false, accumulate, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));
     return 0;
+}
+
+int fp32_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s)
+{
+    return fp32_conv_backward_impl(net, x, n, g2_hwc, true, accumulate, s);
+}
+
+int fp32_colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, bool accumulate, cudaStream_t s)
+{
+    return colsum(net, in, R, ncols, dst, accumulate, s);
 }
 
 int sgd_apply(Net &net, float alpha, cudaStream_t s)

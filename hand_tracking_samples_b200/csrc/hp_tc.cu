@@ -39,7 +39,16 @@ constexpr int STG_BYTES = 4096;                 // per-warp output staging tile:
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 256;
 
-enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1 };
+enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3 };
+enum { TC_FLAG_ACCUMULATE = 1, TC_FLAG_ROWS_HWC_TO_CHW = 2 };
+
+struct EpiArgs {
+    const float *bias;         // TANH_BF16 / SOFTMAX_F32
+    void *out;                 // TANH_BF16: bf16 [M][N]; SOFTMAX_F32 / STORE_F32 / DTANH: fp32 [M][N] (DTANH: may be null)
+    __nv_bfloat16 *out2;       // DTANH: bf16 [M][N]
+    const __nv_bfloat16 *H;    // DTANH: layer output h, bf16 [M][N]: result = (1 - h*h) * acc  (TanH::df, cnn.h:32,467)
+    int flags;                 // STORE_F32: TC_FLAG_ACCUMULATE (out += acc), TC_FLAG_ROWS_HWC_TO_CHW (row k' -> (k'&63)*36 + (k'>>6))
+};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -97,9 +106,10 @@ __device__ __forceinline__ float ex2_fast(float x)
 // ============================================================================
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float *__restrict__ bias,
-               void *__restrict__ out, int M, int N, int K)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs ea, int M, int N, int K)
 {
+    const float *__restrict__ bias = ea.bias;
+    void *__restrict__ out = ea.out;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *staging = smem + STAGES * STAGE_BYTES;  // [4 epilogue warps][2][STG_BYTES]
@@ -212,6 +222,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (m_blk * BM + ew * 32 + r < M) *reinterpret_cast<uint4 *>(gbase + (size_t)r * row_pitch + cq * 16) = val;
                 }
             };
+            // fp32 variant for weight gradients: optional += and optional row permutation (HWC feature order -> .cnnb rows)
+            auto flush_grad = [&](int buf, const uint4 (&v)[8], float *gmat, int col0) {
+                uint8_t *sb = stg + buf * STG_BYTES;
+#pragma unroll
+                for (int q = 0; q < 8; q++) *reinterpret_cast<uint4 *>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) = v[q];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = i * 4 + (lane >> 3), cq = lane & 7;
+                    float4 val = *reinterpret_cast<const float4 *>(sb + r * 128 + ((cq ^ (r & 7)) << 4));
+                    int grow = m_blk * BM + ew * 32 + r;
+                    if (grow < M) {
+                        if (ea.flags & TC_FLAG_ROWS_HWC_TO_CHW) grow = (grow & 63) * 36 + (grow >> 6);
+                        float4 *gp = reinterpret_cast<float4 *>(gmat + (size_t)grow * N + col0 + cq * 4);
+                        if (ea.flags & TC_FLAG_ACCUMULATE) {
+                            const float4 o = *gp;
+                            val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                        }
+                        *gp = val;
+                    }
+                }
+            };
             if (EPI == TC_EPI_TANH_BF16) {
                 uint8_t *gtile = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 2;
 #pragma unroll 1
@@ -236,7 +268,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     flush(c & 1, v, gtile + c * 128, (size_t)N * 2);
                 }
-            } else {
+            } else if (EPI == TC_EPI_SOFTMAX_F32) {
                 uint8_t *gtile = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 4;
                 const bool big = (n_blk * BN) < N_BIG_SPANS * BIG_SPAN;  // one 256-wide span vs sixteen 16-wide spans
                 constexpr float LOG2E = 1.4426950408889634f;
@@ -289,6 +321,68 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     flush(c & 1, o, gtile + c * 128, (size_t)N * 4);
                 }
             }
+            if (EPI == TC_EPI_STORE_F32) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    uint4 o[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) o[q] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+                    flush_grad(c & 1, o, reinterpret_cast<float *>(out), n_blk * BN + c * 32);
+                }
+            }
+            if (EPI == TC_EPI_DTANH) {
+                const int row = m_blk * BM + ew * 32 + lane;
+                const int rowc = row < M ? row : M - 1;   // clamp: rows past M are computed but never stored
+                const __nv_bfloat16 *hrow = ea.H + (size_t)rowc * N + n_blk * BN;
+                uint8_t *gt32 = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 4;
+                uint8_t *gt16 = reinterpret_cast<uint8_t *>(ea.out2) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 2;
+                int fb = 0;
+#pragma unroll 1
+                for (int c = 0; c < BN / 64; c++) {
+                    uint4 ob[8];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        uint32_t r[32];
+                        ptx::tmem_ld32(taddr + c * 64 + h * 32, r);
+                        ptx::tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint4 hv = *reinterpret_cast<const uint4 *>(hrow + c * 64 + h * 32 + q * 8);
+                            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&hw[k]));
+                                v[q * 8 + 2 * k] = (1.0f - hf.x * hf.x) * __uint_as_float(r[q * 8 + 2 * k]);
+                                v[q * 8 + 2 * k + 1] = (1.0f - hf.y * hf.y) * __uint_as_float(r[q * 8 + 2 * k + 1]);
+                            }
+                        }
+                        if (out) {
+                            uint4 o[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                o[q] = make_uint4(__float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+                            flush(fb & 1, o, gt32 + (c * 64 + h * 32) * 4, (size_t)N * 4);
+                            fb++;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                __nv_bfloat162 hh = __floats2bfloat162_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
+                                pk[k] = *reinterpret_cast<uint32_t *>(&hh);
+                            }
+                            ob[h * 4 + q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                    flush(fb & 1, ob, gt16 + c * 128, (size_t)N * 2);
+                    fb++;
+                }
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
@@ -323,6 +417,89 @@ __global__ void __launch_bounds__(256) transpose_to_bf16(const float *__restrict
 }
 
 
+// fp32 W[K][N] -> bf16 Wb[K'][N] in the stored orientation (the B operand of the dX GEMMs, LFull::backward
+// cnn.h:430-437); HWC: destination row k' = pp*64+co reads source row co*36+pp.
+template <bool HWC>
+__global__ void __launch_bounds__(256) convert_rows_bf16(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wb, int N)
+{
+    const int kd = blockIdx.x;
+    const int ks = HWC ? (kd & 63) * 36 + (kd >> 6) : kd;
+    const float4 *src = reinterpret_cast<const float4 *>(w + (size_t)ks * N);
+    uint2 *dst = reinterpret_cast<uint2 *>(wb + (size_t)kd * N);
+    for (int i = threadIdx.x; i < N / 4; i += 256) {
+        const float4 v = src[i];
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        dst[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    }
+}
+
+// bf16 src[n][C] -> dst[C][ldk] (k contiguous) with zero fill for n <= k < n_pad: the K-major operands of the
+// weight-gradient GEMMs (LFull::update, cnn.h:438-445, is the contraction over the batch)
+__global__ void __launch_bounds__(256) transpose_bf16(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int n, int n_pad,
+                                                      int C, int ldk)
+{
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int k = k0 + ty + 8 * i;
+        tile[ty + 8 * i][tx] = (k < n) ? src[(size_t)k * C + c0 + tx] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int k = k0 + tx;
+        if (k < n_pad) dst[(size_t)(c0 + ty + 8 * i) * ldk + k] = tile[tx][ty + 8 * i];
+    }
+}
+
+// Train's loss (cnn.h:566-569) and LSoftMaxChunked::backward (cnn.h:512-526) from the softmax OUTPUT y:
+// e = y - t, mse = sum e^2 / 2304, per span dp = sum e*y, dlogit = y * (e - dp).  fp32 and bf16 copies.
+__global__ void __launch_bounds__(256) loss_from_y(const float *__restrict__ y, const float *__restrict__ t, float *__restrict__ dlog,
+                                                   __nv_bfloat16 *__restrict__ dlog_bf, float *__restrict__ mse)
+{
+    __shared__ float red[8];
+    const int64_t crop = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *yy = y + crop * N_OUT, *tt = t + crop * N_OUT;
+    float yv[8], e[8], se = 0.f, dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        yv[i] = yy[warp * 256 + i * 32 + lane];
+        e[i] = yv[i] - tt[warp * 256 + i * 32 + lane];
+        se += e[i] * e[i];
+        dp += e[i] * yv[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, o);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float d = yv[i] * (e[i] - dp);
+        dlog[crop * N_OUT + warp * 256 + i * 32 + lane] = d;
+        dlog_bf[crop * N_OUT + warp * 256 + i * 32 + lane] = __float2bfloat16_rn(d);
+    }
+    const float ys = yy[2048 + tid];
+    const float e2 = ys - tt[2048 + tid];
+    se += e2 * e2;
+    float dp2 = e2 * ys;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) dp2 += __shfl_xor_sync(0xffffffffu, dp2, o);
+    const float d2 = ys * (e2 - dp2);
+    dlog[crop * N_OUT + 2048 + tid] = d2;
+    dlog_bf[crop * N_OUT + 2048 + tid] = __float2bfloat16_rn(d2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (lane == 0) red[warp] = se;
+    __syncthreads();
+    if (tid == 0 && mse) {
+        float m = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) m += red[k];
+        mse[crop] = m / (float)N_OUT;
+    }
+}
+
 int tc_init(Net &net)
 {
     if (int rc = bind_driver()) return rc;
@@ -337,6 +514,12 @@ int tc_init(Net &net)
     if (int rc = make_map_bf16(&t->tm_w2t, t->w2t, FC2_OUT, FC2_IN, BN)) return rc;
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_SOFTMAX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->w1b, (size_t)FC1_OUT * FC1_IN * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->w2b, (size_t)FC2_OUT * FC2_IN * 2));
+    if (int rc = make_map_bf16(&t->tm_w1b, t->w1b, FC1_IN, FC1_OUT, BN)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w2b, t->w2b, FC2_IN, FC2_OUT, BN)) return rc;
     return tc_conv_init(net);
 }
 
@@ -346,6 +529,9 @@ void tc_destroy(Net &net)
     if (!t) return;
     if (t->w1t) cudaFree(t->w1t);
     if (t->w2t) cudaFree(t->w2t);
+    void *tb[] = {t->w1b, t->w2b, t->dlog_bf, t->da1_bf, t->h1T, t->dlogT, t->p2T, t->da1T};
+    for (void *q : tb)
+        if (q) cudaFree(q);
     if (t->b1_img) cudaFree(t->b1_img);
     if (t->b2_img) cudaFree(t->b2_img);
     if (t->p2) cudaFree(t->p2);
@@ -360,6 +546,10 @@ int tc_refresh_weights(Net &net, cudaStream_t s)
     transpose_to_bf16<true><<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, t->w1t, FC1_IN, FC1_OUT);
     LAUNCH_CHECK(net);
     transpose_to_bf16<false><<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, t->w2t, FC2_IN, FC2_OUT);
+    LAUNCH_CHECK(net);
+    convert_rows_bf16<true><<<FC1_IN, 256, 0, s>>>(net.params + OFF_F1W, t->w1b, FC1_OUT);
+    LAUNCH_CHECK(net);
+    convert_rows_bf16<false><<<FC2_IN, 256, 0, s>>>(net.params + OFF_F2W, t->w2b, FC2_OUT);
     LAUNCH_CHECK(net);
     if (int rc = tc_conv_refresh(net, s)) return rc;
     net.tc_dirty = false;
@@ -402,19 +592,116 @@ int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s
             StageTimer st(net, 1, s);
             const int tiles = m_tiles * (FC1_OUT / BN);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
-            tc_gemm_kernel<TC_EPI_TANH_BF16><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_p2, t->tm_w1t, net.params + OFF_F1B, t->h1, (int)m,
-                                                                                     FC1_OUT, FC1_IN);
+            EpiArgs ea{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0};
+            tc_gemm_kernel<TC_EPI_TANH_BF16><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_p2, t->tm_w1t, ea, (int)m, FC1_OUT, FC1_IN);
             LAUNCH_CHECK(net);
         }
         {
             StageTimer st(net, 2, s);
             const int tiles = m_tiles * (FC2_OUT / BN);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
-            tc_gemm_kernel<TC_EPI_SOFTMAX_F32><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_h1, t->tm_w2t, net.params + OFF_F2B,
-                                                                                       y_out + b * N_OUT, (int)m, FC2_OUT, FC2_IN);
+            EpiArgs ea{net.params + OFF_F2B, y_out + b * N_OUT, nullptr, nullptr, 0};
+            tc_gemm_kernel<TC_EPI_SOFTMAX_F32><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
             LAUNCH_CHECK(net);
         }
     }
+    return 0;
+}
+
+
+template <int EPI>
+static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB, const EpiArgs &ea, int M, int N, int K, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    const int tiles = ((M + BM - 1) / BM) * (N / BN);
+    const int grid = tiles < t->num_sms ? tiles : t->num_sms;
+    tc_gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, ea, M, N, K);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// hp_fp32.cu
+int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
+int fp32_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s);
+int fp32_colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, bool accumulate, cudaStream_t s);
+
+constexpr int64_t TRAIN_CAP = 2048;  // samples per pass (bounded by the FP32 conv-stage workspace)
+
+static int tc_train_ensure(Net &net)
+{
+    TcState *t = net.tc;
+    if (t->dlog_bf) return 0;
+    const int64_t cap = TRAIN_CAP;
+    HP_CUDA_TRY(cudaMalloc((void **)&t->dlog_bf, (size_t)cap * N_OUT * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->da1_bf, (size_t)cap * FC1_OUT * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->h1T, (size_t)FC1_OUT * cap * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->dlogT, (size_t)N_OUT * cap * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->p2T, (size_t)FC1_IN * cap * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->da1T, (size_t)FC1_OUT * cap * 2));
+    HP_CUDA_TRY(cudaMemset(t->dlog_bf, 0, (size_t)cap * N_OUT * 2));
+    HP_CUDA_TRY(cudaMemset(t->da1_bf, 0, (size_t)cap * FC1_OUT * 2));
+    HP_CUDA_TRY(cudaMemset(t->h1T, 0, (size_t)FC1_OUT * cap * 2));
+    HP_CUDA_TRY(cudaMemset(t->dlogT, 0, (size_t)N_OUT * cap * 2));
+    HP_CUDA_TRY(cudaMemset(t->p2T, 0, (size_t)FC1_IN * cap * 2));
+    HP_CUDA_TRY(cudaMemset(t->da1T, 0, (size_t)FC1_OUT * cap * 2));
+    if (int rc = make_map_bf16(&t->tm_dlog, t->dlog_bf, cap, N_OUT, BM)) return rc;
+    if (int rc = make_map_bf16(&t->tm_da1, t->da1_bf, cap, FC1_OUT, BM)) return rc;
+    if (int rc = make_map_bf16(&t->tm_h1T, t->h1T, FC1_OUT, cap, BM)) return rc;
+    if (int rc = make_map_bf16(&t->tm_p2T, t->p2T, FC1_IN, cap, BM)) return rc;
+    if (int rc = make_map_bf16(&t->tm_dlogT, t->dlogT, N_OUT, cap, BN)) return rc;
+    if (int rc = make_map_bf16(&t->tm_da1T, t->da1T, FC1_OUT, cap, BN)) return rc;
+    return 0;
+}
+
+// Forward + backward of one pass (n <= TRAIN_CAP) with every FC contraction on tcgen05:
+//   forward   conv stages (FFMA, bit-faithful: exact pool winners) -> fc1 -> fc2 + softmax          (tensor)
+//   backward  loss + softmax' -> fc2 dW, dX*tanh' -> fc1 dW, dX*tanh' (tensor) -> conv2 / conv1 backward (FFMA)
+// Leaves sum_b g_b in net.grads (.cnnb order).  CNN::Train, cnn.h:558-575.
+int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float *mse, bool accumulate, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    Workspace &w = net.ws;
+    float *G = net.grads;
+    if (net.tc_dirty)
+        if (int rc = tc_refresh_weights(net, s)) return rc;
+    if (int rc = tc_ensure(net, n)) return rc;
+    if (int rc = tc_train_ensure(net)) return rc;
+    if (int rc = ensure_workspace(net, n)) return rc;
+    const int M = (int)n;
+    const int n_pad = (M + BK - 1) / BK * BK;
+    const int flags = accumulate ? TC_FLAG_ACCUMULATE : 0;
+    // ---- forward
+    if (int rc = fp32_conv_stage(net, x, n, t->p2, s)) return rc;   // p2 bf16 in HWC order, winners in w.idx1 / w.idx2
+    if (int rc = launch_gemm<TC_EPI_TANH_BF16>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
+    if (int rc = launch_gemm<TC_EPI_SOFTMAX_F32>(net, t->tm_h1, t->tm_w2t, EpiArgs{net.params + OFF_F2B, w.y, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
+    // ---- loss, fc2
+    loss_from_y<<<(unsigned)n, 256, 0, s>>>(w.y, t_dev, w.dlog, t->dlog_bf, mse);
+    LAUNCH_CHECK(net);
+    if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
+    transpose_bf16<<<dim3(FC1_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->h1, t->h1T, M, n_pad, FC1_OUT, (int)TRAIN_CAP);
+    LAUNCH_CHECK(net);
+    transpose_bf16<<<dim3(N_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->dlog_bf, t->dlogT, M, n_pad, N_OUT, (int)TRAIN_CAP);
+    LAUNCH_CHECK(net);
+    // dW2[2048][2304] = h1^T * dlog
+    if (int rc = launch_gemm<TC_EPI_STORE_F32>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
+    // da1 = (dlog * W2^T) .* (1 - h1^2)
+    if (int rc = launch_gemm<TC_EPI_DTANH>(net, t->tm_dlog, t->tm_w2b, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
+    // ---- fc1
+    if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
+    transpose_bf16<<<dim3(FC1_IN / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->p2, t->p2T, M, n_pad, FC1_IN, (int)TRAIN_CAP);
+    LAUNCH_CHECK(net);
+    transpose_bf16<<<dim3(FC1_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->da1_bf, t->da1T, M, n_pad, FC1_OUT, (int)TRAIN_CAP);
+    LAUNCH_CHECK(net);
+    // dW1[k'][2048] = p2^T * da1, rows un-permuted from HWC to the reference's CHW flatten on store
+    if (int rc = launch_gemm<TC_EPI_STORE_F32>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
+                                               FC1_OUT, n_pad, s)) return rc;
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
+    // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order
+    if (int rc = launch_gemm<TC_EPI_DTANH>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+    // ---- conv stages backward on FFMA (exact winners)
+    if (int rc = fp32_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));
     return 0;
 }
 

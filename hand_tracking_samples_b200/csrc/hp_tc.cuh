@@ -11,6 +11,12 @@ struct TcState {
     __nv_bfloat16 *w2t = nullptr;  // [2304][2048] = fc2.W^T
     uint8_t *b1_img = nullptr;     // 32 KB: conv1 as pooled-window GEMM, B operand [256 (pos,co)][64 (r,c)] bf16, 128B-swizzled image
     uint8_t *b2_img = nullptr;     // 32 KB: conv2 taps, [16 taps][2 k-chunks][64 co][8 ci] bf16 (no-swizzle core matrices)
+    __nv_bfloat16 *w1b = nullptr;  // [2304 (k' HWC)][2048] = fc1.W as stored (B operand of the fc1 dX GEMM)
+    __nv_bfloat16 *w2b = nullptr;  // [2048][2304] = fc2.W as stored
+    // training activations (TRAIN_CAP samples per pass)
+    __nv_bfloat16 *dlog_bf = nullptr, *da1_bf = nullptr;            // [cap][2304], [cap][2048]
+    __nv_bfloat16 *h1T = nullptr, *dlogT = nullptr, *p2T = nullptr, *da1T = nullptr;  // [features][cap]: batch-contiguous (K-major for dW)
+    CUtensorMap tm_w1b, tm_w2b, tm_dlog, tm_da1, tm_h1T, tm_p2T, tm_dlogT, tm_da1T;
     // activations
     __nv_bfloat16 *p2 = nullptr;   // [cap][2304] pooled conv2 stage (fc1 input), HWC flatten
     __nv_bfloat16 *h1 = nullptr;   // [cap][2048] tanh(fc1)
@@ -21,6 +27,7 @@ struct TcState {
 
 int tc_conv_init(Net &net);
 int tc_conv_refresh(Net &net, cudaStream_t s);
+int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float *mse, bool accumulate, cudaStream_t s);
 int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
 
 }  // namespace hp

@@ -292,3 +292,61 @@ def test_full_size_properties():
         net.eval_batch_device(x.data_ptr(), n, y2.data_ptr(), precision=prec, stream=st)
         torch.cuda.synchronize()
         assert torch.equal(y, y2)
+
+
+# ---- tensor-core training ---------------------------------------------------------------------
+TC_GRAD_TOL = 2e-2   # bf16 operands in the FC forward / dX / dW contractions; conv stages stay bit-faithful
+
+
+def test_tensor_path_minibatch_gradients_close_to_oracle(net, orc, p0):
+    import torch
+    n = 9
+    x = np.concatenate([synth.depthlike_crops(5, 31), synth.uniform_crops(4, 32)])
+    t = synth.heatmap_labels(n, 33)
+    want, mse_want = orc.train_minibatch(p0.copy(), x, t, 0.001, apply=False)
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+    mse = torch.empty(n, device="cuda")
+    net.grad_batch_device(xd.data_ptr(), td.data_ptr(), n, mse.data_ptr(), precision=hp.PRECISION_TENSOR,
+                          stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    g = net.get_grads()
+    assert np.allclose(mse.cpu().numpy(), mse_want, rtol=2e-2)
+    for k, (off, cnt) in LAYOUT.items():
+        assert maxnorm_err(g[off:off + cnt], want[off:off + cnt]) <= TC_GRAD_TOL, k
+
+
+def test_tensor_path_gradients_ragged_and_accumulating(net):
+    # 70 samples (not a multiple of the 64-wide K block of the dW GEMMs) == 64 + 6 accumulated
+    import torch
+    x, t = synth.uniform_crops(70, 81), np.concatenate([synth.heatmap_labels(35, 82)] * 2)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def grads(a, b):
+        xd, td = torch.from_numpy(x[a:b].copy()).cuda(), torch.from_numpy(t[a:b].copy()).cuda()
+        net.grad_batch_device(xd.data_ptr(), td.data_ptr(), b - a, None, precision=hp.PRECISION_TENSOR, stream=st)
+        torch.cuda.synchronize()
+        return net.get_grads()
+
+    g_all, g_a, g_b = grads(0, 70), grads(0, 64), grads(64, 70)
+    for k, (off, cnt) in LAYOUT.items():
+        assert maxnorm_err(g_all[off:off + cnt], (g_a + g_b)[off:off + cnt]) <= 1e-5, k
+
+
+def test_loss_curves_over_1k_steps(orc, p0):
+    # BASELINE.json north_star: "training-loss curves matching over 1k steps".  1,000 batch-1 steps exactly as
+    # train-cnn.cpp:160 issues them (alpha = 0.001), cycling 16 samples, against the CPU reference arithmetic.
+    xs, ts = synth.depthlike_crops(16, 91), synth.heatmap_labels(16, 92)
+    order = np.arange(1000) % 16
+    p = p0.copy()
+    want = orc.train_seq(p, xs[order], ts[order], 0.001)
+    for prec, curve_tol, weight_tol in ((hp.PRECISION_FP32, 2e-4, 1e-4), (hp.PRECISION_TENSOR, 3e-2, None)):
+        net = hp.PoseInitializerCNN("", precision=prec)
+        got = np.array([net.Train(xs[i], ts[i], 0.001) for i in order], np.float32)
+        rel = np.abs(got - want) / want
+        assert rel.max() <= curve_tol, (prec, float(rel.max()), int(rel.argmax()))
+        assert got[-16:].mean() < got[:16].mean()                   # the loss goes down (slowly at the reference's alpha)
+        if weight_tol is not None:
+            got_p = net.get_params()
+            for k, (off, cnt) in LAYOUT.items():
+                assert maxnorm_err(got_p[off:off + cnt], p[off:off + cnt]) <= weight_tol, k
+        del net
