@@ -631,7 +631,7 @@ static int fp32_conv_backward_impl(Net &net, const float *x, int64_t n, const fl
     const int64_t R = n * C2_POS;
     if (int rc = colsum(net, w.c2, R, C2_CO, G + OFF_C2B, accumulate, s)) return rc;
     {
-        int splits = (int)((R + 1151) / 1152);  // 8 crops per split
+        int splits = (int)((R + 287) / 288);  // 2 crops per split: 2 N tiles x splits CTAs should cover the 148 SMs
         if (splits > 128) splits = 128;
         int klen = (int)((R + splits - 1) / splits);
         klen = (klen + 15) / 16 * 16;
