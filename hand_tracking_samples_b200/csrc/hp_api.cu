@@ -318,6 +318,7 @@ int hp_create_handposedd(int device, hp_net **out)
     HP_CUDA_TRY(cudaMalloc((void **)&n.grads, (size_t)N_PARAMS * sizeof(float)));
     HP_CUDA_TRY(cudaMemset(n.params, 0, (size_t)N_PARAMS * sizeof(float)));
     HP_CUDA_TRY(cudaMemset(n.grads, 0, (size_t)N_PARAMS * sizeof(float)));
+    if (int rc = fp32_init_attributes()) return rc;
     if (int rc = tc_init(n)) return rc;
     *out = h;
     return HP_OK;

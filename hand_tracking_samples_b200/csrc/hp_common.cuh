@@ -92,6 +92,7 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
 int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *mse, bool accumulate,
                   cudaStream_t s);
 int sgd_apply(Net &net, float alpha, cudaStream_t s);
+int fp32_init_attributes();
 // ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);
 int tc_refresh_weights(Net &net, cudaStream_t s);

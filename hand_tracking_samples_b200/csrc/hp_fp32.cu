@@ -544,6 +544,127 @@ __global__ void __launch_bounds__(256) conv1_wgrad(const float *__restrict__ x, 
     }
 }
 
+// LConv::update for conv2 (cnn.h:269-279) restricted to the pool winners: every (sample, pooled pixel, channel)
+// contributes g * patch at its winning position.  Thread k = ci*16 + ky*4 + kx holds dW[co][k] for all 64 co;
+// the (g, patch offset) pairs are shared by the whole CTA through shared memory.  partial[block][co*256 + k].
+// g2 is in HWC order (pp*64 + co), idx2 in CHW order (co*36 + pp), p1 fp32 [ci][15][15].
+__global__ void __launch_bounds__(256) conv2_wgrad_sparse(const float *__restrict__ p1, const float *__restrict__ g2,
+                                                          const uint8_t *__restrict__ idx2, int64_t n, int per_block, float *__restrict__ partial)
+{
+    // p1 rows padded to 20 floats and planes to 304: the 16 taps x 2 channels a warp reads per step then fall into
+    // 32 distinct banks ({0-3},{20-23},{8-11},{28-31} and the same shifted by 16)
+    constexpr int PITCH = 20, PLANE = 304;
+    __shared__ float sp1[C2_CI * PLANE];
+    __shared__ float2 sgo[P2_N];   // (g, patch base offset as int bits), index pp*64 + co
+    const int k = threadIdx.x, ci = k >> 4, tap_off = ((k >> 2) & 3) * PITCH + (k & 3);
+    float acc[C2_CO];
+#pragma unroll
+    for (int co = 0; co < C2_CO; co++) acc[co] = 0.f;
+    const int64_t b0 = (int64_t)blockIdx.x * per_block;
+    const int64_t b1 = (b0 + per_block < n) ? b0 + per_block : n;
+    for (int64_t crop = b0; crop < b1; crop++) {
+        __syncthreads();
+        for (int i = k; i < P1_N; i += 256) {
+            const int c = i / 225, r = i - c * 225, yy = r / P1_W, xx = r - yy * P1_W;
+            sp1[c * PLANE + yy * PITCH + xx] = p1[crop * P1_N + i];
+        }
+        for (int i = k; i < P2_N; i += 256) {
+            const int pp = i >> 6, co = i & 63;
+            const int a = idx2[crop * P2_N + co * 36 + pp];
+            const int py = pp / P2_W, px = pp - py * P2_W;
+            const int off = (2 * py + (a >> 1)) * PITCH + 2 * px + (a & 1);
+            sgo[i] = make_float2(g2[crop * P2_N + i], __int_as_float(off));
+        }
+        __syncthreads();
+        const float *base = sp1 + ci * PLANE + tap_off;
+#pragma unroll 1
+        for (int pp = 0; pp < 36; pp++) {
+#pragma unroll
+            for (int co = 0; co < C2_CO; co++) {
+                const float2 go = sgo[pp * 64 + co];
+                acc[co] = fmaf(go.x, base[__float_as_int(go.y)], acc[co]);
+            }
+        }
+    }
+    float *dst = partial + (size_t)blockIdx.x * (C2_CO * C2_KDIM);
+#pragma unroll
+    for (int co = 0; co < C2_CO; co++) dst[co * C2_KDIM + k] = acc[co];
+}
+
+// LConv::backward for conv2 (cnn.h:258-268) as a register-tiled gather, fused with both LMaxPool::backward calls
+// and TanH::df of the conv1 stage: g1[ci][Y][X] = (1 - p1^2) * sum_{co,ky,kx} W[co][ci][ky][kx] * e[co][Y-ky][X-kx],
+// where e is dL/dc2 (non-zero only at the pool winners).  One crop per CTA; thread (Y, ci) owns a row of 15 outputs.
+__global__ void __launch_bounds__(256) conv2_dx_direct(const float *__restrict__ g2, const uint8_t *__restrict__ idx2,
+                                                       const float *__restrict__ params, const float *__restrict__ p1, float *__restrict__ g1)
+{
+    extern __shared__ __align__(16) float dyn[];
+    float *se = dyn;                    // [64 co][12 y][16 x (12 used)]
+    float *sw = dyn + 64 * 12 * 16;     // [64 co][4 ky][16 ci][4 kx]
+    const int64_t crop = blockIdx.x;
+    const int t = threadIdx.x;
+    for (int i = t; i < 64 * 12 * 16; i += 256) se[i] = 0.f;
+    for (int i = t; i < C2_CO * C2_KDIM; i += 256) {
+        const int kx = i & 3, ky = (i >> 2) & 3, ci = (i >> 4) & 15, co = i >> 8;   // source OIHW index
+        sw[((co * 4 + ky) * 16 + ci) * 4 + kx] = params[OFF_C2W + i];
+    }
+    __syncthreads();
+    for (int i = t; i < P2_N; i += 256) {
+        const int pp = i >> 6, co = i & 63;
+        const int a = idx2[crop * P2_N + co * 36 + pp];
+        const int py = pp / P2_W, px = pp - py * P2_W;
+        se[(co * 12 + 2 * py + (a >> 1)) * 16 + 2 * px + (a & 1)] = g2[crop * P2_N + i];
+    }
+    __syncthreads();
+    float acc[15];
+#pragma unroll
+    for (int X = 0; X < 15; X++) acc[X] = 0.f;
+    const int Y = t >> 4, ci = t & 15;
+    if (Y < 15) {
+#pragma unroll 1
+        for (int co = 0; co < C2_CO; co++) {
+#pragma unroll
+            for (int ky = 0; ky < 4; ky++) {
+                const int y = Y - ky;
+                if (y < 0 || y >= C2_H) continue;
+                const float4 e0 = *reinterpret_cast<const float4 *>(se + (co * 12 + y) * 16);
+                const float4 e1 = *reinterpret_cast<const float4 *>(se + (co * 12 + y) * 16 + 4);
+                const float4 e2 = *reinterpret_cast<const float4 *>(se + (co * 12 + y) * 16 + 8);
+                const float4 w4 = *reinterpret_cast<const float4 *>(sw + ((co * 4 + ky) * 16 + ci) * 4);
+                const float er[12] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w};
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int X = 0; X < 15; X++)
+#pragma unroll
+                    for (int kx = 0; kx < 4; kx++)
+                        if (X - kx >= 0 && X - kx < C2_W) acc[X] = fmaf(wv[kx], er[X - kx], acc[X]);
+            }
+        }
+    }
+    __syncthreads();   // se is free: reuse it to stage the outputs for coalesced stores
+    if (Y < 15) {
+#pragma unroll
+        for (int X = 0; X < 15; X++) se[ci * 225 + Y * 15 + X] = acc[X];
+    }
+    __syncthreads();
+    for (int i = t; i < P1_N; i += 256) {
+        const float pv = p1[crop * P1_N + i];
+        g1[crop * P1_N + i] = (1.0f - pv * pv) * se[i];
+    }
+}
+
+// dst[i] (+)= sum_s src[s*len + i] for short vectors and many slices: one warp per output element,
+// lanes stride over the slices, fixed-shape shuffle tree (deterministic).
+__global__ void __launch_bounds__(256) reduce_partials_warp(float *__restrict__ dst, const float *__restrict__ src, int S, int len, int accumulate)
+{
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= len) return;
+    float a = 0.f;
+    for (int s = lane; s < S; s += 32) a += src[(size_t)s * len + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) dst[i] = accumulate ? dst[i] + a : a;
+}
+
 // W <- W - alpha * g over the flat .cnnb-ordered stores.
 __global__ void __launch_bounds__(256) sgd_kernel(float4 *__restrict__ p, const float4 *__restrict__ g, float alpha, int n4)
 {
@@ -702,6 +823,46 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
 int fp32_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s)
 {
     return fp32_conv_backward_impl(net, x, n, g2_hwc, true, accumulate, s);
+}
+
+constexpr int CONV2_DX_SMEM = (64 * 12 * 16 + C2_CO * C2_KDIM) * 4;  // 112 KB
+
+// Conv-stage backward for the tensor-core training path: winners-only conv2 weight gradient (no im2col), a
+// direct gather for dL/dp1 (FFMA), winners-only conv1 update.  g2 in HWC order; p1, idx1, idx2 in w.*.
+int tc_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s)
+{
+    Workspace &w = net.ws;
+    float *G = net.grads;
+    const int acc = accumulate ? 1 : 0;
+    // conv2 dB: g2 viewed as [n*36][64]
+    if (int rc = colsum(net, g2_hwc, n * 36, C2_CO, G + OFF_C2B, accumulate, s)) return rc;
+    {
+        int per_block = (int)((n + 147) / 148);
+        int blocks = (int)((n + per_block - 1) / per_block);
+        if (blocks > 128) { per_block = (int)((n + 127) / 128); blocks = (int)((n + per_block - 1) / per_block); }  // partial buffer holds 128 slices
+        conv2_wgrad_sparse<<<blocks, 256, 0, s>>>(w.p1, g2_hwc, w.idx2, n, per_block, w.partial);
+        LAUNCH_CHECK(net);
+        reduce_partials<<<(C2_CO * C2_KDIM + 255) / 256, 256, 0, s>>>(G + OFF_C2W, w.partial, blocks, C2_CO * C2_KDIM, acc);
+        LAUNCH_CHECK(net);
+    }
+    // dL/dp1 through conv2 and the conv1-stage pools / tanh': direct register-tiled gather
+    conv2_dx_direct<<<(unsigned)n, 256, CONV2_DX_SMEM, s>>>(g2_hwc, w.idx2, net.params, w.p1, w.g1);
+    LAUNCH_CHECK(net);
+    {
+        const int blocks = (int)n;   // one crop per CTA: two CTAs per SM hide each other's load latency
+        if ((size_t)blocks * 416 > w.partial_floats) { set_error("partial buffer too small for %d crops", blocks); return 1; }
+        conv1_wgrad<<<blocks, 256, 0, s>>>(x, w.g1, w.idx1, n, 1, w.partial);
+        LAUNCH_CHECK(net);
+        reduce_partials_warp<<<(416 + 7) / 8, 256, 0, s>>>(G + OFF_C1W, w.partial, blocks, 416, acc);
+        LAUNCH_CHECK(net);
+    }
+    return 0;
+}
+
+int fp32_init_attributes()
+{
+    HP_CUDA_TRY(cudaFuncSetAttribute(conv2_dx_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_DX_SMEM));
+    return 0;
 }
 
 int fp32_colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, bool accumulate, cudaStream_t s)

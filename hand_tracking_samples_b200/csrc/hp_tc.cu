@@ -623,6 +623,7 @@ static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB,
 // hp_fp32.cu
 int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
 int fp32_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s);
+int tc_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s);
 int fp32_colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, bool accumulate, cudaStream_t s);
 
 constexpr int64_t TRAIN_CAP = 2048;  // samples per pass (bounded by the FP32 conv-stage workspace)
@@ -654,8 +655,9 @@ static int tc_train_ensure(Net &net)
 }
 
 // Forward + backward of one pass (n <= TRAIN_CAP) with every FC contraction on tcgen05:
-//   forward   conv stages (FFMA, bit-faithful: exact pool winners) -> fc1 -> fc2 + softmax          (tensor)
-//   backward  loss + softmax' -> fc2 dW, dX*tanh' -> fc1 dW, dX*tanh' (tensor) -> conv2 / conv1 backward (FFMA)
+//   forward   conv stages (tensor, emitting p1 and the pool winners) -> fc1 -> fc2 + softmax (tensor)
+//   backward  loss + softmax' -> fc2 dW, dX*tanh' -> fc1 dW, dX*tanh' (tensor) -> conv2 / conv1 backward
+//             (winners-only weight gradients and the dL/dp1 route on FFMA)
 // Leaves sum_b g_b in net.grads (.cnnb order).  CNN::Train, cnn.h:558-575.
 int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float *mse, bool accumulate, cudaStream_t s)
 {
@@ -671,7 +673,7 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     const int n_pad = (M + BK - 1) / BK * BK;
     const int flags = accumulate ? TC_FLAG_ACCUMULATE : 0;
     // ---- forward
-    if (int rc = fp32_conv_stage(net, x, n, t->p2, s)) return rc;   // p2 bf16 in HWC order, winners in w.idx1 / w.idx2
+    if (int rc = tc_conv_stage_train(net, x, n, t->p2, s)) return rc;   // p2 bf16 (HWC); p1, idx1, idx2 into the workspace
     if (int rc = launch_gemm<TC_EPI_TANH_BF16>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
     if (int rc = launch_gemm<TC_EPI_SOFTMAX_F32>(net, t->tm_h1, t->tm_w2t, EpiArgs{net.params + OFF_F2B, w.y, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
     // ---- loss, fc2
@@ -699,8 +701,8 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
     // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order
     if (int rc = launch_gemm<TC_EPI_DTANH>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
-    // ---- conv stages backward on FFMA (exact winners)
-    if (int rc = fp32_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
+    // ---- conv stages backward (winners-only weight gradients; FFMA)
+    if (int rc = tc_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));
     return 0;
 }

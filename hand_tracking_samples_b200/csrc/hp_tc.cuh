@@ -28,6 +28,7 @@ struct TcState {
 int tc_conv_init(Net &net);
 int tc_conv_refresh(Net &net, cudaStream_t s);
 int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float *mse, bool accumulate, cudaStream_t s);
+int tc_conv_stage_train(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
 int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
 
 }  // namespace hp

@@ -53,7 +53,7 @@ constexpr int OFF_B2 = 32768;                  // 32 KB
 constexpr int OFF_IMG = 65536;                 // 2 x IMG_BUF
 constexpr int OFF_P1 = OFF_IMG + 2 * IMG_BUF;  // 2 x P1_BUF
 constexpr int OFF_S = OFF_P1 + 2 * P1_BUF;     // S_ROWS x 128
-constexpr int OFF_BIAS = OFF_S + S_ROWS * 128; // 16 + 64 floats
+constexpr int OFF_BIAS = OFF_S + S_ROWS * 256; // 16 + 64 floats (S rows: 128 B bf16 for inference, 256 B fp32 for training)
 constexpr int OFF_BAR = OFF_BIAS + 512;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
 // TMEM columns
@@ -83,9 +83,14 @@ __device__ long long g_conv_trace[64 * 1024];
 #define TRACE(role, it, ev) do {} while (0)
 #endif
 
+// TRAIN additionally emits what CNN::Train's backward needs (cnn.h:571-575): the pooled conv1 activations p1
+// (fp32, the reference's CHW layout) and the max-pool winners of both stages (LMaxPool::backward, cnn.h:149-164:
+// first strict maximum; the window positions are laid out in the hierarchical scan order of the two stacked pools).
+template <bool TRAIN>
 __global__ void __launch_bounds__(cv::THREADS, 1)
 tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, const uint8_t *__restrict__ b2_img,
-               const float *__restrict__ params, __nv_bfloat16 *__restrict__ p2_out, int n)
+               const float *__restrict__ params, __nv_bfloat16 *__restrict__ p2_out, int n, float *__restrict__ p1_out,
+               uint8_t *__restrict__ idx1_out, uint8_t *__restrict__ idx2_out)
 {
     using namespace cv;
     extern __shared__ uint8_t smem_raw[];
@@ -222,6 +227,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
 #pragma unroll 1
             for (int e = 0; e < 2; e++) {
                 float mx[16];
+                int am[16];
                 const uint32_t u = (uint32_t)(it * 2 + e);
 #pragma unroll 1
                 for (int half = 0; half < 2; half++) {
@@ -234,7 +240,15 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                         uint32_t r[32];
                         ptx::tmem_ld32(ta + c * 32, r);
                         ptx::tmem_ld_wait();
-                        if (half == 0 && c == 0) {
+                        if (TRAIN) {
+                            const int p0 = half * 8 + 2 * c;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[16 + j]);
+                                if ((half == 0 && c == 0) || v0 > mx[j]) { mx[j] = v0; am[j] = p0; }
+                                if (v1 > mx[j]) { mx[j] = v1; am[j] = p0 + 1; }
+                            }
+                        } else if (half == 0 && c == 0) {
 #pragma unroll
                             for (int j = 0; j < 16; j++) mx[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[16 + j]));
                         } else {
@@ -256,6 +270,18 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     const int q = py * 15 + px;
                     *reinterpret_cast<uint4 *>(planes + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4 *>(planes + P1_PLANE + q * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (TRAIN) {
+                        const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            // the bf16-rounded value conv2 actually consumed, in the reference's [c][y][x] layout
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&pk[j >> 1]);
+                            p1_out[crop * P1_N + j * 225 + q] = (j & 1) ? __high2float(h) : __low2float(h);
+                            const int blk = am[j] >> 2, sub = am[j] & 3;   // hierarchical position -> (dy, dx)
+                            const int dy = 2 * (blk >> 1) + (sub >> 1), dx = 2 * (blk & 1) + (sub & 1);
+                            idx1_out[crop * P1_N + j * 225 + q] = (uint8_t)(dy * 4 + dx);
+                        }
+                    }
                 }
             }
             ptx::fence_proxy_async();   // generic-proxy stores -> visible to the MMA's async-proxy reads
@@ -286,7 +312,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     uint32_t r[32];
                     ptx::tmem_ld32(ta + c * 32, r);
                     ptx::tmem_ld_wait();
-                    if (valid) {
+                    if (valid && !TRAIN) {
 #pragma unroll
                         for (int k = 0; k < 4; k++) {   // 16-byte chunk index c*4+k, swizzled by the row to avoid bank conflicts
                             const int chunk = c * 4 + k;
@@ -297,6 +323,13 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                                            pack_bf16(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
                         }
                     }
+                    if (valid && TRAIN) {   // fp32 staging: the pool winners are decided on unrounded pre-activations
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const int chunk = c * 8 + k;   // 16 chunks of 4 channels per 256-byte row
+                            *reinterpret_cast<uint4 *>(S + q * 256 + ((chunk ^ (q & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+                        }
+                    }
                 }
             }
             ptx::tc_fence_before();
@@ -304,24 +337,49 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             if (lane == 0) ptx::mbar_arrive(&acc2_empty[pb]);
             if (ew == 0) TRACE(3, it, 2);
             ptx::named_bar_sync(1, 128);
-            // 36 pooled pixels x 8 chunks of 8 channels
-            for (int item = t128; item < 288; item += 128) {
-                const int pp = item >> 3, chunk = item & 7;
-                const int py = pp / 6, px = pp - py * 6;
-                const int q0 = (2 * py) * 15 + 2 * px;
-                auto ld = [&](int q) { return *reinterpret_cast<const uint4 *>(S + q * 128 + ((chunk ^ (q & 7)) << 4)); };
-                const uint4 a = ld(q0), b = ld(q0 + 1), c = ld(q0 + 15), d = ld(q0 + 16);
-                uint32_t o[4];
-                const uint32_t *pa = &a.x, *pb2 = &b.x, *pc = &c.x, *pd = &d.x;
+            if (!TRAIN) {
+                // 36 pooled pixels x 8 chunks of 8 channels
+                for (int item = t128; item < 288; item += 128) {
+                    const int pp = item >> 3, chunk = item & 7;
+                    const int py = pp / 6, px = pp - py * 6;
+                    const int q0 = (2 * py) * 15 + 2 * px;
+                    auto ld = [&](int q) { return *reinterpret_cast<const uint4 *>(S + q * 128 + ((chunk ^ (q & 7)) << 4)); };
+                    const uint4 a = ld(q0), b = ld(q0 + 1), c = ld(q0 + 15), d = ld(q0 + 16);
+                    uint32_t o[4];
+                    const uint32_t *pa = &a.x, *pb2 = &b.x, *pc = &c.x, *pd = &d.x;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const __nv_bfloat162 m01 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pa + k), *reinterpret_cast<const __nv_bfloat162 *>(pb2 + k));
-                    const __nv_bfloat162 m23 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pc + k), *reinterpret_cast<const __nv_bfloat162 *>(pd + k));
-                    const float2 f = __bfloat1622float2(__hmax2(m01, m23));
-                    const int co = chunk * 8 + 2 * k;
-                    o[k] = pack_bf16(tanh_fast(f.x + bias2[co]), tanh_fast(f.y + bias2[co + 1]));
+                    for (int k = 0; k < 4; k++) {
+                        const __nv_bfloat162 m01 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pa + k), *reinterpret_cast<const __nv_bfloat162 *>(pb2 + k));
+                        const __nv_bfloat162 m23 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pc + k), *reinterpret_cast<const __nv_bfloat162 *>(pd + k));
+                        const float2 f = __bfloat1622float2(__hmax2(m01, m23));
+                        const int co = chunk * 8 + 2 * k;
+                        o[k] = pack_bf16(tanh_fast(f.x + bias2[co]), tanh_fast(f.y + bias2[co + 1]));
+                    }
+                    *reinterpret_cast<uint4 *>(p2_out + crop * P2_N + pp * 64 + chunk * 8) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
-                *reinterpret_cast<uint4 *>(p2_out + crop * P2_N + pp * 64 + chunk * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+                // 36 pooled pixels x 16 chunks of 4 channels; first strict maximum in scan order (0,0),(1,0),(0,1),(1,1)
+                for (int item = t128; item < 576; item += 128) {
+                    const int pp = item >> 4, chunk = item & 15;
+                    const int py = pp / 6, px = pp - py * 6;
+                    const int q0 = (2 * py) * 15 + 2 * px;
+                    auto ld = [&](int q) { return *reinterpret_cast<const float4 *>(S + q * 256 + ((chunk ^ (q & 7)) << 4)); };
+                    const float4 a = ld(q0), b = ld(q0 + 1), c = ld(q0 + 15), d = ld(q0 + 16);
+                    const float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {b.x, b.y, b.z, b.w}, vc[4] = {c.x, c.y, c.z, c.w}, vd[4] = {d.x, d.y, d.z, d.w};
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float m = va[k];
+                        int arg = 0;
+                        if (vb[k] > m) { m = vb[k]; arg = 1; }
+                        if (vc[k] > m) { m = vc[k]; arg = 2; }
+                        if (vd[k] > m) { m = vd[k]; arg = 3; }
+                        const int co = chunk * 4 + k;
+                        o[k] = tanh_fast(m + bias2[co]);
+                        idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg;
+                    }
+                    *reinterpret_cast<uint2 *>(p2_out + crop * P2_N + pp * 64 + chunk * 4) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+                }
             }
             ptx::named_bar_sync(1, 128);
             if (ew == 0) TRACE(3, it, 3);
@@ -368,7 +426,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
 }
 
 // Build the two pre-laid-out weight images from the fp32 master weights.
-//  b1: row nrow = pos*16 + co (pos = dy*4+dx), 64 k = (r,c) of the 8x8 patch; value = w1[co][r-dy][c-dx]
+//  b1: row nrow = pos*16 + co (pos = hierarchical pool-scan index of window offset (dy,dx)), 64 k = (r,c) of the 8x8 patch; value = w1[co][r-dy][c-dx]
 //      inside the 5x5 support, else 0; 128-byte rows, 16-byte chunk r stored at chunk (r ^ (nrow & 7)).
 //  b2: [tap][kchunk][co][8 ci] bf16 (16-byte rows): the un-swizzled K-major core-matrix order.
 __global__ void __launch_bounds__(256) build_conv_images(const float *__restrict__ params, uint8_t *__restrict__ b1, uint8_t *__restrict__ b2)
@@ -376,7 +434,9 @@ __global__ void __launch_bounds__(256) build_conv_images(const float *__restrict
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < 256 * 64) {
         const int nrow = i >> 6, k = i & 63;
-        const int pos = nrow >> 4, co = nrow & 15, dy = pos >> 2, dx = pos & 3;
+        const int pos = nrow >> 4, co = nrow & 15;
+        // window positions in the scan order of two stacked 2x2 pools: outer block (by,bx), inner offset (iy,ix)
+        const int blk = pos >> 2, sub = pos & 3, dy = 2 * (blk >> 1) + (sub >> 1), dx = 2 * (blk & 1) + (sub & 1);
         const int r = k >> 3, c = k & 7;
         const int ky = r - dy, kx = c - dx;
         const float v = (ky >= 0 && ky < 5 && kx >= 0 && kx < 5) ? params[OFF_C1W + co * 25 + ky * 5 + kx] : 0.f;
@@ -401,7 +461,8 @@ int tc_conv_init(Net &net)
     TcState *t = net.tc;
     HP_CUDA_TRY(cudaMalloc((void **)&t->b1_img, 32768));
     HP_CUDA_TRY(cudaMalloc((void **)&t->b2_img, 32768));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
     return 0;
 }
 
@@ -417,7 +478,17 @@ int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cud
 {
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv_kernel<<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n);
+    tc_conv_kernel<false><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// training forward: also writes p1 (fp32 CHW), idx1, idx2 into the FP32 workspace layouts the backward kernels read
+int tc_conv_stage_train(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    const int grid = (int)(n < t->num_sms ? n : t->num_sms);
+    tc_conv_kernel<true><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2);
     LAUNCH_CHECK(net);
     return 0;
 }
