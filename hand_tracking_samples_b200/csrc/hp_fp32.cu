@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) colsum_partial(const float *__restrict__ 
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ logits, float *__restrict__ y,
                                                       const float *__restrict__ t, float *__restrict__ dlog,
-                                                      float *__restrict__ mse)
+                                                      float *__restrict__ mse, __nv_bfloat16 *__restrict__ dlog_bf = nullptr)
 {
     const int64_t crop = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,13 +425,18 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, o);
 #pragma unroll
-        for (int i = 0; i < 8; i++) dlog[crop * N_OUT + warp * 256 + i * 32 + lane] = ev[i] * (e[i] - dp);  // cnn.h:522
+        for (int i = 0; i < 8; i++) {
+            const float d = ev[i] * (e[i] - dp);  // cnn.h:522
+            dlog[crop * N_OUT + warp * 256 + i * 32 + lane] = d;
+            if (dlog_bf) dlog_bf[crop * N_OUT + warp * 256 + i * 32 + lane] = __float2bfloat16_rn(d);
+        }
         const float e2 = es - tt[2048 + tid];
         se += e2 * e2;
         float dp2 = e2 * es;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) dp2 += __shfl_xor_sync(0xffffffffu, dp2, o);
         dlog[crop * N_OUT + 2048 + tid] = es * (e2 - dp2);
+        if (dlog_bf) dlog_bf[crop * N_OUT + 2048 + tid] = __float2bfloat16_rn(es * (e2 - dp2));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
         if (lane == 0) red[warp] = se;
@@ -862,6 +867,13 @@ int tc_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, b
 int fp32_init_attributes()
 {
     HP_CUDA_TRY(cudaFuncSetAttribute(conv2_dx_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_DX_SMEM));
+    return 0;
+}
+
+int fp32_softmax_loss(Net &net, const float *logits, float *y, const float *t, float *dlog, __nv_bfloat16 *dlog_bf, float *mse, int64_t n, cudaStream_t s)
+{
+    softmax_kernel<true><<<(unsigned)n, 256, 0, s>>>(logits, y, t, dlog, mse, dlog_bf);
+    LAUNCH_CHECK(net);
     return 0;
 }
 

@@ -31,13 +31,13 @@ namespace hp {
 constexpr int64_t TC_CHUNK = 16384;  // crops per pass of the tensor-core path (activation workspace bound)
 
 // ---- GEMM tile configuration -----------------------------------------------------------
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;  // UMMA K = 16 bf16 per instruction
+// N tile is a template parameter: 256 for the big-batch GEMMs (and required by the fused chunked softmax), 64 for the
+// small-M training GEMMs, where 256-wide tiles would leave most of the 148 SMs without a tile.
+constexpr int BM = 128, BK = 64, STAGES = 4;    // UMMA K = 16 bf16 per instruction
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
-constexpr int B_BYTES = BN * BK * 2;            // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int STG_BYTES = 4096;                 // per-warp output staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by row
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 256;
+constexpr int gemm_smem(int bn) { return STAGES * (A_BYTES + bn * BK * 2) + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
 
 enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3 };
 enum { TC_FLAG_ACCUMULATE = 1, TC_FLAG_ROWS_HWC_TO_CHW = 2 };
@@ -104,10 +104,13 @@ __device__ __forceinline__ float ex2_fast(float x)
 // ============================================================================
 // C[M x N] = A[M x K] * Bt[N x K]^T  (+ fused epilogue); A, Bt bf16 K-major via TMA.
 // ============================================================================
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs ea, int M, int N, int K)
 {
+    static_assert(EPI != TC_EPI_SOFTMAX_F32 || BN == 256, "the fused chunked softmax needs whole 256-wide spans in one tile");
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     const float *__restrict__ bias = ea.bias;
     void *__restrict__ out = ea.out;
     extern __shared__ uint8_t smem_raw[];
@@ -206,7 +209,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&tmem_full[as], aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
-            const float *bptr = bias + n_blk * BN;
+            const float *bptr = bias ? bias + n_blk * BN : nullptr;
             uint8_t *stg = staging + ew * 2 * STG_BYTES;
             // stage one 32-row x 128-byte segment (this thread's row: 8 x 16 B) and write it out coalesced:
             // each store instruction then covers 4 rows x 128 contiguous bytes instead of 32 scattered rows
@@ -328,6 +331,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ptx::tmem_ld32(taddr + c * 32, r);
                     ptx::tmem_ld_wait();
                     uint4 o[8];
+                    if (bias) {   // LFull::forward: Y = B + x*W (cnn.h:407), logits for the separate softmax / loss kernel
+#pragma unroll
+                        for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) + bptr[c * 32 + j]);
+                    }
 #pragma unroll
                     for (int q = 0; q < 8; q++) o[q] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
                     flush_grad(c & 1, o, reinterpret_cast<float *>(out), n_blk * BN + c * 32);
@@ -510,16 +517,23 @@ int tc_init(Net &net)
     t->num_sms = prop.multiProcessorCount;
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1t, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2t, (size_t)FC2_OUT * FC2_IN * 2));
-    if (int rc = make_map_bf16(&t->tm_w1t, t->w1t, FC1_OUT, FC1_IN, BN)) return rc;
-    if (int rc = make_map_bf16(&t->tm_w2t, t->w2t, FC2_OUT, FC2_IN, BN)) return rc;
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_SOFTMAX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    if (int rc = make_map_bf16(&t->tm_w1t, t->w1t, FC1_OUT, FC1_IN, 256)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w2t, t->w2t, FC2_OUT, FC2_IN, 256)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w1t64, t->w1t, FC1_OUT, FC1_IN, 64)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w2t64, t->w2t, FC2_OUT, FC2_IN, 64)) return rc;
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_SOFTMAX_F32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1b, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2b, (size_t)FC2_OUT * FC2_IN * 2));
-    if (int rc = make_map_bf16(&t->tm_w1b, t->w1b, FC1_IN, FC1_OUT, BN)) return rc;
-    if (int rc = make_map_bf16(&t->tm_w2b, t->w2b, FC2_IN, FC2_OUT, BN)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w1b, t->w1b, FC1_IN, FC1_OUT, 256)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w2b, t->w2b, FC2_IN, FC2_OUT, 256)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w1b64, t->w1b, FC1_IN, FC1_OUT, 64)) return rc;
+    if (int rc = make_map_bf16(&t->tm_w2b64, t->w2b, FC2_IN, FC2_OUT, 64)) return rc;
     return tc_conv_init(net);
 }
 
@@ -590,18 +604,18 @@ int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s
         const int m_tiles = (int)((m + BM - 1) / BM);
         {
             StageTimer st(net, 1, s);
-            const int tiles = m_tiles * (FC1_OUT / BN);
+            const int tiles = m_tiles * (FC1_OUT / 256);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
             EpiArgs ea{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0};
-            tc_gemm_kernel<TC_EPI_TANH_BF16><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_p2, t->tm_w1t, ea, (int)m, FC1_OUT, FC1_IN);
+            tc_gemm_kernel<TC_EPI_TANH_BF16, 256><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_p2, t->tm_w1t, ea, (int)m, FC1_OUT, FC1_IN);
             LAUNCH_CHECK(net);
         }
         {
             StageTimer st(net, 2, s);
-            const int tiles = m_tiles * (FC2_OUT / BN);
+            const int tiles = m_tiles * (FC2_OUT / 256);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
             EpiArgs ea{net.params + OFF_F2B, y_out + b * N_OUT, nullptr, nullptr, 0};
-            tc_gemm_kernel<TC_EPI_SOFTMAX_F32><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
+            tc_gemm_kernel<TC_EPI_SOFTMAX_F32, 256><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
             LAUNCH_CHECK(net);
         }
     }
@@ -609,16 +623,19 @@ int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s
 }
 
 
-template <int EPI>
+template <int EPI, int BN>
 static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB, const EpiArgs &ea, int M, int N, int K, cudaStream_t s)
 {
     TcState *t = net.tc;
     const int tiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = tiles < t->num_sms ? tiles : t->num_sms;
-    tc_gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, ea, M, N, K);
+    tc_gemm_kernel<EPI, BN><<<grid, GEMM_THREADS, gemm_smem(BN), s>>>(tmA, tmB, ea, M, N, K);
     LAUNCH_CHECK(net);
     return 0;
 }
+
+// hp_fp32.cu: softmax + loss + softmax backward from logits, optionally also emitting dlogits as bf16
+int fp32_softmax_loss(Net &net, const float *logits, float *y, const float *t, float *dlog, __nv_bfloat16 *dlog_bf, float *mse, int64_t n, cudaStream_t s);
 
 // hp_fp32.cu
 int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
@@ -649,8 +666,8 @@ static int tc_train_ensure(Net &net)
     if (int rc = make_map_bf16(&t->tm_da1, t->da1_bf, cap, FC1_OUT, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_h1T, t->h1T, FC1_OUT, cap, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_p2T, t->p2T, FC1_IN, cap, BM)) return rc;
-    if (int rc = make_map_bf16(&t->tm_dlogT, t->dlogT, N_OUT, cap, BN)) return rc;
-    if (int rc = make_map_bf16(&t->tm_da1T, t->da1T, FC1_OUT, cap, BN)) return rc;
+    if (int rc = make_map_bf16(&t->tm_dlogT, t->dlogT, N_OUT, cap, 256)) return rc;
+    if (int rc = make_map_bf16(&t->tm_da1T, t->da1T, FC1_OUT, cap, 256)) return rc;
     return 0;
 }
 
@@ -674,21 +691,32 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     const int flags = accumulate ? TC_FLAG_ACCUMULATE : 0;
     // ---- forward
     if (int rc = tc_conv_stage_train(net, x, n, t->p2, s)) return rc;   // p2 bf16 (HWC); p1, idx1, idx2 into the workspace
-    if (int rc = launch_gemm<TC_EPI_TANH_BF16>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
-    if (int rc = launch_gemm<TC_EPI_SOFTMAX_F32>(net, t->tm_h1, t->tm_w2t, EpiArgs{net.params + OFF_F2B, w.y, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
-    // ---- loss, fc2
-    loss_from_y<<<(unsigned)n, 256, 0, s>>>(w.y, t_dev, w.dlog, t->dlog_bf, mse);
-    LAUNCH_CHECK(net);
+    // small batches: 64-wide N tiles so that the GEMMs spread over the SMs (256-wide tiles give 2 x 8 CTAs at n = 256)
+    const bool narrow = ((M + BM - 1) / BM) * (FC1_OUT / 256) < 74;
+    if (narrow) {
+        if (int rc = launch_gemm<TC_EPI_TANH_BF16, 64>(net, t->tm_p2, t->tm_w1t64, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_STORE_F32, 64>(net, t->tm_h1, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, w.logits, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
+        if (int rc = fp32_softmax_loss(net, w.logits, w.y, t_dev, w.dlog, t->dlog_bf, mse, n, s)) return rc;
+    } else {
+        if (int rc = launch_gemm<TC_EPI_TANH_BF16, 256>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_SOFTMAX_F32, 256>(net, t->tm_h1, t->tm_w2t, EpiArgs{net.params + OFF_F2B, w.y, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
+        loss_from_y<<<(unsigned)n, 256, 0, s>>>(w.y, t_dev, w.dlog, t->dlog_bf, mse);
+        LAUNCH_CHECK(net);
+    }
     if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
     transpose_bf16<<<dim3(FC1_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->h1, t->h1T, M, n_pad, FC1_OUT, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     transpose_bf16<<<dim3(N_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->dlog_bf, t->dlogT, M, n_pad, N_OUT, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW2[2048][2304] = h1^T * dlog
-    if (int rc = launch_gemm<TC_EPI_STORE_F32>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
     // da1 = (dlog * W2^T) .* (1 - h1^2)
-    if (int rc = launch_gemm<TC_EPI_DTANH>(net, t->tm_dlog, t->tm_w2b, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
+    if (narrow) {
+        if (int rc = launch_gemm<TC_EPI_DTANH, 64>(net, t->tm_dlog, t->tm_w2b64, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
+    } else {
+        if (int rc = launch_gemm<TC_EPI_DTANH, 256>(net, t->tm_dlog, t->tm_w2b, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
+    }
     // ---- fc1
     if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
     transpose_bf16<<<dim3(FC1_IN / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->p2, t->p2T, M, n_pad, FC1_IN, (int)TRAIN_CAP);
@@ -696,11 +724,15 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     transpose_bf16<<<dim3(FC1_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->da1_bf, t->da1T, M, n_pad, FC1_OUT, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW1[k'][2048] = p2^T * da1, rows un-permuted from HWC to the reference's CHW flatten on store
-    if (int rc = launch_gemm<TC_EPI_STORE_F32>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
-                                               FC1_OUT, n_pad, s)) return rc;
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
+                                                    FC1_OUT, n_pad, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
     // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order
-    if (int rc = launch_gemm<TC_EPI_DTANH>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+    if (narrow) {
+        if (int rc = launch_gemm<TC_EPI_DTANH, 64>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+    } else {
+        if (int rc = launch_gemm<TC_EPI_DTANH, 256>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+    }
     // ---- conv stages backward (winners-only weight gradients; FFMA)
     if (int rc = tc_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));

@@ -16,6 +16,7 @@ struct TcState {
     // training activations (TRAIN_CAP samples per pass)
     __nv_bfloat16 *dlog_bf = nullptr, *da1_bf = nullptr;            // [cap][2304], [cap][2048]
     __nv_bfloat16 *h1T = nullptr, *dlogT = nullptr, *p2T = nullptr, *da1T = nullptr;  // [features][cap]: batch-contiguous (K-major for dW)
+    CUtensorMap tm_w1t64, tm_w2t64, tm_w1b64, tm_w2b64;   // the same weights with 64-row boxes (small-batch GEMMs)
     CUtensorMap tm_w1b, tm_w2b, tm_dlog, tm_da1, tm_h1T, tm_p2T, tm_dlogT, tm_da1T;
     // activations
     __nv_bfloat16 *p2 = nullptr;   // [cap][2304] pooled conv2 stage (fc1 input), HWC flatten
