@@ -292,7 +292,37 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         line["e2e"] = {"value": world * B * ke / float(dt.item()), "unit": "crops/s", "h2d_bytes_per_step": B * 4096 * 4,
                        "d2h_bytes_per_step": B * 2304 * 4, "api": "hp_eval_batch (host buffers, pinned; chunked H2D/compute/D2H overlap)"}
-        del xh, yh
+        # the PCIe ceiling this number lives under: a bare pinned H2D copy of the same 1 GiB
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        xdst = torch.empty_like(x)
+        xdst.copy_(xh, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        xdst.copy_(xh, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = B * 4096 * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        line["e2e"]["pcie_h2d_gbs_measured"] = h2d_gbs
+        line["e2e"]["frac_of_pcie_bound"] = (line["e2e"]["value"] / world) * 4096 * 4 / 1e9 / h2d_gbs
+        del xdst
+        # same call chain as handtrack.h:700-702 through the compact entry point: 16-bit depth crops up (8 KB/crop),
+        # normalise + Eval + decode on the device, 48 decoded floats down (192 B/crop)
+        dh = torch.randint(0, 1200, (B, 4096), dtype=torch.int32).to(torch.int16).pin_memory()
+        dech = torch.empty((B, 48), dtype=torch.float32).pin_memory()
+        dnp = dh.numpy().view(np.uint16)
+        net.eval_depth_batch(dnp, precision=hp.PRECISION_TENSOR, want_y=False, out_dec=dech.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            net.eval_depth_batch(dnp, precision=hp.PRECISION_TENSOR, want_y=False, out_dec=dech.numpy())
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if distributed:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        line["e2e_depth_in_decoded_out"] = {"value": world * B * ke / float(dt.item()), "unit": "crops/s", "h2d_bytes_per_step": B * 4096 * 2,
+                                            "d2h_bytes_per_step": B * 48 * 4,
+                                            "api": "hp_eval_depth_batch (u16 depth in, handtrack.h:700 normalisation + Eval + CNNOutputAnalysis decode on device)"}
+        del xh, yh, dh, dech
 
         # ---- training arm: minibatch 256 per GPU, FP32 path, NCCL all-reduce when N > 1 ----------
         try:

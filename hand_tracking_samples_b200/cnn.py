@@ -130,6 +130,34 @@ class CNN:
                                         self.precision if precision is None else precision))
         return y
 
+    def decode_batch(self, y):
+        """CNNOutputAnalysis numeric core (handtrack.h:218-241): y[n][2304] -> [n][48]."""
+        y = _f32(y, N_OUT)
+        out = np.empty((y.shape[0], 48), np.float32)
+        capi.check(self.L.hp_decode_batch(self.h, y.ctypes.data, y.shape[0], out.ctypes.data))
+        return out
+
+    def eval_decode_batch(self, x, precision=None, want_y=True):
+        x = _f32(x, N_IN)
+        n = x.shape[0]
+        y = np.empty((n, N_OUT), np.float32) if want_y else None
+        dec = np.empty((n, 48), np.float32)
+        capi.check(self.L.hp_eval_decode_batch(self.h, x.ctypes.data, n, y.ctypes.data if want_y else None, dec.ctypes.data,
+                                               self.precision if precision is None else precision))
+        return (y, dec) if want_y else dec
+
+    def eval_depth_batch(self, depth_u16, depth_scale=0.001, dmin=0.1, dmax=0.7, precision=None, want_y=True, want_decoded=True,
+                         out_y=None, out_dec=None):
+        """handtrack.h:700-702: 16-bit depth crops -> normalise -> Eval -> (decode)."""
+        d = np.ascontiguousarray(depth_u16, np.uint16).reshape(-1, N_IN)
+        n = d.shape[0]
+        y = out_y if out_y is not None else (np.empty((n, N_OUT), np.float32) if want_y else None)
+        dec = out_dec if out_dec is not None else (np.empty((n, 48), np.float32) if want_decoded else None)
+        capi.check(self.L.hp_eval_depth_batch(self.h, d.ctypes.data, n, depth_scale, dmin, dmax, y.ctypes.data if y is not None else None,
+                                              dec.ctypes.data if dec is not None else None,
+                                              self.precision if precision is None else precision))
+        return y, dec
+
     def train_batch(self, x, t, alpha, precision=None):
         x = _f32(x, N_IN)
         t = _f32(t, N_OUT)

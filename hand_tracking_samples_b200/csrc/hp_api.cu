@@ -85,6 +85,13 @@ static int ensure_staging(Net &net, int64_t n, bool pin_in, bool pin_out)
         }
         if (dev_alloc(net.dev_t, n * N_OUT)) return HP_ERR_CUDA;
         if (dev_alloc(net.dev_mse, n)) return HP_ERR_CUDA;
+        for (int b = 0; b < 2; b++) {
+            if (dev_alloc(net.dev_norm[b], n * N_IN)) return HP_ERR_CUDA;
+            if (dev_alloc(net.dev_dec[b], n * 48)) return HP_ERR_CUDA;
+            if (net.pin_dec[b]) cudaFreeHost(net.pin_dec[b]);
+            net.pin_dec[b] = nullptr;
+            HP_CUDA_TRY(cudaMallocHost((void **)&net.pin_dec[b], n * 48 * sizeof(float)));
+        }
         net.stage_cap = n;
     }
     // pinned bounce buffers only when the caller's memory is pageable
@@ -356,12 +363,13 @@ int hp_destroy(hp_net *net)
     tc_destroy(n);
     Workspace &w = n.ws;
     void *bufs[] = {n.params, n.grads, w.p1, w.idx1, w.col, w.c2, w.p2, w.idx2, w.h1, w.logits, w.y, w.dlog, w.da1, w.g2, w.colgrad,
-                    w.g1, w.partial, w.w2p, w.p2_bf, w.h1_bf, n.dev_in[0], n.dev_in[1], n.dev_out[0], n.dev_out[1], n.dev_t, n.dev_mse};
+                    w.g1, w.partial, w.w2p, w.p2_bf, w.h1_bf, n.dev_in[0], n.dev_in[1], n.dev_out[0], n.dev_out[1], n.dev_t, n.dev_mse, n.dev_norm[0], n.dev_norm[1], n.dev_dec[0], n.dev_dec[1]};
     for (void *p : bufs)
         if (p) cudaFree(p);
     for (int b = 0; b < 2; b++) {
         if (n.pin_in[b]) cudaFreeHost(n.pin_in[b]);
         if (n.pin_out[b]) cudaFreeHost(n.pin_out[b]);
+        if (n.pin_dec[b]) cudaFreeHost(n.pin_dec[b]);
         if (n.ev_in[b]) cudaEventDestroy(n.ev_in[b]);
         if (n.ev_out[b]) cudaEventDestroy(n.ev_out[b]);
         if (n.ev_comp[b]) cudaEventDestroy(n.ev_comp[b]);
@@ -451,24 +459,24 @@ int hp_eval_batch_device(hp_net *net, const float *x_dev, int64_t n, float *y_de
 
 // HOST buffers: chunks flow  host --H2D--> dev_in[b] --kernels--> dev_out[b] --D2H--> host  with
 // two buffers per direction so that the copies of chunk c+1 / c-1 overlap the compute of chunk c.
-int hp_eval_batch(hp_net *net, const float *x, int64_t n, float *y, int precision)
+// The upload is either fp32 crops (elem = 4) or 16-bit depth (elem = 2, normalised on the device,
+// include/handtrack.h:700); the download is the 2304-float outputs and/or the 48-float decoded peaks.
+struct DepthNorm { float scale, dmin, dmax; };
+static int eval_host_pipeline(Net &N, const void *x, int elem, const DepthNorm *norm, int64_t n, float *y, float *dec, int precision)
 {
-    if (!net || n < 0 || (n && (!x || !y))) { set_error("bad argument"); return HP_ERR_INVALID; }
-    if (int rc = check_precision(precision)) return rc;
-    if (n == 0) return HP_OK;
-    Net &N = net->n;
-    HP_CUDA_TRY(cudaSetDevice(N.device));
     const int64_t chunk = std::min<int64_t>(n, STAGE_CHUNK);
-    const bool pin_x = is_pinned_host(x), pin_y = is_pinned_host(y);
+    const bool pin_x = is_pinned_host(x), pin_y = y ? is_pinned_host(y) : true, pin_d = dec ? is_pinned_host(dec) : true;
     if (int rc = ensure_staging(N, chunk, !pin_x, !pin_y)) return rc;
     cudaStream_t s = N.stream, h2d = N.comm_stream, d2h = N.d2h_stream;
     const int nc = (int)((n + chunk - 1) / chunk);
-    // wait until chunk c is back on the host (and bounce it into pageable y)
+    const size_t in_row = (size_t)N_IN * elem;
+    // wait until chunk c is back on the host (and bounce it into pageable memory)
     auto retire = [&](int c) -> int {
         const int b = c & 1;
         const int64_t m = std::min<int64_t>(chunk, n - (int64_t)c * chunk);
         HP_CUDA_TRY(cudaEventSynchronize(N.ev_out[b]));
-        if (!pin_y) memcpy(y + (int64_t)c * chunk * N_OUT, N.pin_out[b], (size_t)m * N_OUT * sizeof(float));
+        if (y && !pin_y) memcpy(y + (int64_t)c * chunk * N_OUT, N.pin_out[b], (size_t)m * N_OUT * sizeof(float));
+        if (dec && !pin_d) memcpy(dec + (int64_t)c * chunk * 48, N.pin_dec[b], (size_t)m * 48 * sizeof(float));
         return 0;
     };
     for (int c = 0; c < nc; c++) {
@@ -476,23 +484,98 @@ int hp_eval_batch(hp_net *net, const float *x, int64_t n, float *y, int precisio
         const int64_t m = std::min<int64_t>(chunk, n - (int64_t)c * chunk);
         if (c >= 2)  // buffer pair b is reused: chunk c-2 must be fully out first
             if (int rc = retire(c - 2)) return rc;
-        const float *src = x + (int64_t)c * chunk * N_IN;
+        const char *src = (const char *)x + (size_t)c * chunk * in_row;
         if (!pin_x) {
-            memcpy(N.pin_in[b], src, (size_t)m * N_IN * sizeof(float));
-            src = N.pin_in[b];
+            memcpy(N.pin_in[b], src, (size_t)m * in_row);
+            src = (const char *)N.pin_in[b];
         }
-        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[b], src, (size_t)m * N_IN * sizeof(float), cudaMemcpyHostToDevice, h2d));
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[b], src, (size_t)m * in_row, cudaMemcpyHostToDevice, h2d));
         HP_CUDA_TRY(cudaEventRecord(N.ev_in[b], h2d));
         HP_CUDA_TRY(cudaStreamWaitEvent(s, N.ev_in[b], 0));
-        if (int rc = eval_device(N, N.dev_in[b], m, N.dev_out[b], precision, s)) return rc;
+        const float *xin = N.dev_in[b];
+        if (norm) {
+            if (int rc = post_normalize_depth(N, (const uint16_t *)N.dev_in[b], m, norm->scale, norm->dmin, norm->dmax, N.dev_norm[b], s)) return rc;
+            xin = N.dev_norm[b];
+        }
+        if (int rc = eval_device(N, xin, m, N.dev_out[b], precision, s)) return rc;
+        if (dec)
+            if (int rc = post_decode(N, N.dev_out[b], m, N.dev_dec[b], s)) return rc;
         HP_CUDA_TRY(cudaEventRecord(N.ev_comp[b], s));
         HP_CUDA_TRY(cudaStreamWaitEvent(d2h, N.ev_comp[b], 0));
-        float *dst = pin_y ? y + (int64_t)c * chunk * N_OUT : N.pin_out[b];
-        HP_CUDA_TRY(cudaMemcpyAsync(dst, N.dev_out[b], (size_t)m * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, d2h));
+        if (y) {
+            float *dst = pin_y ? y + (int64_t)c * chunk * N_OUT : N.pin_out[b];
+            HP_CUDA_TRY(cudaMemcpyAsync(dst, N.dev_out[b], (size_t)m * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, d2h));
+        }
+        if (dec) {
+            float *dst = pin_d ? dec + (int64_t)c * chunk * 48 : N.pin_dec[b];
+            HP_CUDA_TRY(cudaMemcpyAsync(dst, N.dev_dec[b], (size_t)m * 48 * sizeof(float), cudaMemcpyDeviceToHost, d2h));
+        }
         HP_CUDA_TRY(cudaEventRecord(N.ev_out[b], d2h));
     }
     for (int c = std::max(0, nc - 2); c < nc; c++)
         if (int rc = retire(c)) return rc;
+    return HP_OK;
+}
+
+int hp_eval_batch(hp_net *net, const float *x, int64_t n, float *y, int precision)
+{
+    if (!net || n < 0 || (n && (!x || !y))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return eval_host_pipeline(net->n, x, 4, nullptr, n, y, nullptr, precision);
+}
+
+int hp_eval_decode_batch(hp_net *net, const float *x, int64_t n, float *y, float *decoded, int precision)
+{
+    if (!net || n < 0 || (n && (!x || (!y && !decoded)))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return eval_host_pipeline(net->n, x, 4, nullptr, n, y, decoded, precision);
+}
+
+int hp_eval_depth_batch(hp_net *net, const uint16_t *depth, int64_t n, float depth_scale, float dmin, float dmax, float *y, float *decoded,
+                        int precision)
+{
+    if (!net || n < 0 || (n && (!depth || (!y && !decoded))) || !(dmax > dmin)) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    DepthNorm nm{depth_scale, dmin, dmax};
+    return eval_host_pipeline(net->n, depth, 2, &nm, n, y, decoded, precision);
+}
+
+int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax, float *x_dev, void *stream)
+{
+    if (!net || n < 0 || (n && (!depth_dev || !x_dev)) || !(dmax > dmin)) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return post_normalize_depth(net->n, depth_dev, n, depth_scale, dmin, dmax, x_dev, (cudaStream_t)stream);
+}
+
+int hp_decode_batch_device(hp_net *net, const float *y_dev, int64_t n, float *decoded_dev, void *stream)
+{
+    if (!net || n < 0 || (n && (!y_dev || !decoded_dev))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return post_decode(net->n, y_dev, n, decoded_dev, (cudaStream_t)stream);
+}
+
+int hp_decode_batch(hp_net *net, const float *y, int64_t n, float *decoded)
+{
+    if (!net || n < 0 || (n && (!y || !decoded))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    for (int64_t b = 0; b < n; b += STAGE_CHUNK) {
+        const int64_t m = std::min<int64_t>(STAGE_CHUNK, n - b);
+        if (int rc = ensure_staging(N, m, false, false)) return rc;
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_out[0], y + b * N_OUT, (size_t)m * N_OUT * sizeof(float), cudaMemcpyHostToDevice, N.stream));
+        if (int rc = post_decode(N, N.dev_out[0], m, N.dev_dec[0], N.stream)) return rc;
+        HP_CUDA_TRY(cudaMemcpyAsync(decoded + b * 48, N.dev_dec[0], (size_t)m * 48 * sizeof(float), cudaMemcpyDeviceToHost, N.stream));
+        HP_CUDA_TRY(cudaStreamSynchronize(N.stream));
+    }
     return HP_OK;
 }
 

@@ -93,6 +93,9 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
                   cudaStream_t s);
 int sgd_apply(Net &net, float alpha, cudaStream_t s);
 int fp32_init_attributes();
+// ---- pre/post steps (hp_post.cu) ----------------------------------------------
+int post_normalize_depth(Net &net, const uint16_t *d, int64_t n, float depth_scale, float dmin, float dmax, float *x, cudaStream_t s);
+int post_decode(Net &net, const float *y, int64_t n, float *out, cudaStream_t s);
 // ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);
 int tc_refresh_weights(Net &net, cudaStream_t s);
@@ -118,6 +121,9 @@ struct Net {
     float *dev_in[2] = {nullptr, nullptr};
     float *dev_out[2] = {nullptr, nullptr};
     float *dev_t = nullptr, *dev_mse = nullptr;
+    float *dev_norm[2] = {nullptr, nullptr};   // normalised crops when the upload is 16-bit depth
+    float *dev_dec[2] = {nullptr, nullptr};    // decoded peaks [chunk][48]
+    float *pin_dec[2] = {nullptr, nullptr};
     int64_t stage_cap = 0, pin_in_cap = 0, pin_out_cap = 0;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_bucket[3] = {nullptr, nullptr, nullptr},
                 ev_comm = nullptr;

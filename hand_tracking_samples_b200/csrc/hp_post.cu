@@ -1,0 +1,123 @@
+// hp_post.cu -- the two steps that sit directly before and after the CNN in the reference's tracker
+// (SURVEY.md 8f rows 3 and 1), as device kernels so that a caller can upload 16-bit depth crops (8 KB instead of
+// 16 KB per crop) and download decoded peaks (192 B instead of 9 KB per crop):
+//   normalize_depth_kernel  include/handtrack.h:700   depth -> [0,1] crop:  clamp(1 - (d*scale - dmin)/(dmax - dmin), 0, 1)
+//   decode_kernel           include/handtrack.h:218-241 (numeric core of CNNOutputAnalysis): per 2-D heatmap ImageFindMax,
+//                           PeakSubPixel, PeakVolume, peak value (include/misc_image.h:298-336); per 1-D heatmap
+//                           max_element + PeakSubPixel1D (misc_image.h:340-350, 389-399)
+// Both are bit-exact against the reference routines on identical inputs (explicitly un-fused multiply/add, the
+// reference's sequential summation order, IEEE division).
+#include "hp_common.cuh"
+
+namespace hp {
+
+#define LAUNCH_CHECK(net)                \
+    do {                                 \
+        (net).launches++;                \
+        HP_CUDA_TRY(cudaGetLastError()); \
+    } while (0)
+
+__global__ void __launch_bounds__(256) normalize_depth_kernel(const uint16_t *__restrict__ d, float *__restrict__ x, int64_t count8, float depth_scale,
+                                                              float dmin, float dmax)
+{
+    const float range = __fsub_rn(dmax, dmin);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 raw = reinterpret_cast<const uint4 *>(d)[i];   // 8 depth samples
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t v = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+            const float z = __fmul_rn((float)v, depth_scale);
+            float a = __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(z, dmin), range));
+            a = (a < 0.0f) ? 0.0f : a;   // std::max(a, 0.0f), third_party/geometric.h:62
+            a = (1.0f < a) ? 1.0f : a;   // std::min(.., 1.0f)
+            o[k] = a;
+        }
+        reinterpret_cast<float4 *>(x)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4 *>(x)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// one crop per CTA: warp w decodes 2-D heatmap w; threads 0..15 then decode the sixteen 1-D heatmaps
+__global__ void __launch_bounds__(256) decode_kernel(const float *__restrict__ y, float *__restrict__ out)
+{
+    __shared__ float sy[N_OUT];
+    const int64_t crop = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N_OUT; i += 256) sy[i] = y[crop * N_OUT + i];
+    __syncthreads();
+    const float *m = sy + warp * 256;
+    // ImageFindMax: first strict maximum in raster order, starting from pixel (0,0) (misc_image.h:300-304)
+    float bv = m[lane];
+    int bi = lane;
+    if (lane != 0 && bv != bv) bv = -INFINITY;   // a NaN that is not the starting pixel never wins a `>` comparison
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        const float v = m[lane + 32 * i];
+        if (v > bv) { bv = v; bi = lane + 32 * i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const bool keep_nan0 = (bi == 0 && bv != bv);     // pixel (0,0) NaN: nothing compares greater
+        const bool other_nan0 = (oi == 0 && ov != ov);
+        if (other_nan0 || (!keep_nan0 && (ov > bv || (ov == bv && oi < bi)))) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+        const int bx = bi & 15, by = bi >> 4;
+        float wsum = 0.0f, vx = 0.0f, vy = 0.0f;
+        for (int sy_ = max(0, by - 1); sy_ < min(16, by + 2); sy_++)
+            for (int sx = max(0, bx - 1); sx < min(16, bx + 2); sx++) {   // PeakSubPixel, misc_image.h:316-322
+                const float w = m[sy_ * 16 + sx];
+                vx = __fadd_rn(vx, __fmul_rn((float)sx, w));
+                vy = __fadd_rn(vy, __fmul_rn((float)sy_, w));
+                wsum = __fadd_rn(wsum, w);
+            }
+        const float px = (wsum == 0) ? (float)bx : __fdiv_rn(vx, wsum);
+        const float py = (wsum == 0) ? (float)by : __fdiv_rn(vy, wsum);
+        const int rx = (int)__fadd_rn(px, 0.5f), ry = (int)__fadd_rn(py, 0.5f);   // PeakVolume, misc_image.h:330
+        float vol = 0.0f;
+        for (int sy_ = max(0, ry - 1); sy_ < min(16, ry + 2); sy_++)
+            for (int sx = max(0, rx - 1); sx < min(16, rx + 2); sx++) vol = __fadd_rn(vol, m[sy_ * 16 + sx]);
+        float *o = out + crop * 48 + 4 * warp;
+        o[0] = px;
+        o[1] = py;
+        o[2] = vol;
+        o[3] = m[bi];
+    }
+    if (tid < 16) {   // Peaks1D, misc_image.h:389-399
+        const float *r = sy + 2048 + 16 * tid;
+        int p = 0;
+        for (int x = 1; x < 16; x++)
+            if (r[p] < r[x]) p = x;
+        float v = 0.0f, wsum = 0.0f;
+        for (int i = max(0, p - 1); i < min(16, p + 2); i++) {
+            const float w = r[i];
+            v = __fadd_rn(v, __fmul_rn((float)i, w));
+            wsum = __fadd_rn(wsum, w);
+        }
+        out[crop * 48 + 32 + tid] = __fdiv_rn((wsum == 0) ? (float)p : __fdiv_rn(v, wsum), 15.0f);
+    }
+}
+
+int post_normalize_depth(Net &net, const uint16_t *d, int64_t n, float depth_scale, float dmin, float dmax, float *x, cudaStream_t s)
+{
+    const int64_t count8 = n * (N_IN / 8);
+    int blocks = (int)((count8 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    normalize_depth_kernel<<<blocks, 256, 0, s>>>(d, x, count8, depth_scale, dmin, dmax);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+int post_decode(Net &net, const float *y, int64_t n, float *out, cudaStream_t s)
+{
+    decode_kernel<<<(unsigned)n, 256, 0, s>>>(y, out);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+}  // namespace hp

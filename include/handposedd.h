@@ -126,6 +126,28 @@ HP_API int hp_eval_batch(hp_net *net, const float *x, int64_t n, float *y, int p
 HP_API int hp_eval_batch_device(hp_net *net, const float *x_dev, int64_t n, float *y_dev,
                                 int precision, void *stream);
 
+/* ---- the steps on either side of Eval in the reference's tracker ---- */
+
+#define HP_N_DECODED 48
+/* Replaces: the numeric core of CNNOutputAnalysis::CNNOutputAnalysis (include/handtrack.h:218-241) built on
+ * ImageFindMax / PeakSubPixel / PeakVolume / Peaks1D (include/misc_image.h:298-336, 340-350, 389-399).
+ * decoded[n][48] = for each of the 8 landmark heatmaps (image_point.x, image_point.y, confidence, peak value
+ * [crays.w]), then the 16 Peaks1D values (CNNOutputAnalysis::vals).  Bit-exact on identical y.  HOST buffers. */
+HP_API int hp_decode_batch(hp_net *net, const float *y, int64_t n, float *decoded);
+HP_API int hp_decode_batch_device(hp_net *net, const float *y_dev, int64_t n, float *decoded_dev, void *stream);
+/* Eval followed by the decode in one pipelined call: y and decoded are each optional (not both NULL); with
+ * y == NULL only 192 bytes per crop travel back over PCIe instead of 9,216. */
+HP_API int hp_eval_decode_batch(hp_net *net, const float *x, int64_t n, float *y, float *decoded, int precision);
+/* Replaces: the crop normalisation of HandTracker::update_cnn_model_threadsafe (include/handtrack.h:700) followed
+ * by Eval (handtrack.h:701) and, optionally, the decode (handtrack.h:702): takes the segmented 64x64 crops as the
+ * camera's 16-bit depth (8 KB per crop over PCIe instead of 16 KB) and applies
+ *     x = clamp(1 - (d*depth_scale - dmin) / (dmax - dmin), 0, 1)
+ * on the device, bit-exactly.  The reference uses drange = {0.1, 0.7} and depth_scale = 0.001. */
+HP_API int hp_eval_depth_batch(hp_net *net, const uint16_t *depth, int64_t n, float depth_scale, float dmin, float dmax, float *y,
+                               float *decoded, int precision);
+HP_API int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax,
+                                     float *x_dev, void *stream);
+
 /* ---- training ------------------------------------------------------------ */
 
 /* Replaces: CNN::Train (cnn.h:558-580), batched.  One optimiser step on a

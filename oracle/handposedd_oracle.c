@@ -457,3 +457,74 @@ ORC_API void orc_init_xavier(float *params)
     r = sqrtf(6.0f / (FC2_IN + FC2_OUT));
     for (int i = 0; i < FC2_IN * FC2_OUT; i++) params[OFF_F2W + i] = next_uniform(-r, r);
 }
+
+/* ---- CNN output decode -------------------------------------------------
+ * The numeric core of CNNOutputAnalysis::CNNOutputAnalysis (include/handtrack.h:218-241):
+ * per 2-D heatmap ImageFindMax (first maximum in raster order, misc_image.h:298-305), PeakSubPixel
+ * (3x3 weighted centroid, misc_image.h:312-324), PeakVolume (3x3 sum around the rounded centroid,
+ * misc_image.h:328-336) and the peak value; per 1-D heatmap std::max_element + PeakSubPixel1D
+ * (misc_image.h:340-350, 389-399).  out[48] = 8 x (px, py, confidence, peak) then 16 values.
+ * Pinned bit-exactly against oracle/_ref/libpostref.so (tests/test_oracle.py). */
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+ORC_API void orc_decode(const float *y, long n, float *out)
+{
+    for (long b = 0; b < n; b++) {
+        const float *yy = y + b * N_OUT;
+        float *o = out + b * 48;
+        for (int i = 0; i < 8; i++) {
+            const float *m = yy + 256 * i;
+            int bx = 0, by = 0;
+            for (int py = 0; py < 16; py++)
+                for (int px = 0; px < 16; px++)
+                    if (m[py * 16 + px] > m[by * 16 + bx]) { bx = px; by = py; }
+            float wsum = 0.0f, vx = 0.0f, vy = 0.0f;
+            for (int sy = imax(0, by - 1); sy < imin(16, by + 2); sy++)
+                for (int sx = imax(0, bx - 1); sx < imin(16, bx + 2); sx++) {
+                    float w = m[sy * 16 + sx];
+                    float tx = (float)sx * w, ty = (float)sy * w;
+                    vx = vx + tx;
+                    vy = vy + ty;
+                    wsum += w;
+                }
+            float px = (wsum == 0) ? (float)bx : vx / wsum;
+            float py = (wsum == 0) ? (float)by : vy / wsum;
+            int rx = (int)(px + 0.5f), ry = (int)(py + 0.5f);
+            float vol = 0.0f;
+            for (int sy = imax(0, ry - 1); sy < imin(16, ry + 2); sy++)
+                for (int sx = imax(0, rx - 1); sx < imin(16, rx + 2); sx++) vol += m[sy * 16 + sx];
+            o[4 * i + 0] = px;
+            o[4 * i + 1] = py;
+            o[4 * i + 2] = vol;
+            o[4 * i + 3] = m[16 * by + bx];
+        }
+        for (int row = 0; row < 16; row++) {
+            const float *r = yy + 2048 + 16 * row;
+            int p = 0;
+            for (int x = 1; x < 16; x++)
+                if (r[p] < r[x]) p = x; /* std::max_element: first of the largest */
+            float v = 0.0f, wsum = 0.0f;
+            for (int i = imax(0, p - 1); i < imin(16, p + 2); i++) {
+                float w = r[i];
+                float tt = (float)i * w;
+                v = v + tt;
+                wsum += w;
+            }
+            o[32 + row] = ((wsum == 0) ? (float)p : v / wsum) / (float)(16 - 1);
+        }
+    }
+}
+
+/* ---- depth -> [0,1] crop normalisation, include/handtrack.h:700 ---------
+ * (float)clamp(1.0f - (d*depth_scale - dmin) / (dmax - dmin), 0.0f, 1.0f), clamp = min(max(a,mn),mx)
+ * (third_party/geometric.h:62). */
+ORC_API void orc_normalize_depth(const unsigned short *d, long count, float depth_scale, float dmin, float dmax, float *out)
+{
+    for (long i = 0; i < count; i++) {
+        float z = (float)d[i] * depth_scale;
+        float a = 1.0f - (z - dmin) / (dmax - dmin);
+        a = a < 0.0f ? 0.0f : a; /* std::max(a, 0) */
+        a = 1.0f < a ? 1.0f : a; /* std::min(.., 1) */
+        out[i] = a;
+    }
+}

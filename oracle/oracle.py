@@ -44,6 +44,10 @@ def have_ref() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libcnnref.so"))
 
 
+def have_postref() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libpostref.so"))
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
@@ -65,6 +69,9 @@ class Oracle:
         L.orc_train_minibatch.argtypes = [_f32p, _f32p, _f32p, C.c_long, C.c_float, _f64p, _f32p, C.c_int, C.c_void_p]
         L.orc_peek.argtypes = [C.c_void_p, C.c_int, _f32p]
         L.orc_init_xavier.argtypes = [_f32p]
+        L.orc_decode.argtypes = [_f32p, C.c_long, _f32p]
+        L.orc_normalize_depth.argtypes = [np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS"), C.c_long, C.c_float, C.c_float,
+                                          C.c_float, _f32p]
         self.L = L
         self.ws = C.c_void_p(L.orc_ws_create())
 
@@ -109,6 +116,19 @@ class Oracle:
         self.L.orc_train_minibatch(params, x, t, x.shape[0], alpha, g, mse, int(apply), self.ws)
         return g, mse
 
+    def decode(self, y):
+        """CNNOutputAnalysis numeric core: y[n][2304] -> [n][48]."""
+        y = _f32(y).reshape(-1, N_OUT)
+        out = np.empty((y.shape[0], 48), np.float32)
+        self.L.orc_decode(y, y.shape[0], out)
+        return out
+
+    def normalize_depth(self, d, depth_scale=0.001, dmin=0.1, dmax=0.7):
+        d = np.ascontiguousarray(d, np.uint16)
+        out = np.empty(d.shape, np.float32)
+        self.L.orc_normalize_depth(d.reshape(-1), d.size, depth_scale, dmin, dmax, out.reshape(-1))
+        return out
+
     _PEEK = {0: 57600, 1: 57600, 3: 3600, 5: 9216, 6: 2304, 8: 2048, 9: 2304, 10: 2304,
              109: 2304, 107: 2048, 106: 2304, 104: 9216, 103: 3600, 100: 57600}
 
@@ -116,6 +136,32 @@ class Oracle:
         out = np.empty(self._PEEK[which], np.float32)
         n = self.L.orc_peek(self.ws, which, out)
         assert n == out.size
+        return out
+
+
+class PostRef:
+    """The reference's decode / crop-normalisation routines (oracle/_ref/libpostref.so, ref_post_shim.cpp)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libpostref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = C.CDLL(path)
+        L.ref_decode.argtypes = [_f32p, C.c_long, _f32p]
+        L.ref_normalize_depth.argtypes = [np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS"), C.c_long, C.c_float, C.c_float,
+                                          C.c_float, _f32p]
+        self.L = L
+
+    def decode(self, y):
+        y = _f32(y).reshape(-1, N_OUT)
+        out = np.empty((y.shape[0], 48), np.float32)
+        self.L.ref_decode(y, y.shape[0], out)
+        return out
+
+    def normalize_depth(self, d, depth_scale=0.001, dmin=0.1, dmax=0.7):
+        d = np.ascontiguousarray(d, np.uint16)
+        out = np.empty(d.shape, np.float32)
+        self.L.ref_normalize_depth(d.reshape(-1), d.size, depth_scale, dmin, dmax, out.reshape(-1))
         return out
 
 

@@ -1,0 +1,53 @@
+// ref_post_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// C-ABI access to the UNMODIFIED reference routines on either side of the CNN,
+// compiled in place from /root/reference (oracle/Makefile, -I$(REFERENCE_ROOT)) into oracle/_ref/libpostref.so:
+//   ref_decode            the numeric core of CNNOutputAnalysis::CNNOutputAnalysis (include/handtrack.h:218-241)
+//                         built from the reference's own ImageFindMax / PeakSubPixel / PeakVolume / Peaks1D
+//                         (include/misc_image.h:298-336, 389-399) in the constructor's call order
+//   ref_normalize_depth   the depth -> [0,1] crop normalisation of include/handtrack.h:700
+// handtrack.h itself is not included (it does not compile headless under g++), so the two call
+// sequences are restated here; every arithmetic routine they call is the reference's.
+#include <cfloat>
+#include <cstring>
+#include "third_party/linalg.h"
+#include "third_party/geometric.h"
+#include "include/misc_image.h"
+
+extern "C" {
+
+// out[48]: 8 x (image_point.x, image_point.y, confidence, peak value) then the 16 Peaks1D values
+__attribute__((visibility("default"))) void ref_decode(const float *cnn_output, long n, float *out)
+{
+    const int2 hdim(16, 16);
+    for (long b = 0; b < n; b++) {
+        const float *y = cnn_output + b * 2304;
+        float *o = out + b * 48;
+        for (int i = 0; i < 8; i++) {                        // handtrack.h:221-234
+            const float *base = y + product(hdim) * i;
+            Image<float> fmap(hdim, std::vector<float>(base, base + product(hdim)));
+            int2 mx = ImageFindMax(fmap);                    // handtrack.h:226
+            float2 p = PeakSubPixel(fmap, mx);               // handtrack.h:230
+            o[4 * i + 0] = p.x;
+            o[4 * i + 1] = p.y;
+            o[4 * i + 2] = PeakVolume(fmap, p);              // handtrack.h:232
+            o[4 * i + 3] = base[hdim.x * mx.y + mx.x];       // handtrack.h:234 (crays.w)
+        }
+        const float *vptr = y + product(hdim) * 8;           // handtrack.h:236-239
+        int2 vdim(16, 16);
+        Image<float> vmap(vdim, std::vector<float>(vptr, vptr + product(vdim)));
+        std::vector<float> vals = Peaks1D(vmap);
+        for (int k = 0; k < 16; k++) o[32 + k] = vals[k];
+    }
+}
+
+// handtrack.h:700: (float)clamp(1.0f - (d*depth_scale - drange.x) / (drange.y - drange.x), 0.0f, 1.0f)
+__attribute__((visibility("default"))) void ref_normalize_depth(const unsigned short *d, long count, float depth_scale, float dmin, float dmax,
+                                                                float *out)
+{
+    float2 drange = {dmin, dmax};
+    for (long i = 0; i < count; i++)
+        out[i] = (float)clamp(1.0f - (d[i] * depth_scale - drange.x) / (drange.y - drange.x), 0.0f, 1.0f);
+}
+
+}  // extern "C"

@@ -83,3 +83,20 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def main_post():
+    """Fixtures for the decode / depth-normalisation rows, from oracle/_ref/libpostref.so."""
+    from oracle.oracle import PostRef
+    r = PostRef()
+    np.save(os.path.join(OUT, "decode_init.npy"), r.decode(np.load(os.path.join(OUT, "eval_init.npy"))))
+    np.save(os.path.join(OUT, "decode_peaky.npy"), r.decode(np.load(os.path.join(OUT, "eval_peaky.npy"))))
+    rng = np.random.default_rng(77)
+    d = rng.integers(0, 1200, (2, 4096)).astype(np.uint16)
+    d[0, :64] = 0
+    d[1, :64] = 65535
+    np.savez_compressed(os.path.join(OUT, "depth_norm.npz"), depth=d, x=r.normalize_depth(d))
+
+
+if __name__ == "__main__" and "--post" in sys.argv:
+    main_post()

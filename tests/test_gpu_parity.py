@@ -375,3 +375,45 @@ def test_loss_curves_over_1k_steps(orc, p0):
             for k, (off, cnt) in LAYOUT.items():
                 assert maxnorm_err(got_p[off:off + cnt], p[off:off + cnt]) <= weight_tol, k
         del net
+
+
+# ---- output decode and 16-bit depth upload ----------------------------
+def test_decode_is_bit_exact(net, orc):
+    rng = np.random.default_rng(0)
+    y = rng.random((40, 2304), dtype=np.float32)
+    y[3, :256] = 0
+    y[4, 256:512] = 0.5
+    y[5, 2048:2064] = 0
+    y[6, 512 + 255] = 9.0
+    y[7, 2048 + 16 * 3 + 15] = 9.0
+    assert np.array_equal(net.decode_batch(y), orc.decode(y))
+    for name in ("init", "peaky"):
+        assert np.array_equal(net.decode_batch(golden("eval_%s.npy" % name)), golden("decode_%s.npy" % name))
+    assert net.decode_batch(np.zeros((0, 2304), np.float32)).shape == (0, 48)
+
+
+def test_depth_upload_path(net, orc, p0):
+    import torch
+    g = golden("depth_norm.npz")
+    d = np.concatenate([g["depth"], np.random.default_rng(5).integers(0, 900, (9, 4096)).astype(np.uint16)])
+    n = d.shape[0]
+    # device normalisation is bit-exact (handtrack.h:700)
+    dd = torch.from_numpy(d.astype(np.int32)).to(torch.uint16).cuda() if hasattr(torch, "uint16") else None
+    if dd is not None:
+        xd = torch.empty((n, 4096), device="cuda")
+        from hand_tracking_samples_b200 import capi
+        capi.check(net.L.hp_normalize_depth_device(net.h, dd.data_ptr(), n, 0.001, 0.1, 0.7, xd.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(xd.cpu().numpy(), orc.normalize_depth(d))
+        assert np.array_equal(xd.cpu().numpy()[:2], g["x"])
+    # u16 upload + Eval + decode == fp32 upload of the normalised crops (same kernels downstream)
+    x = orc.normalize_depth(d)
+    y_ref = net.eval_batch(x)
+    y, dec = net.eval_depth_batch(d)
+    assert np.array_equal(y, y_ref)
+    assert np.array_equal(dec, orc.decode(y_ref))
+    assert maxnorm_err(y, orc.eval(p0, x)) <= FP32_TOL
+    dec_only = net.eval_decode_batch(x, want_y=False)
+    assert np.array_equal(dec_only, dec)
+    ytc, dectc = net.eval_depth_batch(d, precision=hp.PRECISION_TENSOR)
+    assert maxnorm_err(ytc, y_ref) <= TC_TOL

@@ -153,3 +153,39 @@ def test_reference_saveb_file_layout(tmp_path, p0):
     r.saveb_file(path)
     raw = np.fromfile(path, np.float32)
     assert raw.size == N_PARAMS and np.array_equal(raw, p0)
+
+
+# ---- decode and depth normalisation ---------------------------------
+def _tricky_outputs():
+    rng = np.random.default_rng(0)
+    y = rng.random((40, 2304), dtype=np.float32)
+    y[3, :256] = 0            # empty heatmap: wsum == 0 branch of PeakSubPixel
+    y[4, 256:512] = 0.5       # constant heatmap: ImageFindMax keeps pixel (0,0)
+    y[5, 2048:2064] = 0       # empty 1-D heatmap
+    y[6, 512 + 255] = 9.0     # peak in the last corner (clamped 3x3 window)
+    y[7, 2048 + 16 * 3 + 15] = 9.0
+    return y
+
+
+def test_decode_matches_golden(orc):
+    for name in ("init", "peaky"):
+        y = np.load(os.path.join(GOLDEN, "eval_%s.npy" % name))
+        assert np.array_equal(orc.decode(y), np.load(os.path.join(GOLDEN, "decode_%s.npy" % name)))
+
+
+def test_depth_normalisation_matches_golden(orc):
+    g = np.load(os.path.join(GOLDEN, "depth_norm.npz"))
+    x = orc.normalize_depth(g["depth"])
+    assert np.array_equal(x, g["x"]) and x.min() == 0.0 and x.max() == 1.0
+
+
+def test_decode_and_normalise_bit_exact_against_reference(orc):
+    from oracle.oracle import PostRef, have_postref
+    if not have_postref():
+        pytest.skip("oracle/_ref/libpostref.so not built")
+    r = PostRef()
+    y = _tricky_outputs()
+    assert np.array_equal(orc.decode(y), r.decode(y))
+    d = np.random.default_rng(1).integers(0, 65536, (3, 4096)).astype(np.uint16)
+    assert np.array_equal(orc.normalize_depth(d), r.normalize_depth(d))
+    assert np.array_equal(orc.normalize_depth(d, 0.000125, 0.2, 0.9), r.normalize_depth(d, 0.000125, 0.2, 0.9))
