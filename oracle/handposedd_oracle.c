@@ -13,7 +13,7 @@
  * reference header itself, compiled in place from /root/reference by
  * oracle/Makefile into oracle/_ref/libcnnref.so (oracle/ref_shim.cpp), and
  * against the fixtures in tests/golden/ that were produced by that library
- * (tests/golden/make_golden.py).  tests/test_oracle_vs_ref.py demands
+ * (tests/golden/make_golden.py).  tests/test_oracle.py demands
  * BIT-EXACT agreement (Eval outputs, per-sample gradients, weights after N
  * Train steps, Init() weights) when both are built with
  * `-O2 -msse2 -ffp-contract=off`.
