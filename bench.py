@@ -346,6 +346,22 @@ def main():
         except Exception as e:  # the training arm must not take the headline down with it
             line["train"] = {"error": str(e)[:200]}
 
+        # ---- BASELINE.json configs[0]: one crop at a time through the drop-in call (the reference's own usage pattern) ----
+        try:
+            from hand_tracking_samples_b200 import synth as _synth
+            x1, t1 = _synth.depthlike_crops(1, 3), _synth.heatmap_labels(1, 4)
+            lat = {}
+            for name, prec in (("fp32", hp.PRECISION_FP32), ("tensor", hp.PRECISION_TENSOR)):
+                for _ in range(20):
+                    net.eval_batch(x1, precision=prec)
+                t0 = time.perf_counter()
+                for _ in range(200):
+                    net.eval_batch(x1, precision=prec)
+                lat["eval_us_" + name] = (time.perf_counter() - t0) / 200 * 1e6
+            line["single_crop"] = dict(lat, note="host-call latency of CNN::Eval on one crop, pageable host buffers, H2D+kernels+D2H+sync")
+        except Exception as e:
+            line["single_crop"] = {"error": str(e)[:200]}
+
         # ---- CPU baseline: the reference's own code on this box's host cores (rank 0, bounded sample) ----
         if rank == 0:
             threads = os.cpu_count() or 1

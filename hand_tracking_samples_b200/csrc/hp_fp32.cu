@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(256) conv1_fwd_fp32(const float *__restrict__ 
         patch[r][0] = lo.x; patch[r][1] = lo.y; patch[r][2] = lo.z; patch[r][3] = lo.w;
         patch[r][4] = hi.x; patch[r][5] = hi.y; patch[r][6] = hi.z; patch[r][7] = hi.w;
     }
-    for (int co = 0; co < C1_CO; co++) {
+    // blockIdx.y splits the 16 output channels (small batches: 4 CTAs per crop cut the latency of a lone Eval)
+    const int co_per = C1_CO / gridDim.y;
+    for (int co = blockIdx.y * co_per; co < (int)(blockIdx.y + 1) * co_per; co++) {
         float acc[4][4];
         const float bias = b[co];
 #pragma unroll
@@ -690,7 +692,7 @@ int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, c
 {
     Workspace &w = net.ws;
     const float *P = net.params;
-    conv1_fwd_fp32<<<(unsigned)n, 256, 0, s>>>(x, P, w.p1, w.idx1);
+    conv1_fwd_fp32<<<dim3((unsigned)n, n < 148 ? 4 : 1), 256, 0, s>>>(x, P, w.p1, w.idx1);
     LAUNCH_CHECK(net);
     im2col_p1<<<(unsigned)n, 256, 0, s>>>(w.p1, w.col);
     LAUNCH_CHECK(net);
@@ -705,6 +707,54 @@ int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, c
     return 0;
 }
 
+// out[m][j] = act(bias[j] + sum_s partial[s][m][j]), s ascending: the ordered tail of a split-K LFull::forward
+template <bool TANH>
+__global__ void __launch_bounds__(256) bias_reduce_act(const float *__restrict__ partial, const float *__restrict__ bias, float *__restrict__ out,
+                                                       int S, int M, int N)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= M * N) return;
+    float a = bias[i % N];
+    for (int s = 0; s < S; s++) a += partial[(size_t)s * M * N + i];
+    out[i] = TANH ? tanh_ref(a) : a;
+}
+
+// LFull::forward for a handful of crops (the reference's own use: one Eval per camera frame): the layer is a
+// stream of 18.9 MB of weights, so K is split 8 ways over the grid to get every SM pulling on HBM.
+constexpr int SMALL_BATCH = 64, SMALL_SPLITS = 8;
+template <bool TANH>
+static int fc_small(Net &net, const float *x, int M, int K, const float *W, const float *bias, int N, float *out, cudaStream_t s)
+{
+    const int klen = K / SMALL_SPLITS;   // 288 or 256: multiples of 16
+    GemmArgs g{M, N, K, x, K, W, N, net.ws.partial, N, nullptr, nullptr, klen, 0};
+    if (int rc = launch_sgemm<128, true, false, EPI_STORE>(net, g, SMALL_SPLITS, s)) return rc;
+    bias_reduce_act<TANH><<<(M * N + 255) / 256, 256, 0, s>>>(net.ws.partial, bias, out, SMALL_SPLITS, M, N);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// out[m][i] = (1 - h[m][i]^2) * sum_s partial[s][m][i]: ordered tail of a split-K LFull::backward + TanH::df
+__global__ void __launch_bounds__(256) dtanh_reduce(const float *__restrict__ partial, const float *__restrict__ h, float *__restrict__ out, int S,
+                                                    int MN)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= MN) return;
+    float a = 0.f;
+    for (int s = 0; s < S; s++) a += partial[(size_t)s * MN + i];
+    const float hv = h[i];
+    out[i] = (1.0f - hv * hv) * a;
+}
+// D[M][Nin] = (E[M][Kout] * W[Nin][Kout]^T) .* (1 - H^2) for a handful of samples, K split over the grid
+static int fc_dx_small(Net &net, const float *E, int M, int Kout, const float *W, int Nin, const float *H, float *D, cudaStream_t s)
+{
+    const int klen = Kout / SMALL_SPLITS;
+    GemmArgs g{M, Nin, Kout, E, Kout, W, Kout, net.ws.partial, Nin, nullptr, nullptr, klen, 0};
+    if (int rc = launch_sgemm<128, true, true, EPI_STORE>(net, g, SMALL_SPLITS, s)) return rc;
+    dtanh_reduce<<<(M * Nin + 255) / 256, 256, 0, s>>>(net.ws.partial, H, D, SMALL_SPLITS, M * Nin);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
 int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool training, cudaStream_t s)
 {
     Workspace &w = net.ws;
@@ -713,15 +763,24 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
         StageTimer st(net, 0, s);
         if (int rc = fp32_conv_stage(net, x, n, nullptr, s)) return rc;
     }
-    {   // fc1 + tanh
-        StageTimer st(net, 1, s);
-        GemmArgs g{(int)n, FC1_OUT, FC1_IN, w.p2, FC1_IN, P + OFF_F1W, FC1_OUT, w.h1, FC1_OUT, P + OFF_F1B, nullptr, FC1_IN, 0};
-        if (int rc = launch_sgemm<128, true, false, EPI_BIAS_TANH>(net, g, 1, s)) return rc;
-    }
-    {   // fc2 logits
+    if (n <= SMALL_BATCH) {
+        {
+            StageTimer st(net, 1, s);
+            if (int rc = fc_small<true>(net, w.p2, (int)n, FC1_IN, P + OFF_F1W, P + OFF_F1B, FC1_OUT, w.h1, s)) return rc;
+        }
         StageTimer st(net, 2, s);
-        GemmArgs g{(int)n, FC2_OUT, FC2_IN, w.h1, FC2_IN, P + OFF_F2W, FC2_OUT, w.logits, FC2_OUT, P + OFF_F2B, nullptr, FC2_IN, 0};
-        if (int rc = launch_sgemm<128, true, false, EPI_BIAS>(net, g, 1, s)) return rc;
+        if (int rc = fc_small<false>(net, w.h1, (int)n, FC2_IN, P + OFF_F2W, P + OFF_F2B, FC2_OUT, w.logits, s)) return rc;
+    } else {
+        {   // fc1 + tanh
+            StageTimer st(net, 1, s);
+            GemmArgs g{(int)n, FC1_OUT, FC1_IN, w.p2, FC1_IN, P + OFF_F1W, FC1_OUT, w.h1, FC1_OUT, P + OFF_F1B, nullptr, FC1_IN, 0};
+            if (int rc = launch_sgemm<128, true, false, EPI_BIAS_TANH>(net, g, 1, s)) return rc;
+        }
+        {   // fc2 logits
+            StageTimer st(net, 2, s);
+            GemmArgs g{(int)n, FC2_OUT, FC2_IN, w.h1, FC2_IN, P + OFF_F2W, FC2_OUT, w.logits, FC2_OUT, P + OFF_F2B, nullptr, FC2_IN, 0};
+            if (int rc = launch_sgemm<128, true, false, EPI_BIAS>(net, g, 1, s)) return rc;
+        }
     }
     if (!training) {
         StageTimer st(net, 3, s);
@@ -805,7 +864,9 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, 1, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
-    {
+    if (n <= SMALL_BATCH) {
+        if (int rc = fc_dx_small(net, w.dlog, (int)n, FC2_OUT, P + OFF_F2W, FC2_IN, w.h1, w.da1, s)) return rc;
+    } else {
         GemmArgs g{(int)n, FC2_IN, FC2_OUT, w.dlog, FC2_OUT, P + OFF_F2W, FC2_OUT, w.da1, FC2_IN, nullptr, w.h1, FC2_OUT, 0};
         if (int rc = launch_sgemm<128, true, true, EPI_DTANH>(net, g, 1, s)) return rc;
     }
@@ -816,7 +877,9 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, 1, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
-    {
+    if (n <= SMALL_BATCH) {
+        if (int rc = fc_dx_small(net, w.da1, (int)n, FC1_OUT, P + OFF_F1W, FC1_IN, w.p2, w.g2, s)) return rc;
+    } else {
         GemmArgs g{(int)n, FC1_IN, FC1_OUT, w.da1, FC1_OUT, P + OFF_F1W, FC1_OUT, w.g2, FC1_IN, nullptr, w.p2, FC1_OUT, 0};
         if (int rc = launch_sgemm<128, true, true, EPI_DTANH>(net, g, 1, s)) return rc;
     }
