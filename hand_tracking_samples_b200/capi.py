@@ -22,7 +22,7 @@ SYMBOLS = [
     "hp_save_cnnb", "hp_load_cnnb_file", "hp_save_cnnb_file", "hp_eval_batch", "hp_eval_batch_device",
     "hp_decode_batch", "hp_decode_batch_device", "hp_eval_decode_batch", "hp_eval_depth_batch", "hp_normalize_depth_device",
     "hp_train_batch", "hp_train_batch_device", "hp_grad_batch_device", "hp_get_grads", "hp_device_ptrs",
-    "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_shutdown", "hp_launch_count", "hp_profile", "hp_profile_read",
+    "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_set_bf16_gradients", "hp_dp_shutdown", "hp_launch_count", "hp_debug_step_times", "hp_profile", "hp_profile_read",
     "hp_peek", "hp_last_error", "hp_version",
 ]
 
@@ -78,9 +78,11 @@ def lib():
     L.hp_apply_grads_device.argtypes = [vp, fp, vp]
     L.hp_dp_unique_id.argtypes = [vp]
     L.hp_dp_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.hp_dp_set_bf16_gradients.argtypes = [vp, C.c_int]
     L.hp_dp_shutdown.argtypes = [vp]
     L.hp_launch_count.argtypes = [vp]
     L.hp_launch_count.restype = i64
+    L.hp_debug_step_times.argtypes = [vp, vp]
     L.hp_profile.argtypes = [vp, C.c_int]
     L.hp_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     L.hp_peek.argtypes = [vp, C.c_int, i64, vp]

@@ -228,6 +228,9 @@ class CNN:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         capi.check(self.L.hp_dp_init(self.h, buf, rank, world))
 
+    def dp_set_bf16_gradients(self, enable=True):
+        capi.check(self.L.hp_dp_set_bf16_gradients(self.h, int(enable)))
+
     def dp_shutdown(self):
         capi.check(self.L.hp_dp_shutdown(self.h))
 

@@ -14,6 +14,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <atomic>
@@ -187,19 +188,44 @@ static int nccl_bind()
         if (_r != 0) { set_error("%s failed: %s", #expr, g_nccl.GetErrorString(_r)); return HP_ERR_NCCL; } \
     } while (0)
 
-// all-reduce the three gradient buckets behind the backward pass, fc2 first
-static int dp_allreduce(Net &net, cudaStream_t s)
+// The tail of an optimiser step, pipelined per gradient bucket (fc2 | fc1 | conv, in the order backward produces them)
+// on the side stream while the rest of backward still runs on the caller's stream:
+//   wait "bucket's weight gradient done"  ->  NCCL all-reduce (data parallel only)
+//   -> wait "the dX GEMM that reads these weights is done"  ->  SGD on the bucket  ->  rebuild its bf16 shadows
+// The caller's stream then waits once for the whole tail.
+static int finish_step(Net &net, float alpha, int precision, cudaStream_t s)
 {
-    if (net.world <= 1) return 0;
-    const int off[4] = {OFF_F2W, OFF_F1W, 0, 0};
-    const int end[4] = {N_PARAMS, OFF_F2W, OFF_F1W, 0};
+    const int off[3] = {OFF_F2W, OFF_F1W, 0};
+    const int end[3] = {N_PARAMS, OFF_F2W, OFF_F1W};
+    // all-reduces back to back on the (high-priority) comm stream; SGD + shadow refresh of each bucket on a third
+    // stream, so that bucket b+1's all-reduce does not queue behind bucket b's update
+    cudaStream_t cs = net.comm_stream, us = net.d2h_stream;
     for (int b = 0; b < 3; b++) {
-        HP_CUDA_TRY(cudaStreamWaitEvent(net.comm_stream, net.ev_bucket[b], 0));
-        HP_NCCL_TRY(g_nccl.AllReduce(net.grads + off[b], net.grads + off[b], (size_t)(end[b] - off[b]), /*ncclFloat32*/ 7,
-                                     /*ncclSum*/ 0, net.nccl_comm, net.comm_stream));
+        const bool bf16_wire = net.world > 1 && net.dp_bf16 && precision == HP_PRECISION_TENSOR && b < 2;
+        if (net.world > 1) {
+            HP_CUDA_TRY(cudaStreamWaitEvent(cs, net.ev_bucket[b], 0));
+            if (bf16_wire) {
+                // halve the bytes on NVLink: the local sums go out as bf16 and come back as the bf16 sum over ranks
+                if (int rc = grads_to_bf16(net, off[b], end[b] - off[b], cs)) return rc;
+                HP_NCCL_TRY(g_nccl.AllReduce(net.grads_bf + off[b], net.grads_bf + off[b], (size_t)(end[b] - off[b]), /*ncclBfloat16*/ 9,
+                                             /*ncclSum*/ 0, net.nccl_comm, cs));
+                if (int rc = grads_from_bf16(net, off[b], end[b] - off[b], cs)) return rc;
+            } else
+            HP_NCCL_TRY(g_nccl.AllReduce(net.grads + off[b], net.grads + off[b], (size_t)(end[b] - off[b]), /*ncclFloat32*/ 7,
+                                         /*ncclSum*/ 0, net.nccl_comm, cs));
+            HP_CUDA_TRY(cudaEventRecord(net.ev_ar[b], cs));
+            HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_ar[b], 0));
+        } else {
+            HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_bucket[b], 0));
+        }
+        if (b < 2) HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_dx[b], 0));
+        if (int rc = sgd_apply_range(net, alpha, off[b], end[b] - off[b], us)) return rc;
+        if (precision == HP_PRECISION_TENSOR)
+            if (int rc = tc_refresh_bucket(net, b, us)) return rc;
     }
-    HP_CUDA_TRY(cudaEventRecord(net.ev_comm, net.comm_stream));
-    HP_CUDA_TRY(cudaStreamWaitEvent(s, net.ev_comm, 0));
+    HP_CUDA_TRY(cudaEventRecord(net.ev_tail, us));
+    HP_CUDA_TRY(cudaStreamWaitEvent(s, net.ev_tail, 0));
+    net.tc_dirty = (precision != HP_PRECISION_TENSOR);
     return 0;
 }
 
@@ -312,15 +338,26 @@ int hp_create_handposedd(int device, hp_net **out)
     Net &n = h->n;
     n.device = device;
     HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.stream, cudaStreamNonBlocking));
-    HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.comm_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;   // NCCL's CTAs must win SM slots against the compute kernels as soon as any CTA retires
+        HP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        HP_CUDA_TRY(cudaStreamCreateWithPriority(&n.comm_stream, cudaStreamNonBlocking, hi));
+    }
     HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.d2h_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
         HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_in[b], cudaEventDisableTiming));
         HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_out[b], cudaEventDisableTiming));
         HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_comp[b], cudaEventDisableTiming));
     }
-    for (int b = 0; b < 3; b++) HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_bucket[b], cudaEventDisableTiming));
+    // step-timeline events: timing costs ~20 us per step, so it is opt-in (hp_debug_step_times)
+    n.step_timing = getenv("HP_STEP_TIMING") != nullptr;
+    const unsigned evf = n.step_timing ? cudaEventDefault : cudaEventDisableTiming;
+    for (int b = 0; b < 3; b++) HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_bucket[b], evf));
+    HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_start, evf));
     HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_comm, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_dx[b], evf));
+    for (int b = 0; b < 3; b++) HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_ar[b], evf));
+    HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_tail, evf));
     HP_CUDA_TRY(cudaMalloc((void **)&n.params, (size_t)N_PARAMS * sizeof(float)));
     HP_CUDA_TRY(cudaMalloc((void **)&n.grads, (size_t)N_PARAMS * sizeof(float)));
     HP_CUDA_TRY(cudaMemset(n.params, 0, (size_t)N_PARAMS * sizeof(float)));
@@ -377,6 +414,13 @@ int hp_destroy(hp_net *net)
     for (int b = 0; b < 3; b++)
         if (n.ev_bucket[b]) cudaEventDestroy(n.ev_bucket[b]);
     if (n.ev_comm) cudaEventDestroy(n.ev_comm);
+    for (int b = 0; b < 2; b++)
+        if (n.ev_dx[b]) cudaEventDestroy(n.ev_dx[b]);
+    for (int b = 0; b < 3; b++)
+        if (n.ev_ar[b]) cudaEventDestroy(n.ev_ar[b]);
+    if (n.ev_tail) cudaEventDestroy(n.ev_tail);
+    if (n.ev_start) cudaEventDestroy(n.ev_start);
+    if (n.grads_bf) cudaFree(n.grads_bf);
     if (n.prof_ev) {
         for (int i = 0; i < Net::PROF_MAX; i++) cudaEventDestroy(n.prof_ev[i]);
         delete[] n.prof_ev;
@@ -603,9 +647,9 @@ int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, i
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
     cudaStream_t s = (cudaStream_t)stream;
+    HP_CUDA_TRY(cudaEventRecord(N.ev_start, s));
     if (int rc = grad_device(N, x_dev, t_dev, n, mse_dev, precision, s)) return rc;
-    if (int rc = dp_allreduce(N, s)) return rc;
-    return sgd_apply(N, alpha, s);
+    return finish_step(N, alpha, precision, s);
 }
 
 int hp_train_batch(hp_net *net, const float *x, const float *t, int64_t n, float alpha, float *mse_out, int precision)
@@ -662,6 +706,24 @@ int hp_dp_init(hp_net *net, const void *id128, int rank, int world)
     HP_NCCL_TRY(g_nccl.CommInitRank(&N.nccl_comm, world, id, rank));
     N.rank = rank;
     N.world = world;
+    // The persistent tensor-core kernels take one CTA with ~200 KB of shared memory on every SM, which leaves NCCL's
+    // CTAs nowhere to run until a kernel drains.  In data-parallel mode a few SMs are therefore left out of the
+    // persistent grids so that the gradient all-reduce really overlaps the backward pass.
+    if (world > 1 && N.tc) {
+        int reserve = 16;
+        if (const char *e = getenv("HP_DP_RESERVE_SMS")) reserve = atoi(e);
+        tc_set_reserved_sms(N, reserve);
+    }
+    return HP_OK;
+}
+
+int hp_dp_set_bf16_gradients(hp_net *net, int enable)
+{
+    if (!net) { set_error("net is NULL"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    if (enable && !N.grads_bf) HP_CUDA_TRY(cudaMalloc((void **)&N.grads_bf, (size_t)N_PARAMS * sizeof(__nv_bfloat16)));
+    N.dp_bf16 = enable != 0;
     return HP_OK;
 }
 
@@ -708,6 +770,23 @@ int hp_profile_read(hp_net *net, int n_stages, double *total_ms, int64_t *interv
         HP_CUDA_TRY(cudaEventElapsedTime(&ms, N.prof_ev[i], N.prof_ev[i + 1]));
         total_ms[st] += ms;
         intervals[st]++;
+    }
+    return HP_OK;
+}
+
+// Milliseconds from the start of the last hp_train_batch_device call to: bucket 0/1/2 gradients ready, dX 0/1 done,
+// all-reduce 0/1/2 done (data parallel only), update tail done.  out[9].  Diagnostic for the overlap of the tail.
+int hp_debug_step_times(hp_net *net, float *out)
+{
+    if (!net || !out) return HP_ERR_INVALID;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    cudaEvent_t ev[9] = {N.ev_bucket[0], N.ev_bucket[1], N.ev_bucket[2], N.ev_dx[0], N.ev_dx[1], N.ev_ar[0], N.ev_ar[1], N.ev_ar[2], N.ev_tail};
+    for (int i = 0; i < 9; i++) {
+        out[i] = -1.f;
+        if (!N.step_timing || (i >= 5 && i <= 7 && N.world <= 1)) continue;
+        if (cudaEventElapsedTime(&out[i], N.ev_start, ev[i]) != cudaSuccess) { cudaGetLastError(); out[i] = -1.f; }
     }
     return HP_OK;
 }

@@ -92,6 +92,9 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
 int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *mse, bool accumulate,
                   cudaStream_t s);
 int sgd_apply(Net &net, float alpha, cudaStream_t s);
+int sgd_apply_range(Net &net, float alpha, int off, int count, cudaStream_t s);
+int grads_to_bf16(Net &net, int off, int count, cudaStream_t s);
+int grads_from_bf16(Net &net, int off, int count, cudaStream_t s);
 int fp32_init_attributes();
 // ---- pre/post steps (hp_post.cu) ----------------------------------------------
 int post_normalize_depth(Net &net, const uint16_t *d, int64_t n, float depth_scale, float dmin, float dmax, float *x, cudaStream_t s);
@@ -99,6 +102,7 @@ int post_decode(Net &net, const float *y, int64_t n, float *out, cudaStream_t s)
 // ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);
 int tc_refresh_weights(Net &net, cudaStream_t s);
+int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s);   // 0: fc2 shadows, 1: fc1 shadows, 2: conv images
 int tc_init(Net &net);
 void tc_destroy(Net &net);
 
@@ -109,7 +113,7 @@ struct Net {
     int device = 0;
     cudaStream_t stream = nullptr;        // internal stream for the HOST-buffer entry points
     cudaStream_t comm_stream = nullptr;   // gradient all-reduce stream (H2D copy stream of the host-buffer Eval)
-    cudaStream_t d2h_stream = nullptr;    // D2H copy stream of the host-buffer Eval
+    cudaStream_t d2h_stream = nullptr;    // D2H copy stream of the host-buffer Eval; SGD / shadow-refresh stream of the training tail
     float *params = nullptr;              // FP32 master weights, .cnnb order
     float *grads = nullptr;               // FP32 gradient sums, .cnnb order
     Workspace ws;
@@ -126,10 +130,13 @@ struct Net {
     float *pin_dec[2] = {nullptr, nullptr};
     int64_t stage_cap = 0, pin_in_cap = 0, pin_out_cap = 0;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_bucket[3] = {nullptr, nullptr, nullptr},
-                ev_comm = nullptr;
+                ev_comm = nullptr, ev_dx[2] = {nullptr, nullptr}, ev_ar[3] = {nullptr, nullptr, nullptr}, ev_tail = nullptr, ev_start = nullptr;   // ev_dx[b]: the dX GEMM that reads bucket b's weights is done
     // data parallelism
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    bool dp_bf16 = false;                 // FC gradient buckets travel as bf16 (tensor-precision steps only)
+    __nv_bfloat16 *grads_bf = nullptr;    // wire buffer, .cnnb order
+    bool step_timing = false;
     int64_t launches = 0;
     int64_t last_n = 0;
     // per-stage timing (hp_profile): a pool of events, (stage, begin, end) triples

@@ -870,6 +870,7 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         GemmArgs g{(int)n, FC2_IN, FC2_OUT, w.dlog, FC2_OUT, P + OFF_F2W, FC2_OUT, w.da1, FC2_IN, nullptr, w.h1, FC2_OUT, 0};
         if (int rc = launch_sgemm<128, true, true, EPI_DTANH>(net, g, 1, s)) return rc;
     }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_dx[0], s));
     // ---- fc1
     if (int rc = colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
     {
@@ -883,6 +884,7 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         GemmArgs g{(int)n, FC1_IN, FC1_OUT, w.da1, FC1_OUT, P + OFF_F1W, FC1_OUT, w.g2, FC1_IN, nullptr, w.p2, FC1_OUT, 0};
         if (int rc = launch_sgemm<128, true, true, EPI_DTANH>(net, g, 1, s)) return rc;
     }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_dx[1], s));
     if (int rc = fp32_conv_backward_impl(net, x, n, w.g2, false, accumulate, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));
     return 0;
@@ -943,6 +945,48 @@ int fp32_softmax_loss(Net &net, const float *logits, float *y, const float *t, f
 int fp32_colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, bool accumulate, cudaStream_t s)
 {
     return colsum(net, in, R, ncols, dst, accumulate, s);
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restrict__ src, uint2 *__restrict__ dst, int n4)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 v = src[i];
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        dst[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    }
+}
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const uint2 *__restrict__ src, float4 *__restrict__ dst, int n4)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const uint2 v = src[i];
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.y));
+        dst[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+// gradient bucket [off, off+count) -> bf16 wire buffer and back (data-parallel bf16 transport)
+int grads_to_bf16(Net &net, int off, int count, cudaStream_t s)
+{
+    f32_to_bf16_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4 *>(net.grads + off), reinterpret_cast<uint2 *>(net.grads_bf + off), count / 4);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+int grads_from_bf16(Net &net, int off, int count, cudaStream_t s)
+{
+    bf16_to_f32_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const uint2 *>(net.grads_bf + off), reinterpret_cast<float4 *>(net.grads + off), count / 4);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// SGD over one gradient bucket [off, off+count) (both multiples of 4 floats)
+int sgd_apply_range(Net &net, float alpha, int off, int count, cudaStream_t s)
+{
+    int blocks = (count / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sgd_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<float4 *>(net.params + off), reinterpret_cast<const float4 *>(net.grads + off), alpha, count / 4);
+    LAUNCH_CHECK(net);
+    net.tc_dirty = true;
+    return 0;
 }
 
 int sgd_apply(Net &net, float alpha, cudaStream_t s)

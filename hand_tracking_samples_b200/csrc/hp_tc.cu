@@ -507,6 +507,14 @@ __global__ void __launch_bounds__(256) loss_from_y(const float *__restrict__ y, 
     }
 }
 
+void tc_set_reserved_sms(Net &net, int reserve)
+{
+    TcState *t = net.tc;
+    if (reserve < 0) reserve = 0;
+    if (reserve > t->total_sms / 2) reserve = t->total_sms / 2;
+    t->num_sms = t->total_sms - reserve;
+}
+
 int tc_init(Net &net)
 {
     if (int rc = bind_driver()) return rc;
@@ -514,7 +522,7 @@ int tc_init(Net &net)
     net.tc = t;
     cudaDeviceProp prop;
     HP_CUDA_TRY(cudaGetDeviceProperties(&prop, net.device));
-    t->num_sms = prop.multiProcessorCount;
+    t->num_sms = t->total_sms = prop.multiProcessorCount;
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1t, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2t, (size_t)FC2_OUT * FC2_IN * 2));
     if (int rc = make_map_bf16(&t->tm_w1t, t->w1t, FC1_OUT, FC1_IN, 256)) return rc;
@@ -554,18 +562,30 @@ void tc_destroy(Net &net)
     net.tc = nullptr;
 }
 
-int tc_refresh_weights(Net &net, cudaStream_t s)
+// rebuild the bf16 shadows of one gradient bucket's weights: 0 = fc2 (w2t, w2b), 1 = fc1 (w1t, w1b), 2 = conv images
+int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s)
 {
     TcState *t = net.tc;
-    transpose_to_bf16<true><<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, t->w1t, FC1_IN, FC1_OUT);
-    LAUNCH_CHECK(net);
-    transpose_to_bf16<false><<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, t->w2t, FC2_IN, FC2_OUT);
-    LAUNCH_CHECK(net);
-    convert_rows_bf16<true><<<FC1_IN, 256, 0, s>>>(net.params + OFF_F1W, t->w1b, FC1_OUT);
-    LAUNCH_CHECK(net);
-    convert_rows_bf16<false><<<FC2_IN, 256, 0, s>>>(net.params + OFF_F2W, t->w2b, FC2_OUT);
-    LAUNCH_CHECK(net);
-    if (int rc = tc_conv_refresh(net, s)) return rc;
+    if (bucket == 0) {
+        transpose_to_bf16<false><<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, t->w2t, FC2_IN, FC2_OUT);
+        LAUNCH_CHECK(net);
+        convert_rows_bf16<false><<<FC2_IN, 256, 0, s>>>(net.params + OFF_F2W, t->w2b, FC2_OUT);
+        LAUNCH_CHECK(net);
+    } else if (bucket == 1) {
+        transpose_to_bf16<true><<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, t->w1t, FC1_IN, FC1_OUT);
+        LAUNCH_CHECK(net);
+        convert_rows_bf16<true><<<FC1_IN, 256, 0, s>>>(net.params + OFF_F1W, t->w1b, FC1_OUT);
+        LAUNCH_CHECK(net);
+    } else {
+        if (int rc = tc_conv_refresh(net, s)) return rc;
+    }
+    return 0;
+}
+
+int tc_refresh_weights(Net &net, cudaStream_t s)
+{
+    for (int b = 0; b < 3; b++)
+        if (int rc = tc_refresh_bucket(net, b, s)) return rc;
     net.tc_dirty = false;
     return 0;
 }
@@ -717,6 +737,7 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     } else {
         if (int rc = launch_gemm<TC_EPI_DTANH, 256>(net, t->tm_dlog, t->tm_w2b, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
     }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_dx[0], s));
     // ---- fc1
     if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
     transpose_bf16<<<dim3(FC1_IN / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->p2, t->p2T, M, n_pad, FC1_IN, (int)TRAIN_CAP);
@@ -733,6 +754,7 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     } else {
         if (int rc = launch_gemm<TC_EPI_DTANH, 256>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     }
+    HP_CUDA_TRY(cudaEventRecord(net.ev_dx[1], s));
     // ---- conv stages backward (winners-only weight gradients; FFMA)
     if (int rc = tc_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));

@@ -23,10 +23,12 @@ struct TcState {
     __nv_bfloat16 *h1 = nullptr;   // [cap][2048] tanh(fc1)
     int64_t cap = 0;
     CUtensorMap tm_w1t, tm_w2t, tm_p2, tm_h1;
-    int num_sms = 148;
+    int num_sms = 148;     // CTAs of the persistent grids (SM count minus the SMs reserved for NCCL in data-parallel mode)
+    int total_sms = 148;
 };
 
 int tc_conv_init(Net &net);
+void tc_set_reserved_sms(Net &net, int reserve);
 int tc_conv_refresh(Net &net, cudaStream_t s);
 int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float *mse, bool accumulate, cudaStream_t s);
 int tc_conv_stage_train(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);

@@ -32,6 +32,23 @@ for prec, tol in ((hp.PRECISION_FP32, 2e-5), (hp.PRECISION_TENSOR, 2e-2)):
     if rank == 0:
         print("precision", prec, "update rel err DP(%d ranks) vs 1 GPU: %.3e (tol %g)  ranks identical: %s" % (world, g.item(), tol, identical), flush=True)
     assert g.item() <= tol and identical
+# opt-in bf16 gradient transport (tensor-precision steps only): same step within the tensor-path bound
+net.Init()
+net.dp_set_bf16_gradients(True)
+xd, td = torch.from_numpy(x[lo:hi].copy()).cuda(), torch.from_numpy(t[lo:hi].copy()).cuda()
+net.train_batch_device(xd.data_ptr(), td.data_ptr(), hi - lo, 0.001, None, precision=hp.PRECISION_TENSOR, stream=st)
+torch.cuda.synchronize()
+p_bf = net.get_params()
+ref = hp.PoseInitializerCNN("", device=local)
+ref.train_batch(x, t, 0.001, precision=hp.PRECISION_TENSOR)
+p_1 = ref.get_params()
+p0 = hp.PoseInitializerCNN("", device=local).get_params()
+rel = np.abs((p_bf - p0) - (p_1 - p0)).max() / np.abs(p_1 - p0).max()
+same = torch.from_numpy(p_bf).cuda(); ref0 = same.clone(); dist.broadcast(ref0, 0)
+if rank == 0:
+    print("bf16 wire: update rel err %.3e, ranks identical %s" % (rel, bool(torch.equal(same, ref0))), flush=True)
+assert rel <= 2e-2 and torch.equal(same, ref0)
+net.dp_set_bf16_gradients(False)
 # inference shards: contiguous slices, replicated weights, no collective
 net.Init()
 y_shard = net.eval_batch(x[lo:hi], precision=hp.PRECISION_TENSOR)
