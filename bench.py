@@ -253,7 +253,7 @@ def main():
         per_kernel.append({"kernel": names[i], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": ach / pk["bf16_tflops_sustained"], "launch_ms": launch_ms, "crops_per_launch": crops_per_launch,
                            "algorithmic_flop_per_crop": flops[i], "share_of_step": stage_ms[i] / max(sum(stage_ms), 1e-9),
-                           "traffic": traffic.get(names[i].split(" ")[0] + ("" if i == 0 else "<%d>" % (i - 1)))})
+                           "traffic": traffic.get(("tc_conv_kernel", "tc_gemm_kernel<0>", "tc_gemm_kernel<1>")[i])})
     dom = max(range(3), key=lambda i: stage_ms[i])
     roofline = dict(per_kernel[dom])
     roofline["peak_source"] = pk["source"] + ", sustained bf16 (kernels are timed inside a long step)"
