@@ -158,6 +158,21 @@ class CNN:
                                               self.precision if precision is None else precision))
         return y, dec
 
+    def render_labels(self, points, vals):
+        """GatherHandExpectedCNN label vector (handtrack.h:160-173): points[n][8][2], vals[n][16] -> [n][2304]."""
+        p = _f32(points, 16)
+        v = _f32(vals, 16)
+        t = np.empty((p.shape[0], N_OUT), np.float32)
+        capi.check(self.L.hp_render_labels(self.h, p.ctypes.data, v.ctypes.data, p.shape[0], t.ctypes.data))
+        return t
+
+    def train_batch_points(self, x, points, vals, alpha, precision=None):
+        x, p, v = _f32(x, N_IN), _f32(points, 16), _f32(vals, 16)
+        mse = np.empty(x.shape[0], np.float32)
+        capi.check(self.L.hp_train_batch_points(self.h, x.ctypes.data, p.ctypes.data, v.ctypes.data, x.shape[0], alpha, mse.ctypes.data,
+                                                self.precision if precision is None else precision))
+        return mse
+
     def train_batch(self, x, t, alpha, precision=None):
         x = _f32(x, N_IN)
         t = _f32(t, N_OUT)

@@ -606,6 +606,53 @@ int hp_decode_batch_device(hp_net *net, const float *y_dev, int64_t n, float *de
     return post_decode(net->n, y_dev, n, decoded_dev, (cudaStream_t)stream);
 }
 
+int hp_render_labels_device(hp_net *net, const float *points_dev, const float *vals_dev, int64_t n, float *t_dev, void *stream)
+{
+    if (!net || n < 0 || (n && (!points_dev || !vals_dev || !t_dev))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return post_render_labels(net->n, points_dev, vals_dev, n, t_dev, (cudaStream_t)stream);
+}
+
+// HOST buffers: x[n][4096] crops, points[n][8][2] + vals[n][16] label parameters (128 B per sample instead of 9,216)
+int hp_train_batch_points(hp_net *net, const float *x, const float *points, const float *vals, int64_t n, float alpha, float *mse_out, int precision)
+{
+    if (!net || n < 0 || (n && (!x || !points || !vals))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    if (int rc = ensure_staging(N, n, false, false)) return rc;
+    cudaStream_t s = N.stream;
+    float *dpts = N.dev_dec[0], *dvals = N.dev_dec[1];   // [n][48] scratch each: room for 16 floats per sample
+    HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[0], x, (size_t)n * N_IN * sizeof(float), cudaMemcpyHostToDevice, s));
+    HP_CUDA_TRY(cudaMemcpyAsync(dpts, points, (size_t)n * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
+    HP_CUDA_TRY(cudaMemcpyAsync(dvals, vals, (size_t)n * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (int rc = post_render_labels(N, dpts, dvals, n, N.dev_t, s)) return rc;
+    if (int rc = hp_train_batch_device(net, N.dev_in[0], N.dev_t, n, alpha, N.dev_mse, precision, s)) return rc;
+    if (mse_out) HP_CUDA_TRY(cudaMemcpyAsync(mse_out, N.dev_mse, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HP_CUDA_TRY(cudaStreamSynchronize(s));
+    return HP_OK;
+}
+
+int hp_render_labels(hp_net *net, const float *points, const float *vals, int64_t n, float *t)
+{
+    if (!net || n < 0 || (n && (!points || !vals || !t))) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    for (int64_t b = 0; b < n; b += STAGE_CHUNK) {
+        const int64_t m = std::min<int64_t>(STAGE_CHUNK, n - b);
+        if (int rc = ensure_staging(N, m, false, false)) return rc;
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_dec[0], points + b * 16, (size_t)m * 16 * sizeof(float), cudaMemcpyHostToDevice, N.stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_dec[1], vals + b * 16, (size_t)m * 16 * sizeof(float), cudaMemcpyHostToDevice, N.stream));
+        if (int rc = post_render_labels(N, N.dev_dec[0], N.dev_dec[1], m, N.dev_t, N.stream)) return rc;
+        HP_CUDA_TRY(cudaMemcpyAsync(t + b * N_OUT, N.dev_t, (size_t)m * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, N.stream));
+        HP_CUDA_TRY(cudaStreamSynchronize(N.stream));
+    }
+    return HP_OK;
+}
+
 int hp_decode_batch(hp_net *net, const float *y, int64_t n, float *decoded)
 {
     if (!net || n < 0 || (n && (!y || !decoded))) { set_error("bad argument"); return HP_ERR_INVALID; }

@@ -99,6 +99,7 @@ int fp32_init_attributes();
 // ---- pre/post steps (hp_post.cu) ----------------------------------------------
 int post_normalize_depth(Net &net, const uint16_t *d, int64_t n, float depth_scale, float dmin, float dmax, float *x, cudaStream_t s);
 int post_decode(Net &net, const float *y, int64_t n, float *out, cudaStream_t s);
+int post_render_labels(Net &net, const float *points, const float *vals, int64_t n, float *t, cudaStream_t s);
 // ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);
 int tc_refresh_weights(Net &net, cudaStream_t s);

@@ -2,6 +2,7 @@
 // (SURVEY.md 8f rows 3 and 1), as device kernels so that a caller can upload 16-bit depth crops (8 KB instead of
 // 16 KB per crop) and download decoded peaks (192 B instead of 9 KB per crop):
 //   normalize_depth_kernel  include/handtrack.h:700   depth -> [0,1] crop:  clamp(1 - (d*scale - dmin)/(dmax - dmin), 0, 1)
+//   render_labels_kernel    include/handtrack.h:160-173 (label vector of GatherHandExpectedCNN from 8 image points + 16 key values)
 //   decode_kernel           include/handtrack.h:218-241 (numeric core of CNNOutputAnalysis): per 2-D heatmap ImageFindMax,
 //                           PeakSubPixel, PeakVolume, peak value (include/misc_image.h:298-336); per 1-D heatmap
 //                           max_element + PeakSubPixel1D (misc_image.h:340-350, 389-399)
@@ -100,6 +101,68 @@ __global__ void __launch_bounds__(256) decode_kernel(const float *__restrict__ y
         }
         out[crop * 48 + 32 + tid] = __fdiv_rn((wsum == 0) ? (float)p : __fdiv_rn(v, wsum), 15.0f);
     }
+}
+
+// GatherHandExpectedCNN's label vector (include/handtrack.h:160-173): RenderHeatMap + NormalizeHeatMap
+// (misc_image.h:248-270) for the 8 feature points, Render1DHeatMaps (misc_image.h:279-295) for the 16 key values,
+// u8-quantised, then c/255 (misc_image.h:171).  One sample per CTA: warp w renders 2-D heatmap w, threads 0..15
+// render the 1-D rows.  Integer sums are exact; exp is correctly rounded so the u8 truncation matches the reference.
+__device__ __forceinline__ int to_gray(float x)
+{
+    float y = __fmul_rn(x, 255.0f);
+    y = (y < 0.0f) ? 0.0f : y;
+    y = (255.0f < y) ? 255.0f : y;
+    return (int)(unsigned char)y;
+}
+__global__ void __launch_bounds__(256) render_labels_kernel(const float *__restrict__ points, const float *__restrict__ vals, float *__restrict__ t)
+{
+    __shared__ float st[N_OUT];
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N_OUT; i += 256) st[i] = 0.f;
+    __syncthreads();
+    {
+        const float pkx = points[b * 16 + 2 * warp], pky = points[b * 16 + 2 * warp + 1];
+        const int hx = (int)pkx, hy = (int)pky;
+        const int px = hx - 2 + lane % 5, py = hy - 2 + lane / 5;
+        const bool in = lane < 25 && px >= 0 && px < 16 && py >= 0 && py < 16;
+        int c = 0;
+        if (in) {
+            const float dx = __fsub_rn(pkx, (float)px), dy = __fsub_rn(pky, (float)py);
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            c = to_gray(exp_cr(__fdiv_rn(-d2, 2.0f * 0.33f)));
+        }
+        int sum = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (in) {
+            const int q = sum ? (c * 255 / sum) : c;
+            st[warp * 256 + py * 16 + px] = __fdiv_rn((float)(q & 255), 255.0f);
+        }
+    }
+    if (tid < 16) {
+        const float v = __fmul_rn(vals[b * 16 + tid], 15.0f);
+        const int x0 = max(0, (int)v - 2), x1 = min(16, (int)v + 3);
+        int r[5], sum = 0;
+        for (int x = x0, k = 0; x < x1; x++, k++) {
+            const float d = __fsub_rn((float)x, v);
+            r[k] = to_gray(exp_cr(__fdiv_rn(-__fmul_rn(d, d), 2.0f * 0.5f)));
+            sum += r[k];
+        }
+        for (int x = x0, k = 0; x < x1; x++, k++) {
+            const int q = sum ? (r[k] * 255 / sum) : r[k];
+            st[2048 + tid * 16 + x] = __fdiv_rn((float)(q & 255), 255.0f);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N_OUT; i += 256) t[b * N_OUT + i] = st[i];
+}
+
+int post_render_labels(Net &net, const float *points, const float *vals, int64_t n, float *t, cudaStream_t s)
+{
+    render_labels_kernel<<<(unsigned)n, 256, 0, s>>>(points, vals, t);
+    LAUNCH_CHECK(net);
+    return 0;
 }
 
 int post_normalize_depth(Net &net, const uint16_t *d, int64_t n, float depth_scale, float dmin, float dmax, float *x, cudaStream_t s)

@@ -148,6 +148,14 @@ HP_API int hp_eval_depth_batch(hp_net *net, const uint16_t *depth, int64_t n, fl
 HP_API int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax,
                                      float *x_dev, void *stream);
 
+/* Replaces: the label vector of GatherHandExpectedCNN (include/handtrack.h:160-173): RenderHeatMaps +
+ * NormalizeHeatMap (include/misc_image.h:248-277) for the 8 image feature points, Render1DHeatMaps
+ * (misc_image.h:279-295) for the 16 key values, u8 quantisation and c/255 (misc_image.h:169-171).
+ * points[n][8][2] (heatmap pixel coordinates), vals[n][16] -> t[n][2304], bit-exact.  The pose-dependent inputs
+ * (ImageFeaturePoints, HandPoseToKeyAngleSet) stay with the host solver. */
+HP_API int hp_render_labels(hp_net *net, const float *points, const float *vals, int64_t n, float *t);
+HP_API int hp_render_labels_device(hp_net *net, const float *points_dev, const float *vals_dev, int64_t n, float *t_dev, void *stream);
+
 /* ---- training ------------------------------------------------------------ */
 
 /* Replaces: CNN::Train (cnn.h:558-580), batched.  One optimiser step on a
@@ -159,6 +167,10 @@ HP_API int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int
  * (sum e^2 / 2304, cnn.h:566-569).  HOST buffers. */
 HP_API int hp_train_batch(hp_net *net, const float *x, const float *t, int64_t n, float alpha,
                           float *mse_out, int precision);
+/* Same step with the labels given as their 32 generating numbers per sample (hp_render_labels on the device):
+ * 128 bytes of label upload per sample instead of 9,216.  HOST buffers. */
+HP_API int hp_train_batch_points(hp_net *net, const float *x, const float *points, const float *vals, int64_t n, float alpha,
+                                 float *mse_out, int precision);
 /* DEVICE buffers, caller's stream.  With data parallelism enabled (hp_dp_init)
  * the gradient sum is all-reduced over NCCL behind the backward pass before
  * the update. */

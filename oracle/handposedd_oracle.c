@@ -528,3 +528,55 @@ ORC_API void orc_normalize_depth(const unsigned short *d, long count, float dept
         out[i] = a;
     }
 }
+
+/* ---- label rendering ----------------------------------------------------
+ * GatherHandExpectedCNN's label vector (include/handtrack.h:160-173) from 8 image feature points and 16 key
+ * values: RenderHeatMap (misc_image.h:259-270: 5x5 window around (int)peak, exp(-d2/(2*0.33)), ToGrayScale =
+ * (u8)clamp(255x,0,255), misc_image.h:169), NormalizeHeatMap (integer c*255/sum, misc_image.h:248-257),
+ * Render1DHeatMaps (misc_image.h:279-295: exp(-d2/(2*0.5)), per-row integer normalisation), GrayScaleToFloat
+ * (c/255.0f, misc_image.h:171).  points[n][8][2], vals[n][16] -> t[n][2304]. */
+static unsigned char to_gray(float x)
+{
+    float y = x * 255.0f;
+    y = y < 0.0f ? 0.0f : y;
+    y = 255.0f < y ? 255.0f : y;
+    return (unsigned char)y;
+}
+ORC_API void orc_render_labels(const float *points, const float *vals, long n, float *t)
+{
+    for (long b = 0; b < n; b++) {
+        float *o = t + b * N_OUT;
+        for (int i = 0; i < 8; i++) {
+            unsigned char h[256];
+            memset(h, 0, sizeof h);
+            float pkx = points[b * 16 + 2 * i], pky = points[b * 16 + 2 * i + 1];
+            int hx = (int)pkx, hy = (int)pky;
+            for (int py = imax(0, hy - 2); py < imin(16, hy + 3); py++)
+                for (int px = imax(0, hx - 2); px < imin(16, hx + 3); px++) {
+                    float dx = pkx - (float)px, dy = pky - (float)py;
+                    float xx = dx * dx, yy = dy * dy;
+                    float d2 = xx + yy;
+                    h[py * 16 + px] = to_gray(expf(-d2 / (2.0f * 0.33f)));
+                }
+            int sum = 0;
+            for (int k = 0; k < 256; k++) sum += h[k];
+            if (sum)
+                for (int k = 0; k < 256; k++) h[k] = (unsigned char)(h[k] * 255 / sum);
+            for (int k = 0; k < 256; k++) o[i * 256 + k] = h[k] / 255.0f;
+        }
+        for (int y = 0; y < 16; y++) {
+            unsigned char r[16];
+            memset(r, 0, sizeof r);
+            float v = vals[b * 16 + y] * (float)(16 - 1);
+            int sum = 0;
+            for (int x = imax(0, (int)v - 2); x < imin(16, (int)v + 3); x++) {
+                float d = (float)x - v;
+                float d2 = d * d; /* pow(.,2.0f): exact square rounded once */
+                r[x] = to_gray(expf(-d2 / (2.0f * 0.5f)));
+                sum += r[x];
+            }
+            for (int x = imax(0, (int)v - 2); sum && x < imin(16, (int)v + 3); x++) r[x] = (unsigned char)(r[x] * 255 / sum);
+            for (int x = 0; x < 16; x++) o[2048 + y * 16 + x] = r[x] / 255.0f;
+        }
+    }
+}

@@ -72,6 +72,7 @@ class Oracle:
         L.orc_decode.argtypes = [_f32p, C.c_long, _f32p]
         L.orc_normalize_depth.argtypes = [np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS"), C.c_long, C.c_float, C.c_float,
                                           C.c_float, _f32p]
+        L.orc_render_labels.argtypes = [_f32p, _f32p, C.c_long, _f32p]
         self.L = L
         self.ws = C.c_void_p(L.orc_ws_create())
 
@@ -123,6 +124,14 @@ class Oracle:
         self.L.orc_decode(y, y.shape[0], out)
         return out
 
+    def render_labels(self, points, vals):
+        """GatherHandExpectedCNN label vector: points[n][8][2], vals[n][16] -> [n][2304]."""
+        p = _f32(points).reshape(-1, 16)
+        v = _f32(vals).reshape(-1, 16)
+        t = np.empty((p.shape[0], N_OUT), np.float32)
+        self.L.orc_render_labels(p, v, p.shape[0], t)
+        return t
+
     def normalize_depth(self, d, depth_scale=0.001, dmin=0.1, dmax=0.7):
         d = np.ascontiguousarray(d, np.uint16)
         out = np.empty(d.shape, np.float32)
@@ -150,7 +159,15 @@ class PostRef:
         L.ref_decode.argtypes = [_f32p, C.c_long, _f32p]
         L.ref_normalize_depth.argtypes = [np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS"), C.c_long, C.c_float, C.c_float,
                                           C.c_float, _f32p]
+        L.ref_render_labels.argtypes = [_f32p, _f32p, C.c_long, _f32p]
         self.L = L
+
+    def render_labels(self, points, vals):
+        p = _f32(points).reshape(-1, 16)
+        v = _f32(vals).reshape(-1, 16)
+        t = np.empty((p.shape[0], N_OUT), np.float32)
+        self.L.ref_render_labels(p, v, p.shape[0], t)
+        return t
 
     def decode(self, y):
         y = _f32(y).reshape(-1, N_OUT)

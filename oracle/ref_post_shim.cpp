@@ -6,6 +6,7 @@
 //                         built from the reference's own ImageFindMax / PeakSubPixel / PeakVolume / Peaks1D
 //                         (include/misc_image.h:298-336, 389-399) in the constructor's call order
 //   ref_normalize_depth   the depth -> [0,1] crop normalisation of include/handtrack.h:700
+//   ref_render_labels     the label vector of GatherHandExpectedCNN (include/handtrack.h:160-173) from feature points + key values
 // handtrack.h itself is not included (it does not compile headless under g++), so the two call
 // sequences are restated here; every arithmetic routine they call is the reference's.
 #include <cfloat>
@@ -48,6 +49,25 @@ __attribute__((visibility("default"))) void ref_normalize_depth(const unsigned s
     float2 drange = {dmin, dmax};
     for (long i = 0; i < count; i++)
         out[i] = (float)clamp(1.0f - (d[i] * depth_scale - drange.x) / (drange.y - drange.x), 0.0f, 1.0f);
+}
+
+// the label vector GatherHandExpectedCNN builds (include/handtrack.h:160-173) from 8 image
+// feature points and 16 key values: RenderHeatMaps (misc_image.h:259-277) + Render1DHeatMaps (misc_image.h:279-295),
+// u8-quantised, then GrayScaleToFloat (misc_image.h:171).  points[n][8][2], vals[n][16] -> t[n][2304].
+__attribute__((visibility("default"))) void ref_render_labels(const float *points, const float *vals, long n, float *t)
+{
+    DCamera hcam(int2(16, 16));
+    for (long b = 0; b < n; b++) {
+        std::vector<float2> fp;
+        for (int i = 0; i < 8; i++) fp.push_back(float2(points[b * 16 + 2 * i], points[b * 16 + 2 * i + 1]));
+        auto hmaps = RenderHeatMaps(fp, hcam);
+        std::vector<float> v(vals + b * 16, vals + b * 16 + 16);
+        auto vmap = Render1DHeatMaps(v, 16);
+        float *o = t + b * 2304;
+        for (int i = 0; i < 8; i++)
+            for (int k = 0; k < 256; k++) o[i * 256 + k] = GrayScaleToFloat(hmaps[i].raster[k]);
+        for (int k = 0; k < 256; k++) o[2048 + k] = GrayScaleToFloat(vmap.raster[k]);
+    }
 }
 
 }  // extern "C"

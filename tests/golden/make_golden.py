@@ -100,3 +100,24 @@ def main_post():
 
 if __name__ == "__main__" and "--post" in sys.argv:
     main_post()
+
+
+def main_labels():
+    """Fixture for the label-rendering row, from oracle/_ref/libpostref.so; labels are k/255 so they are
+    stored as the u8 numerators."""
+    from oracle.oracle import PostRef
+    r = PostRef()
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(-1, 17, (64, 16)).astype(np.float32)
+    vals = rng.uniform(-0.1, 1.1, (64, 16)).astype(np.float32)
+    pts[0] = 0
+    pts[1] = 15.999
+    vals[0] = 0
+    vals[1] = 1.0
+    pts[2] = 7.5
+    t = r.render_labels(pts, vals)
+    np.savez_compressed(os.path.join(OUT, "labels_render.npz"), points=pts, vals=vals, t_u8=np.round(t * 255).astype(np.uint8))
+
+
+if __name__ == "__main__" and "--labels" in sys.argv:
+    main_labels()

@@ -417,3 +417,19 @@ def test_depth_upload_path(net, orc, p0):
     assert np.array_equal(dec_only, dec)
     ytc, dectc = net.eval_depth_batch(d, precision=hp.PRECISION_TENSOR)
     assert maxnorm_err(ytc, y_ref) <= TC_TOL
+
+
+def test_label_rendering_is_bit_exact_and_trains(net, orc, p0):
+    g = golden("labels_render.npz")
+    want = g["t_u8"].astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(net.render_labels(g["points"], g["vals"]), want)
+    rng = np.random.default_rng(4)
+    p = rng.uniform(-1, 17, (3000, 16)).astype(np.float32)
+    v = rng.uniform(-0.1, 1.1, (3000, 16)).astype(np.float32)
+    assert np.array_equal(net.render_labels(p, v), orc.render_labels(p, v))
+    # training from label parameters == training from the rendered labels
+    x = synth.depthlike_crops(8, 77)
+    twin = hp.PoseInitializerCNN("")
+    m1 = net.train_batch_points(x, p[:8], v[:8], 0.001)
+    m2 = twin.train_batch(x, orc.render_labels(p[:8], v[:8]), 0.001)
+    assert np.array_equal(m1, m2) and np.array_equal(net.get_params(), twin.get_params())
