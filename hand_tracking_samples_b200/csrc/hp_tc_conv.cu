@@ -182,7 +182,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
         }
     } else if (warp == 2) {
         // ===================== conv2 MMA issuer: 2 M tiles x 16 taps per crop =====================
-        constexpr uint32_t idesc2 = ptx::make_idesc_bf16(128, 64);
+        constexpr uint32_t idesc2 = ptx::make_idesc_bf16(128, 64), idesc2_m64 = ptx::make_idesc_bf16(64, 64);
         ptx::mbar_wait(wgt_full, 0);
         const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_B2), 1024, 128);
         for (int it = 0; it < my_crops; it++) {
@@ -199,12 +199,16 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++) {
                     const uint32_t d = tmem_base + ACC2 + pb * 128 + mt * 64;
+                    // rows 0..127 as one M=128 tile; the valid outputs end at row 176, so the second tile is M=64
+                    // (rows 128..191): same tensor time, but half the A bytes through the shared-memory port,
+                    // which is what paces these N=64 MMAs
+                    const uint32_t idesc = mt == 0 ? idesc2 : idesc2_m64;
 #pragma unroll
                     for (int tap = 0; tap < 16; tap++) {
                         const int shift = (tap >> 2) * 15 + (tap & 3);   // rows: ky*15 + kx
                         const uint64_t ad = ad0 + (mt * 128 + shift), bd = bd0 + tap * (2048 >> 4);
-                        if (tap == 0) ptx::umma_f16_c<false>(d, ad, bd, idesc2);
-                        else ptx::umma_f16_c<true>(d, ad, bd, idesc2);
+                        if (tap == 0) ptx::umma_f16_c<false>(d, ad, bd, idesc);
+                        else ptx::umma_f16_c<true>(d, ad, bd, idesc);
                     }
                 }
                 ptx::umma_commit(&acc2_full[pb]);
@@ -303,9 +307,11 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             if (ew == 0) TRACE(3, it, 1);
 #pragma unroll 1
             for (int mt = 0; mt < 2; mt++) {
-                const int q = mt * 128 + t128;
+                // M=128 tile: accumulator row i sits in TMEM lane i.  M=64 tile: row r sits in lane (r % 16) + 32 * (r / 16),
+                // i.e. the lower half of each warp's lane quarter.
+                const int q = mt == 0 ? t128 : 128 + ew * 16 + lane;
                 const int yy = q / 15, xx = q - yy * 15;
-                const bool valid = (yy < 12) && (xx < 12);
+                const bool valid = (yy < 12) && (xx < 12) && (mt == 0 || lane < 16);
                 const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC2 + pb * 128 + mt * 64;
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
