@@ -23,7 +23,7 @@
 //
 // Warp roles (512 threads, 1 CTA/SM, crops strided over the grid):
 //   warp 0      loads the two 32 KB weight images with cp.async.bulk; allocates TMEM
-//   warp 1      conv1 MMA issuer (16 MMAs M128 N128 K16 per crop)
+//   warp 1      conv1 MMA issuer (12 MMAs M128 N128 K16 per crop: all-zero K steps of the embedded 5x5 kernels are skipped)
 //   warp 2      conv2 MMA issuer (32 MMAs M128 N64 K16 per crop); two issuers because at 32-64 tensor
 //               cycles per instruction a single issuing thread, not the tensor pipe, sets the pace
 //   warps 4-7   epilogue 1: TMEM -> running max over window positions -> +bias, tanh -> p1 planes (smem)
@@ -169,10 +169,18 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                 if (ptx::elect_one()) {
                     const uint32_t d = tmem_base + ACC1 + half * 128;
                     const uint64_t ad = ad0 + ((e * IMG_COPY) >> 4), bd = bd0 + ((half * 16384) >> 4);
-                    ptx::umma_f16_c<false>(d, ad, bd, idesc1);
-                    ptx::umma_f16_c<true>(d, ad + (256 >> 4), bd + 2, idesc1);
-                    ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
-                    ptx::umma_f16_c<true>(d, ad + (768 >> 4), bd + 6, idesc1);
+                    // K step ks covers patch rows 2ks, 2ks+1.  Half 0 holds the window positions with dy in {0,1}, whose
+                    // 5x5 kernels touch patch rows 0..5 only; half 1 (dy in {2,3}) touches rows 2..7: in each half one
+                    // of the four K steps multiplies by all-zero weights and is skipped (12 MMAs per crop instead of 16).
+                    if (half == 0) {
+                        ptx::umma_f16_c<false>(d, ad, bd, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (256 >> 4), bd + 2, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
+                    } else {
+                        ptx::umma_f16_c<false>(d, ad + (256 >> 4), bd + 2, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (768 >> 4), bd + 6, idesc1);
+                    }
                     ptx::umma_commit(&acc1_full[half]);
                     if (g == 3) ptx::umma_commit(&img_empty[ib]);
                 }
