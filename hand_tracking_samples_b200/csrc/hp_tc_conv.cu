@@ -21,14 +21,15 @@
 //   input channels = one MMA.  Rows whose (y,x) fall outside the 12x12 valid outputs compute
 //   garbage that is never read.
 //
-// Warp roles (512 threads, 1 CTA/SM, crops strided over the grid):
+// Warp roles (640 threads, 1 CTA/SM, crops strided over the grid):
 //   warp 0      loads the two 32 KB weight images with cp.async.bulk; allocates TMEM
 //   warp 1      conv1 MMA issuer (12 MMAs M128 N128 K16 per crop: all-zero K steps of the embedded 5x5 kernels are skipped)
 //   warp 2      conv2 MMA issuer (32 MMAs M128 N64 K16 per crop); two issuers because at 32-64 tensor
 //               cycles per instruction a single issuing thread, not the tensor pipe, sets the pace
-//   warps 4-7   epilogue 1: TMEM -> running max over window positions -> +bias, tanh -> p1 planes (smem)
-//   warps 8-11  epilogue 2: TMEM -> bf16 staging -> 2x2 max, +bias, tanh -> global features
-//   warps 12-15 loader: fp32 crop from global -> two bf16 image copies in smem (double-buffered)
+//   warps 4-11  epilogue 1 (two warpgroups, one per pooled-column parity): TMEM -> running max over window
+//               positions -> +bias, tanh -> p1 planes (smem)
+//   warps 12-15 epilogue 2: TMEM -> bf16 staging -> 2x2 max, +bias, tanh -> global features
+//   warps 16-19 loader: fp32 crop from global -> two bf16 image copies in smem (double-buffered)
 #include "hp_ptx.cuh"
 #include "hp_tc.cuh"
 
@@ -41,7 +42,7 @@ namespace hp {
     } while (0)
 
 namespace cv {
-constexpr int THREADS = 512;
+constexpr int THREADS = 640;
 constexpr int IMG_COPY = 9216;                 // one bf16 image copy (8 KB) + slack for the pad rows' reads
 constexpr int IMG_BUF = 2 * IMG_COPY;          // aligned copy + copy shifted by 4 pixels
 constexpr int P1_ROWS = 304;                   // 225 pixels + tap-shift overhang of the second M tile
@@ -101,13 +102,14 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
     uint64_t *wgt_full = bars + 0;
     uint64_t *img_full = bars + 1;    // [2]
     uint64_t *img_empty = bars + 3;   // [2]
-    uint64_t *acc1_full = bars + 5;   // [2]
+    uint64_t *acc1_full = bars + 17;  // [4]: one per group g = e*2 + half (each completes once per crop, so the two
+                                      //      epilogue-1 warpgroups can wait on plain per-crop parity)
     uint64_t *acc1_empty = bars + 7;  // [2]
     uint64_t *p1_full = bars + 9;     // [2]
     uint64_t *p1_empty = bars + 11;   // [2]
     uint64_t *acc2_full = bars + 13;  // [2]
     uint64_t *acc2_empty = bars + 15; // [2]
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 17);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 21);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int my_crops = (n > (int)blockIdx.x) ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -118,8 +120,9 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             ptx::mbar_init(&img_full[b], 128);
             ptx::mbar_init(&img_empty[b], 1);
             ptx::mbar_init(&acc1_full[b], 1);
+            ptx::mbar_init(&acc1_full[2 + b], 1);
             ptx::mbar_init(&acc1_empty[b], 4);
-            ptx::mbar_init(&p1_full[b], 4);
+            ptx::mbar_init(&p1_full[b], 8);
             ptx::mbar_init(&p1_empty[b], 1);
             ptx::mbar_init(&acc2_full[b], 1);
             ptx::mbar_init(&acc2_empty[b], 4);
@@ -181,7 +184,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                         ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
                         ptx::umma_f16_c<true>(d, ad + (768 >> 4), bd + 6, idesc1);
                     }
-                    ptx::umma_commit(&acc1_full[half]);
+                    ptx::umma_commit(&acc1_full[g]);
                     if (g == 3) ptx::umma_commit(&img_empty[ib]);
                 }
                 __syncwarp();
@@ -225,27 +228,31 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             __syncwarp();
             TRACE(1, it, 3);
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 12) {
         // ===================== epilogue 1: conv1 accumulators -> p1 planes =====================
-        const int ew = warp - 4;
+        // Two warpgroups: warps 4-7 drain the even-column tile (e = 0) of every crop, warps 8-11 the odd-column tile
+        // (e = 1).  One warpgroup alone needs ~2 k cycles per crop for its four accumulator reads and two tanh/pack
+        // passes, which -- not the tensor pipe -- set the pace of the whole kernel.
+        const int ew = warp & 3;
+        const int my_e = (warp - 4) >> 2;
         const int m = ew * 32 + lane;           // row of the M tile: (py, px')
         const int py = m >> 3, pxh = m & 7;
         for (int it = 0; it < my_crops; it++) {
             const int pb = it & 1;
             uint8_t *planes = smem + OFF_P1 + pb * P1_BUF;
-            if (ew == 0) TRACE(2, it, 0);
+            if (warp == 4) TRACE(2, it, 0);
             ptx::mbar_wait(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
-            if (ew == 0) TRACE(2, it, 1);
-#pragma unroll 1
-            for (int e = 0; e < 2; e++) {
+            if (warp == 4) TRACE(2, it, 1);
+            {
+                const int e = my_e;
                 float mx[16];
                 int am[16];
                 const uint32_t u = (uint32_t)(it * 2 + e);
 #pragma unroll 1
                 for (int half = 0; half < 2; half++) {
-                    ptx::mbar_wait(&acc1_full[half], u & 1);
+                    ptx::mbar_wait(&acc1_full[e * 2 + half], it & 1);
                     ptx::tc_fence_after();
-                    if (ew == 0) TRACE(2, it, 2 + 2 * (e * 2 + half));
+                    if (ew == 0) TRACE(2 + 3 * e, it, 2 + 2 * (e * 2 + half));
                     const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC1 + half * 128;
 #pragma unroll
                     for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
@@ -271,7 +278,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
-                    if (ew == 0) TRACE(2, it, 3 + 2 * (e * 2 + half));
+                    if (ew == 0) TRACE(2 + 3 * e, it, 3 + 2 * (e * 2 + half));
                 }
                 const int px = 2 * pxh + e;
                 if (py < 15 && px < 15) {
@@ -299,11 +306,11 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             ptx::fence_proxy_async();   // generic-proxy stores -> visible to the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
-            if (ew == 0) TRACE(2, it, 10);
+            if (ew == 0) TRACE(2 + 3 * my_e, it, 10);
         }
-    } else if (warp >= 8 && warp < 12) {
+    } else if (warp >= 12 && warp < 16) {
         // ===================== epilogue 2: conv2 accumulators -> pooled features =====================
-        const int ew = warp - 8;
+        const int ew = warp - 12;
         const int t128 = ew * 32 + lane;
         uint8_t *S = smem + OFF_S;
         for (int it = 0; it < my_crops; it++) {
@@ -398,9 +405,9 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             ptx::named_bar_sync(1, 128);
             if (ew == 0) TRACE(3, it, 3);
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 16) {
         // ===================== loader: fp32 crop -> two bf16 image copies =====================
-        const int t = threadIdx.x - 12 * 32;  // 0..127
+        const int t = threadIdx.x - 16 * 32;  // 0..127
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1;
             const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -413,9 +420,9 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                 v[k][1] = __ldg(src + 2 * j + 1);
                 v[k][2] = (j < 511) ? __ldg(src + 2 * j + 2) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (warp == 12) TRACE(4, it, 0);
+            if (warp == 16) TRACE(4, it, 0);
             ptx::mbar_wait(&img_empty[ib], ((it >> 1) & 1) ^ 1);
-            if (warp == 12) TRACE(4, it, 1);
+            if (warp == 16) TRACE(4, it, 1);
             uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -428,7 +435,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             }
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&img_full[ib]);
-            if (warp == 12) TRACE(4, it, 2);
+            if (warp == 16) TRACE(4, it, 2);
         }
     }
     ptx::tc_fence_before();
