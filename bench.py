@@ -149,7 +149,18 @@ def run_reference(args):
             "cpu_baseline": {"value": tot, "unit": "crops/s", "cores": used, "kind": kind,
                              "sample": "%d uniform[0,1) crops per step, %d threads, unmodified third_party/cnn.h" % (sample, used)},
             "e2e": {"value": tot, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# fd 1 is pointed at stderr for the whole run so that library chatter (NCCL's version banner, ...) cannot land next
+# to the ONE JSON line, which is written to the saved real stdout
+sys.stdout.flush()
+REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -331,8 +342,16 @@ def main():
             tx = torch.rand((TB, 4096), device=dev, generator=gen)
             tt = torch.from_numpy(synth.heatmap_labels(TB, 4321 + rank)).to(dev)
             mse = torch.empty(TB, device=dev)
+            exchange = "none (1 GPU)"
             if distributed:
-                dp.init_data_parallel(net)
+                try:
+                    dp.init_data_parallel(net, mode="peer")
+                    exchange = ("one kernel per gradient bucket (fc2 | fc1 | conv) over NVLink peer memory behind backward: reduce-scatter of the "
+                                "9,458,400 fp32 gradient sums + SGD + all-gather of the updated weights (csrc/hp_peer.cu); bf16-shadow refresh "
+                                "per bucket on a third stream")
+                except Exception as e:
+                    dp.init_data_parallel(net, mode="nccl")
+                    exchange = "NCCL all-reduce + local SGD (peer-memory path unavailable: %s)" % str(e)[:120]
             kt = max(min(K, 200), 20)
             line["train"] = {}
             for name, prec in (("tensor", hp.PRECISION_TENSOR), ("fp32", hp.PRECISION_FP32)):
@@ -341,15 +360,7 @@ def main():
                 line["train"][name] = {"value": world * TB * kt / (mst * 1e-3), "unit": "samples/s", "batch_per_gpu": TB, "steps": kt,
                                        "ms_per_step": mst / kt, "tflops": FLOP_PER_TRAIN_SAMPLE * TB * kt / (mst * 1e-3) / 1e12,
                                        "final_mse": float(mse.mean().item())}
-            line["train"]["allreduce"] = ("NCCL sum of 9,458,400 fp32 gradients per step in 3 buckets (fc2 | fc1 | conv) behind backward; "
-                                          "per-bucket SGD + bf16-shadow refresh on a third stream") if distributed else "none (1 GPU)"
-            if distributed:
-                net.dp_set_bf16_gradients(True)
-                mst = timed(lambda: net.train_batch_device(tx.data_ptr(), tt.data_ptr(), TB, 0.001 / (TB * world), mse.data_ptr(),
-                                                           precision=hp.PRECISION_TENSOR, stream=stream), kt, 3)
-                net.dp_set_bf16_gradients(False)
-                line["train"]["tensor_bf16_wire"] = {"value": world * TB * kt / (mst * 1e-3), "unit": "samples/s", "ms_per_step": mst / kt,
-                                                     "note": "opt-in: FC gradient buckets all-reduced as bf16 (18.9 MB instead of 37.8 MB)"}
+            line["train"]["exchange"] = exchange
             # compute-dominated point: 2048 samples per GPU per step
             TL = 2048
             txl = torch.rand((TL, 4096), device=dev, generator=gen)
@@ -361,6 +372,18 @@ def main():
             line["train"]["tensor_batch2048"] = {"value": world * TL * ktl / (mst * 1e-3), "unit": "samples/s", "batch_per_gpu": TL,
                                                  "ms_per_step": mst / ktl, "tflops": FLOP_PER_TRAIN_SAMPLE * TL * ktl / (mst * 1e-3) / 1e12}
             del txl, ttl, msel
+            if distributed:
+                # comparison arm: the same step with NCCL all-reduce + local SGD kernel (fp32 wire, then opt-in bf16 wire)
+                net_n = hp.PoseInitializerCNN("", device=local)
+                dp.init_data_parallel(net_n, mode="nccl")
+                for key, bf in (("tensor_nccl", False), ("tensor_nccl_bf16_wire", True)):
+                    net_n.dp_set_bf16_gradients(bf)
+                    mst = timed(lambda: net_n.train_batch_device(tx.data_ptr(), tt.data_ptr(), TB, 0.001 / (TB * world), mse.data_ptr(),
+                                                                 precision=hp.PRECISION_TENSOR, stream=stream), kt, 3)
+                    line["train"][key] = {"value": world * TB * kt / (mst * 1e-3), "unit": "samples/s", "ms_per_step": mst / kt,
+                                          "note": "baseline exchange: NCCL all-reduce (%s) + local SGD kernel" % ("bf16 wire" if bf else "fp32 wire")}
+                dp.shutdown_data_parallel(net_n)
+                del net_n
             line["train"]["workload"] = "BASELINE.json configs[2]: forward+backward+SGD, minibatch %d synthetic crops per GPU" % TB
         except Exception as e:  # the training arm must not take the headline down with it
             line["train"] = {"error": str(e)[:200]}
@@ -391,9 +414,9 @@ def main():
                                               % (max(64, 16 * threads), used, v1),
                                     "single_thread": v1}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
-        net.dp_shutdown()
+        dp.shutdown_data_parallel(net)
         dist.destroy_process_group()
 
 

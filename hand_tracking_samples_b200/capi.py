@@ -15,6 +15,7 @@ N_IN = 4096
 N_OUT = 2304
 N_PARAMS = 9458400
 CNNB_BYTES = 37833600
+PEER_HANDLE_BYTES = 192
 
 # every symbol include/handposedd.h declares
 SYMBOLS = [
@@ -23,7 +24,7 @@ SYMBOLS = [
     "hp_decode_batch", "hp_decode_batch_device", "hp_eval_decode_batch", "hp_eval_depth_batch", "hp_normalize_depth_device",
     "hp_render_labels", "hp_render_labels_device", "hp_train_batch_points",
     "hp_train_batch", "hp_train_batch_device", "hp_grad_batch_device", "hp_get_grads", "hp_device_ptrs",
-    "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_set_bf16_gradients", "hp_dp_shutdown", "hp_launch_count", "hp_debug_step_times", "hp_profile", "hp_profile_read",
+    "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_set_bf16_gradients", "hp_dp_peer_export", "hp_dp_peer_init", "hp_dp_peer_status", "hp_dp_shutdown", "hp_launch_count", "hp_debug_step_times", "hp_profile", "hp_profile_read",
     "hp_peek", "hp_last_error", "hp_version",
 ]
 
@@ -83,6 +84,9 @@ def lib():
     L.hp_dp_unique_id.argtypes = [vp]
     L.hp_dp_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.hp_dp_set_bf16_gradients.argtypes = [vp, C.c_int]
+    L.hp_dp_peer_export.argtypes = [vp, vp]
+    L.hp_dp_peer_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.hp_dp_peer_status.argtypes = [vp, C.POINTER(C.c_int)]
     L.hp_dp_shutdown.argtypes = [vp]
     L.hp_launch_count.argtypes = [vp]
     L.hp_launch_count.restype = i64

@@ -246,6 +246,21 @@ class CNN:
     def dp_set_bf16_gradients(self, enable=True):
         capi.check(self.L.hp_dp_set_bf16_gradients(self.h, int(enable)))
 
+    def dp_peer_export(self):
+        buf = (C.c_char * capi.PEER_HANDLE_BYTES)()
+        capi.check(self.L.hp_dp_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def dp_peer_init(self, all_handles, rank, world):
+        assert len(all_handles) == world * capi.PEER_HANDLE_BYTES
+        buf = (C.c_char * len(all_handles)).from_buffer_copy(all_handles)
+        capi.check(self.L.hp_dp_peer_init(self.h, buf, rank, world))
+
+    def dp_peer_status(self):
+        v = C.c_int(0)
+        capi.check(self.L.hp_dp_peer_status(self.h, C.byref(v)))
+        return v.value
+
     def dp_shutdown(self):
         capi.check(self.L.hp_dp_shutdown(self.h))
 

@@ -8,6 +8,7 @@
 #include "../../include/handposedd.h"
 #include "hp_common.cuh"
 #include "hp_tc.cuh"
+#include "hp_peer.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -200,8 +201,23 @@ static int finish_step(Net &net, float alpha, int precision, cudaStream_t s)
     // all-reduces back to back on the (high-priority) comm stream; SGD + shadow refresh of each bucket on a third
     // stream, so that bucket b+1's all-reduce does not queue behind bucket b's update
     cudaStream_t cs = net.comm_stream, us = net.d2h_stream;
+    const bool peer = net.world > 1 && net.peer && net.peer->ready;
     for (int b = 0; b < 3; b++) {
-        const bool bf16_wire = net.world > 1 && net.dp_bf16 && precision == HP_PRECISION_TENSOR && b < 2;
+        const bool bf16_wire = !peer && net.world > 1 && net.dp_bf16 && precision == HP_PRECISION_TENSOR && b < 2;
+        if (peer) {
+            // reduce-scatter + SGD + all-gather of the updated weights in one kernel over NVLink peer memory (hp_peer.cu).
+            // Peers store into this rank's FP32 master weights, so on the FP32 path (whose dX GEMMs read them) the
+            // kernel must also wait for the dX GEMM of the bucket; the tensor path only reads the bf16 shadows.
+            HP_CUDA_TRY(cudaStreamWaitEvent(cs, net.ev_bucket[b], 0));
+            if (b < 2 && precision != HP_PRECISION_TENSOR) HP_CUDA_TRY(cudaStreamWaitEvent(cs, net.ev_dx[b], 0));
+            if (int rc = peer_sgd_bucket(net, alpha, off[b], end[b] - off[b], cs)) return rc;
+            HP_CUDA_TRY(cudaEventRecord(net.ev_ar[b], cs));
+            HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_ar[b], 0));
+            if (b < 2) HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_dx[b], 0));
+            if (precision == HP_PRECISION_TENSOR)
+                if (int rc = tc_refresh_bucket(net, b, us)) return rc;
+            continue;
+        }
         if (net.world > 1) {
             HP_CUDA_TRY(cudaStreamWaitEvent(cs, net.ev_bucket[b], 0));
             if (bf16_wire) {
@@ -774,10 +790,46 @@ int hp_dp_set_bf16_gradients(hp_net *net, int enable)
     return HP_OK;
 }
 
+int hp_dp_peer_export(hp_net *net, void *handle_out)
+{
+    if (!net || !handle_out) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    return peer_export(N, handle_out);
+}
+
+int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world)
+{
+    if (!net || !all_handles || world < 2 || rank < 0 || rank >= world) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    if (int rc = peer_init(N, all_handles, rank, world)) return rc;
+    N.rank = rank;
+    N.world = world;
+    if (N.tc) {   // leave a few SMs out of the persistent grids so the exchange kernel's CTAs become resident at once
+        int reserve = 16;
+        if (const char *e = getenv("HP_DP_RESERVE_SMS")) reserve = atoi(e);
+        tc_set_reserved_sms(N, reserve);
+    }
+    return HP_OK;
+}
+
+int hp_dp_peer_status(hp_net *net, int *timed_out_on_rank_plus_1)
+{
+    if (!net || !timed_out_on_rank_plus_1) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    return peer_status(N, timed_out_on_rank_plus_1);
+}
+
 int hp_dp_shutdown(hp_net *net)
 {
     if (!net) return HP_OK;
     Net &N = net->n;
+    if (N.peer) {
+        cudaSetDevice(N.device);
+        peer_shutdown(N);
+    }
     if (N.nccl_comm) {
         cudaSetDevice(N.device);
         cudaDeviceSynchronize();

@@ -108,6 +108,7 @@ int tc_init(Net &net);
 void tc_destroy(Net &net);
 
 struct TcState;  // opaque: tensor maps + bf16 shadow weights (hp_tc.cu)
+struct PeerState;  // opaque: peers' weight/gradient stores mapped over NVLink (hp_peer.cu)
 
 struct Net {
     int refcount = 1;
@@ -134,6 +135,7 @@ struct Net {
                 ev_comm = nullptr, ev_dx[2] = {nullptr, nullptr}, ev_ar[3] = {nullptr, nullptr, nullptr}, ev_tail = nullptr, ev_start = nullptr;   // ev_dx[b]: the dX GEMM that reads bucket b's weights is done
     // data parallelism
     void *nccl_comm = nullptr;
+    PeerState *peer = nullptr;            // NVLink peer-memory exchange (hp_dp_peer_init); takes precedence over NCCL
     int rank = 0, world = 1;
     bool dp_bf16 = false;                 // FC gradient buckets travel as bf16 (tensor-precision steps only)
     __nv_bfloat16 *grads_bf = nullptr;    // wire buffer, .cnnb order

@@ -1,0 +1,216 @@
+// hp_peer.cu -- the data-parallel exchange step of a training step as ONE kernel over NVLink peer memory:
+// reduce-scatter of the gradient sums + the SGD update of CNN::Train (cnn.h:574-575, LFull::update cnn.h:438-445,
+// LConv::update cnn.h:269-279) + all-gather of the UPDATED WEIGHTS, replacing "NCCL all-reduce, then sgd_kernel".
+//
+// One process per GPU.  Every rank exports its weight store, its gradient store and a small flag array as CUDA IPC
+// handles (hp_dp_peer_export); hp_dp_peer_init maps the peers' stores into this process.  For a gradient bucket
+// [off, off+count) of the flat .cnnb-ordered stores, rank r owns the r-th contiguous slice and
+//     1. waits until every rank's gradient sums of the bucket are complete          (flag barrier, per CTA)
+//     2. reads its slice of all G gradient stores (G-1 of them through NVLink), adds them in rank order
+//     3. w <- fma(-alpha, sum, w) on its slice of its own master weights
+//     4. stores the new w into ALL G weight stores (G-1 of them through NVLink)
+//     5. signals / waits for "every rank's stores have landed"                       (flag barrier, per CTA)
+// so every rank ends with bit-identical weights (they are the owner's bits), the wire volume is that of a ring
+// all-reduce ((G-1)/G of the bucket each way), and the separate 113 MB read-modify-write pass of the SGD kernel is
+// gone.  NVSwitch gives every peer full bandwidth, so the slice loops just keep many 16-byte loads in flight.
+//
+// Barriers: flags[b][p] on rank r is written only by CTA b of rank p and holds the last epoch that CTA reached;
+// epochs increase monotonically (2 per launch), so no reset and no double buffering.  A CTA spins only on remote
+// CTAs of the same kernel launch, which become resident as soon as their own rank's stream reaches the launch: no
+// CTA waits on a CTA of its own grid, hence no co-residency requirement.  A spin longer than PEER_TIMEOUT_NS sets an
+// error word (read by hp_dp_peer_status) instead of hanging the GPU.
+#include "hp_common.cuh"
+#include "hp_peer.cuh"
+
+namespace hp {
+
+#define LAUNCH_CHECK(net)                                   \
+    do {                                                    \
+        (net).launches++;                                   \
+        HP_CUDA_TRY(cudaGetLastError());                    \
+    } while (0)
+
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;  // 4 s
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All CTAs with this blockIdx on all ranks meet here.  Everything the CTA's threads wrote before the call is
+// visible to the peers' CTAs after they return (bar.sync, then a system-scope release by the signalling threads).
+template <int WORLD>
+__device__ __forceinline__ void peer_barrier(const PeerPtrs &P, int rank, uint32_t epoch)
+{
+    __syncthreads();
+    if (threadIdx.x < WORLD) {
+        const int p = threadIdx.x;
+        __threadfence_system();
+        st_release_sys(P.flags[p] + blockIdx.x * PEER_MAX_WORLD + rank, epoch);
+        const uint32_t *mine = P.flags[rank] + blockIdx.x * PEER_MAX_WORLD + p;
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) {
+                atomicExch(P.error, 1u + (uint32_t)p);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 ld_peer(const float4 *p)
+{
+    // peer gradient sums change every step and are read exactly once: bypass L1, do not allocate
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <int WORLD, int U>
+__global__ void __launch_bounds__(PEER_THREADS) peer_sgd_kernel(PeerPtrs P, int rank, int off, int count4, float alpha, uint32_t epoch)
+{
+    peer_barrier<WORLD>(P, rank, epoch + 1);
+    const int lo = (int)((int64_t)count4 * rank / WORLD), hi = (int)((int64_t)count4 * (rank + 1) / WORLD);
+    const int stride = gridDim.x * PEER_THREADS;
+    for (int base = lo + blockIdx.x * PEER_THREADS + threadIdx.x; base < hi; base += stride * U) {
+        float4 g[U][WORLD];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * stride;
+#pragma unroll
+            for (int p = 0; p < WORLD; p++)
+                if (i < hi) g[u][p] = ld_peer(reinterpret_cast<const float4 *>(P.grads[p] + off) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * stride;
+            if (i < hi) {
+                float4 s = g[u][0];     // rank order 0..G-1 on every owner: deterministic
+#pragma unroll
+                for (int p = 1; p < WORLD; p++) { s.x += g[u][p].x; s.y += g[u][p].y; s.z += g[u][p].z; s.w += g[u][p].w; }
+                float4 w = reinterpret_cast<const float4 *>(P.params[rank] + off)[i];
+                w.x = fmaf(-alpha, s.x, w.x); w.y = fmaf(-alpha, s.y, w.y);
+                w.z = fmaf(-alpha, s.z, w.z); w.w = fmaf(-alpha, s.w, w.w);
+#pragma unroll
+                for (int p = 0; p < WORLD; p++) reinterpret_cast<float4 *>(P.params[p] + off)[i] = w;
+            }
+        }
+    }
+    peer_barrier<WORLD>(P, rank, epoch + 2);
+}
+
+int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
+{
+    PeerState *ps = net.peer;
+    if (!ps) { set_error("peer path not initialised"); return 2; }
+    const int count4 = count / 4;
+    // enough CTAs to keep ~1 MB in flight per peer link on the big buckets, a handful on the 67 KB conv bucket
+    int blocks = (count4 / ps->world + PEER_THREADS * 2 - 1) / (PEER_THREADS * 2);
+    if (blocks > ps->max_blocks) blocks = ps->max_blocks;
+    if (blocks < 1) blocks = 1;
+    const uint32_t epoch = ps->epoch;
+    ps->epoch += 2;
+    switch (ps->world) {
+    case 2: peer_sgd_kernel<2, 4><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+    case 3: peer_sgd_kernel<3, 2><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+    case 4: peer_sgd_kernel<4, 2><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+    case 5: peer_sgd_kernel<5, 2><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+    case 6: peer_sgd_kernel<6, 2><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+    case 7: peer_sgd_kernel<7, 2><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+    case 8: peer_sgd_kernel<8, 2><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+    default: set_error("peer path supports 2..8 ranks, got %d", ps->world); return 2;
+    }
+    LAUNCH_CHECK(net);
+    net.tc_dirty = true;
+    return 0;
+}
+
+int peer_export(Net &net, void *out)
+{
+    if (!net.peer) {
+        PeerState *ps = new PeerState;
+        HP_CUDA_TRY(cudaMalloc((void **)&ps->my_flags, PEER_FLAG_WORDS * sizeof(uint32_t)));
+        HP_CUDA_TRY(cudaMemset(ps->my_flags, 0, PEER_FLAG_WORDS * sizeof(uint32_t)));
+        HP_CUDA_TRY(cudaDeviceSynchronize());
+        net.peer = ps;
+    }
+    cudaIpcMemHandle_t h[3];
+    HP_CUDA_TRY(cudaIpcGetMemHandle(&h[0], net.params));
+    HP_CUDA_TRY(cudaIpcGetMemHandle(&h[1], net.grads));
+    HP_CUDA_TRY(cudaIpcGetMemHandle(&h[2], net.peer->my_flags));
+    static_assert(sizeof(h) == 192, "HP_PEER_HANDLE_BYTES");
+    memcpy(out, h, sizeof(h));
+    return 0;
+}
+
+int peer_init(Net &net, const void *handles, int rank, int world)
+{
+    PeerState *ps = net.peer;
+    if (!ps) { set_error("call hp_dp_peer_export first"); return 2; }
+    if (world < 2 || world > PEER_MAX_WORLD) { set_error("peer path supports 2..%d ranks, got %d", PEER_MAX_WORLD, world); return 2; }
+    ps->rank = rank;
+    ps->world = world;
+    for (int p = 0; p < world; p++) {
+        if (p == rank) {
+            ps->ptrs.params[p] = net.params;
+            ps->ptrs.grads[p] = net.grads;
+            ps->ptrs.flags[p] = ps->my_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, (const char *)handles + (size_t)p * sizeof(h), sizeof(h));
+        void *m[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3; k++) {
+            HP_CUDA_TRY(cudaIpcOpenMemHandle(&m[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+            ps->mapped[ps->n_mapped++] = m[k];
+        }
+        ps->ptrs.params[p] = (float *)m[0];
+        ps->ptrs.grads[p] = (float *)m[1];
+        ps->ptrs.flags[p] = (uint32_t *)m[2];
+    }
+    ps->ptrs.error = ps->my_flags + PEER_MAX_BLOCKS * PEER_MAX_WORLD;
+    ps->max_blocks = PEER_MAX_BLOCKS;
+    if (const char *e = getenv("HP_PEER_BLOCKS")) {
+        int b = atoi(e);
+        if (b >= 1 && b <= PEER_MAX_BLOCKS) ps->max_blocks = b;
+    }
+    ps->epoch = 0;
+    ps->ready = true;
+    return 0;
+}
+
+int peer_status(Net &net, int *err)
+{
+    *err = 0;
+    if (!net.peer || !net.peer->ready) return 0;
+    uint32_t v = 0;
+    HP_CUDA_TRY(cudaMemcpy(&v, net.peer->ptrs.error, sizeof(v), cudaMemcpyDeviceToHost));
+    *err = (int)v;
+    return 0;
+}
+
+void peer_shutdown(Net &net)
+{
+    PeerState *ps = net.peer;
+    if (!ps) return;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < ps->n_mapped; i++) cudaIpcCloseMemHandle(ps->mapped[i]);
+    if (ps->my_flags) cudaFree(ps->my_flags);
+    delete ps;
+    net.peer = nullptr;
+}
+
+}  // namespace hp

@@ -1,0 +1,39 @@
+// hp_peer.cuh -- state of the NVLink peer-memory data-parallel path (hp_peer.cu).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+
+namespace hp {
+
+constexpr int PEER_MAX_WORLD = 8;
+constexpr int PEER_MAX_BLOCKS = 128;
+constexpr int PEER_THREADS = 512;
+constexpr int PEER_FLAG_WORDS = PEER_MAX_BLOCKS * PEER_MAX_WORLD + 32;   // barrier flags + error word
+
+struct PeerPtrs {                        // passed to the kernel by value
+    float *params[PEER_MAX_WORLD];       // every rank's FP32 master weights (.cnnb order); [rank] is local
+    float *grads[PEER_MAX_WORLD];        // every rank's gradient sums
+    uint32_t *flags[PEER_MAX_WORLD];     // every rank's flag array [PEER_MAX_BLOCKS][PEER_MAX_WORLD]
+    uint32_t *error;                     // local error word (barrier timeout)
+};
+
+struct PeerState {
+    PeerPtrs ptrs;
+    uint32_t *my_flags = nullptr;
+    void *mapped[3 * PEER_MAX_WORLD];
+    int n_mapped = 0;
+    int rank = 0, world = 1;
+    int max_blocks = PEER_MAX_BLOCKS;
+    uint32_t epoch = 0;                  // identical on all ranks: every rank makes the same sequence of launches
+    bool ready = false;
+};
+
+struct Net;
+int peer_export(Net &net, void *out192);
+int peer_init(Net &net, const void *handles, int rank, int world);
+int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s);
+int peer_status(Net &net, int *err);
+void peer_shutdown(Net &net);
+
+}  // namespace hp

@@ -1,8 +1,10 @@
 """Host-side plumbing for the multi-GPU paths: one process per GPU.
 
 * inference: contiguous batch slices per rank, weights replicated, NO collective;
-* training: data parallel -- each rank computes the gradient sum of its slice, the
-  C ABI all-reduces it over NCCL (hp_dp_init) and every rank applies the same update.
+* training: data parallel -- each rank computes the gradient sum of its slice; the exchange
+  step is either ONE kernel per gradient bucket over NVLink peer memory (reduce-scatter + SGD +
+  all-gather of the updated weights, hp_dp_peer_init; the default) or an NCCL all-reduce
+  followed by the local SGD kernel (hp_dp_init; the comparison baseline).
 
 torch.distributed is only the rendezvous/side channel here (unique-id broadcast,
 barriers, max-over-ranks timing); the gradient all-reduce itself runs inside
@@ -14,6 +16,16 @@ import os
 def shard_range(n, rank, world):
     """Contiguous slice [lo, hi) of n units owned by `rank` ([g*N/G, (g+1)*N/G))."""
     return n * rank // world, n * (rank + 1) // world
+
+
+# gradient buckets of the flat .cnnb-ordered stores, in the order backward produces them: fc2 | fc1 | conv1+conv2
+BUCKETS = ((4737504, 9458400), (16864, 4737504), (0, 16864))
+
+
+def peer_slice(count4, rank, world):
+    """float4 range [lo, hi) of a bucket of count4 float4s that `rank` reduces, updates and publishes in the
+    peer-memory exchange kernel (csrc/hp_peer.cu, peer_sgd_kernel: same integer arithmetic)."""
+    return count4 * rank // world, count4 * (rank + 1) // world
 
 
 def env_rank_world():
@@ -30,11 +42,39 @@ def broadcast_bytes(data, src=0):
     return obj[0]
 
 
-def init_data_parallel(cnn):
-    """Join the net to an NCCL communicator spanning the default process group."""
+def all_gather_bytes(data):
+    """All-gather equal-length bytes objects over the default group, concatenated in rank order."""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, data)
+    return b"".join(out)
+
+
+def init_data_parallel(cnn, mode="peer"):
+    """Join the net to the data-parallel group spanning the default process group.
+    mode "peer": NVLink peer-memory exchange kernel (CUDA IPC handles all-gathered here);
+    mode "nccl": NCCL all-reduce + local SGD."""
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
-    uid = cnn.dp_unique_id() if rank == 0 else None
-    uid = broadcast_bytes(uid, 0)
-    cnn.dp_init(uid, rank, world)
+    if mode == "peer":
+        handles = all_gather_bytes(cnn.dp_peer_export())
+        cnn.dp_peer_init(handles, rank, world)
+        dist.barrier()
+    elif mode == "nccl":
+        uid = cnn.dp_unique_id() if rank == 0 else None
+        uid = broadcast_bytes(uid, 0)
+        cnn.dp_init(uid, rank, world)
+    else:
+        raise ValueError(mode)
     return rank, world
+
+
+def shutdown_data_parallel(cnn):
+    """Host-side barrier (no rank may unmap a store a peer's kernel still writes), then hp_dp_shutdown."""
+    import torch
+    import torch.distributed as dist
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier()
+    cnn.dp_shutdown()
+    dist.barrier()

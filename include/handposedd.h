@@ -200,6 +200,19 @@ HP_API int hp_dp_init(hp_net *net, const void *id128, int rank, int world);
 /* Opt-in: steps run with HP_PRECISION_TENSOR send the two FC gradient buckets (99.8 % of the bytes) over NVLink as
  * bf16 and sum them in bf16 (18.9 MB instead of 37.8 MB per step).  FP32 steps always travel as fp32. */
 HP_API int hp_dp_set_bf16_gradients(hp_net *net, int enable);
+/* NVLink peer-memory exchange (one process per GPU of one NVSwitch box, 2..8 ranks): the reduce-scatter of the
+ * gradient sums, the SGD update (cnn.h:438-445, 269-279) and the all-gather of the updated weights run as ONE kernel
+ * per gradient bucket that reads the peers' gradient stores and writes the peers' weight stores directly
+ * (csrc/hp_peer.cu); no NCCL on the data path.  Every rank calls hp_dp_peer_export (HP_PEER_HANDLE_BYTES of CUDA IPC
+ * handles), the host program all-gathers them in rank order by any channel, every rank calls hp_dp_peer_init with
+ * the world*HP_PEER_HANDLE_BYTES concatenation.  All ranks must then make the same sequence of training calls.
+ * Takes precedence over hp_dp_init's NCCL all-reduce when both are set up.  Call hp_dp_shutdown on all ranks
+ * (after a host-side barrier) before destroying the nets. */
+#define HP_PEER_HANDLE_BYTES 192
+HP_API int hp_dp_peer_export(hp_net *net, void *handle_out);
+HP_API int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world);
+/* 0, or 1 + the rank an exchange kernel gave up waiting for (4 s); the weights are then undefined. */
+HP_API int hp_dp_peer_status(hp_net *net, int *timed_out_on_rank_plus_1);
 HP_API int hp_dp_shutdown(hp_net *net);
 
 /* ---- diagnostics --------------------------------------------------------- */

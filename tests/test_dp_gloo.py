@@ -38,11 +38,28 @@ def _worker(rank, world, port, out):
         g = torch.from_numpy(g_local.copy())
         dist.all_reduce(g)  # what ncclAllReduce(sum) does inside libhandposedd
         uid = dp.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 0)
+        # the peer-memory exchange (csrc/hp_peer.cu) restated on the host: IPC handles all-gathered in rank order;
+        # rank r sums ITS slice of every rank's gradient store in rank order, updates its slice of the weights and
+        # publishes the new weights to everybody
+        handles = dp.all_gather_bytes(bytes([rank + 1]) * 192)
+        out["handles_ok_%d" % rank] = handles == b"".join(bytes([r + 1]) * 192 for r in range(world))
+        stores = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(stores, torch.from_numpy(g_local.copy()))     # "peer-mapped gradient stores"
+        w_new = torch.zeros(len(p0), dtype=torch.float64)
+        for b_lo, b_hi in dp.BUCKETS:
+            lo4, hi4 = dp.peer_slice((b_hi - b_lo) // 4, rank, world)
+            sl = slice(b_lo + 4 * lo4, b_lo + 4 * hi4)
+            acc = stores[0][sl].clone()
+            for r in range(1, world):
+                acc += stores[r][sl]
+            w_new[sl] = torch.from_numpy(p0.astype(np.float64))[sl] - 0.001 * acc
+        dist.all_reduce(w_new)    # slices are disjoint and cover every bucket: the sum is the all-gather
         if rank == 0:
             g_full, mse_full = o.train_minibatch(p0.copy(), x, t, 0.001, apply=False)
             out["max_abs_diff"] = float(np.abs(g.numpy() - g_full).max())
             out["max_abs"] = float(np.abs(g_full).max())
             out["uid_ok"] = uid == bytes(range(128))
+            out["peer_w_diff"] = float(np.abs(w_new.numpy() - (p0.astype(np.float64) - 0.001 * g_full)).max())
         else:
             out["uid_ok_1"] = uid == bytes(range(128))
     finally:
@@ -60,10 +77,23 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_peer_slices_partition_every_bucket():
+    from hand_tracking_samples_b200 import dp
+    assert sorted(dp.BUCKETS) == [(0, 16864), (16864, 4737504), (4737504, 9458400)]
+    for lo, hi in dp.BUCKETS:
+        assert (hi - lo) % 4 == 0 and lo % 4 == 0
+        for world in range(2, 9):
+            edges = [dp.peer_slice((hi - lo) // 4, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == (hi - lo) // 4
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+
+
 def test_data_parallel_gradient_identity_gloo():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out["uid_ok"] and out["uid_ok_1"]
+    assert out["handles_ok_0"] and out["handles_ok_1"]
+    assert out["peer_w_diff"] <= 1e-12
     # double accumulation on both sides: the shard sums add up to the full-batch sum to rounding
     assert out["max_abs_diff"] <= 1e-12 * max(1.0, out["max_abs"]) + 1e-15

@@ -6,7 +6,7 @@ rank, world, local = dp.env_rank_world()
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 net = hp.PoseInitializerCNN("", device=local)
-dp.init_data_parallel(net)
+dp.init_data_parallel(net, mode=os.environ.get('HP_DP_MODE', 'peer'))
 if os.environ.get('HP_BF16_WIRE'): net.dp_set_bf16_gradients(True)
 TB = 256
 tx = torch.rand((TB, 4096), device="cuda"); tt = torch.from_numpy(synth.heatmap_labels(TB, 1)).cuda(); mse = torch.empty(TB, device="cuda")
@@ -26,5 +26,5 @@ for prec, name in ((hp.PRECISION_TENSOR, "tensor"),):
     tms = np.zeros(9, np.float32); capi.check(net.L.hp_debug_step_times(net.h, tms.ctypes.data))
     if rank == 0:
         print("step timeline us: bucket0/1/2 ready %s  dx0/1 %s  allreduce0/1/2 done %s  tail %.0f" % ((tms[:3]*1e3).round(), (tms[3:5]*1e3).round(), (tms[5:8]*1e3).round(), tms[8]*1e3), flush=True)
-        print("world %d reserve %s %s: %.1f us/step  %.0f samples/s" % (world, os.environ.get("HP_DP_RESERVE_SMS", "default"), name, ms.item() * 1e3, world * TB / (ms.item() * 1e-3)), flush=True)
-net.dp_shutdown(); dist.destroy_process_group()
+        print("mode", os.environ.get("HP_DP_MODE", "peer"), "world %d reserve %s %s: %.1f us/step  %.0f samples/s" % (world, os.environ.get("HP_DP_RESERVE_SMS", "default"), name, ms.item() * 1e3, world * TB / (ms.item() * 1e-3)), flush=True)
+dp.shutdown_data_parallel(net); dist.destroy_process_group()
