@@ -929,6 +929,25 @@ int tc_conv_backward(Net &net, const float *x, int64_t n, const float *g2_hwc, b
     return 0;
 }
 
+int fp32_reduce_warp(Net &net, float *dst, const float *partial, int S, int len, bool accumulate, cudaStream_t s)
+{
+    reduce_partials_warp<<<(len + 7) / 8, 256, 0, s>>>(dst, partial, S, len, accumulate ? 1 : 0);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+int fp32_conv1_wgrad(Net &net, const float *x, int64_t n, bool accumulate, cudaStream_t s)
+{
+    Workspace &w = net.ws;
+    const int blocks = (int)n;   // one crop per CTA: two CTAs per SM hide each other's load latency
+    if ((size_t)blocks * 416 > w.partial_floats) { set_error("partial buffer too small for %d crops", blocks); return 1; }
+    conv1_wgrad<<<blocks, 256, 0, s>>>(x, w.g1, w.idx1, n, 1, w.partial);
+    LAUNCH_CHECK(net);
+    reduce_partials_warp<<<(416 + 7) / 8, 256, 0, s>>>(net.grads + OFF_C1W, w.partial, blocks, 416, accumulate ? 1 : 0);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
 int fp32_init_attributes()
 {
     HP_CUDA_TRY(cudaFuncSetAttribute(conv2_dx_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_DX_SMEM));

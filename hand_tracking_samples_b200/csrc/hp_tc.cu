@@ -19,6 +19,7 @@
 
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace hp {
 
@@ -48,6 +49,8 @@ struct EpiArgs {
     __nv_bfloat16 *out2;       // DTANH: bf16 [M][N]
     const __nv_bfloat16 *H;    // DTANH: layer output h, bf16 [M][N]: result = (1 - h*h) * acc  (TanH::df, cnn.h:32,467)
     int flags;                 // STORE_F32: TC_FLAG_ACCUMULATE (out += acc), TC_FLAG_ROWS_HWC_TO_CHW (row k' -> (k'&63)*36 + (k'>>6))
+    int ksplit;                // STORE_F32 only, 0/1 = off: K is cut into ksplit ranges of whole 64-blocks, every (range, tile) pair is a
+                               // work item and range r stores its partial product at out + r*M*N (long-K, small-output weight gradients)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -125,8 +128,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = N / BN;
     const int m_tiles = (M + BM - 1) / BM;
-    const int num_tiles = m_tiles * n_tiles;
-    const int num_kb = K / BK;
+    const int mn_tiles = m_tiles * n_tiles;
+    const int kb_total = (K + BK - 1) / BK;     // a ragged last block reads zeros (TMA out-of-bounds fill)
+    const int ksplit = (EPI == TC_EPI_STORE_F32 && ea.ksplit > 1) ? ea.ksplit : 1;
+    const int kb_per = (kb_total + ksplit - 1) / ksplit;
+    const int num_tiles = mn_tiles * ksplit;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -155,8 +161,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-                for (int kb = 0; kb < num_kb; kb++) {
+                const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+                const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+                const int kb0 = split * kb_per, kb1 = (kb0 + kb_per < kb_total) ? kb0 + kb_per : kb_total;
+                for (int kb = kb0; kb < kb1; kb++) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     uint8_t *sa = smem + stage * STAGE_BYTES;
@@ -178,7 +186,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
-            for (int kb = 0; kb < num_kb; kb++) {
+            const int split = tile / mn_tiles;
+            const int kb0 = split * kb_per, kb1 = (kb0 + kb_per < kb_total) ? kb0 + kb_per : kb_total;
+            for (int kb = kb0; kb < kb1; kb++) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
@@ -186,13 +196,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t adesc = ptx::make_desc_sw128(sa);
                     const uint64_t bdesc = ptx::make_desc_sw128(sa + A_BYTES);
                     // advance 16 bf16 = 32 B along K inside the 128B-swizzled row: +2 in the >>4 address field
-                    if (kb == 0) ptx::umma_f16_c<false>(tmem_d, adesc, bdesc, idesc);
+                    if (kb == kb0) ptx::umma_f16_c<false>(tmem_d, adesc, bdesc, idesc);
                     else ptx::umma_f16_c<true>(tmem_d, adesc, bdesc, idesc);
                     ptx::umma_f16_c<true>(tmem_d, adesc + 2, bdesc + 2, idesc);
                     ptx::umma_f16_c<true>(tmem_d, adesc + 4, bdesc + 4, idesc);
                     ptx::umma_f16_c<true>(tmem_d, adesc + 6, bdesc + 6, idesc);
                     ptx::umma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[as]);
+                    if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -203,7 +213,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+            const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(&tmem_full[as], aphase);
@@ -337,7 +348,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int q = 0; q < 8; q++) o[q] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-                    flush_grad(c & 1, o, reinterpret_cast<float *>(out), n_blk * BN + c * 32);
+                    flush_grad(c & 1, o, reinterpret_cast<float *>(out) + (size_t)split * M * N, n_blk * BN + c * 32);
                 }
             }
             if (EPI == TC_EPI_DTANH) {
@@ -461,6 +472,159 @@ __global__ void __launch_bounds__(256) transpose_bf16(const __nv_bfloat16 *__res
     }
 }
 
+// ---- conv2 backward on the tensor cores ---------------------------------------------------------------------
+// LConv::backward (cnn.h:258-268) and LConv::update (cnn.h:269-279) of the 4x4 16->64 layer as two GEMMs over the
+// dense error E[(n,pos)][co] (LMaxPool::backward, cnn.h:149-164, puts the fc1-side gradient at each 2x2 window's
+// winner and zero elsewhere):
+//     dL/dcol [(n,pos)][k]  = E  x W2[co][k]                        (M = 144 n, N = 256, K = 64)      -> col2im -> dL/dp1
+//     dW2^T   [k][co]       = col^T[k][(n,pos)] x E^T[co][(n,pos)]  (M = 256, N = 64, K = 144 n, split-K)
+// with k = (ky*4+kx)*16 + ci.  This kernel writes the three bf16 operands for one crop: E rows, and the
+// (n,pos)-contiguous transposes E^T and col^T (im2col of p1).  The CTA of the last crop also zeroes the columns up to
+// the next multiple of 64 that the last K block of the split-K GEMM reads.
+__global__ void __launch_bounds__(256) conv2_bwd_operands(const float *__restrict__ g2_hwc, const uint8_t *__restrict__ idx2, const float *__restrict__ p1,
+                                                          __nv_bfloat16 *__restrict__ E, __nv_bfloat16 *__restrict__ ET, __nv_bfloat16 *__restrict__ colT,
+                                                          float *__restrict__ db_partial, int n, int64_t ld)
+{
+    __shared__ __align__(16) float sg[P2_N];
+    __shared__ __align__(16) float sp1[P1_N];
+    __shared__ __align__(16) uint8_t si[P2_N];
+    __shared__ __align__(16) uint8_t s_off[C2_POS];   // pos -> y*15 + x      (its patch origin in a p1 plane)
+    __shared__ __align__(16) uint8_t s_pp[C2_POS];    // pos -> pooled window (y/2)*6 + x/2
+    __shared__ __align__(16) uint8_t s_sub[C2_POS];   // pos -> offset inside the window (y&1)*2 + (x&1)
+    const int64_t crop = blockIdx.x;
+    const int t = threadIdx.x;
+    for (int i = t; i < P2_N / 4; i += 256) {
+        reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(g2_hwc + crop * P2_N)[i];
+        if (i < P2_N / 16) reinterpret_cast<uint4 *>(si)[i] = reinterpret_cast<const uint4 *>(idx2 + crop * P2_N)[i];
+    }
+    for (int i = t; i < P1_N / 4; i += 256) reinterpret_cast<float4 *>(sp1)[i] = reinterpret_cast<const float4 *>(p1 + crop * P1_N)[i];
+    if (t < C2_POS) {
+        const int y = t / C2_W, xx = t - y * C2_W;
+        s_off[t] = (uint8_t)(y * P1_W + xx);
+        s_pp[t] = (uint8_t)((y >> 1) * P2_W + (xx >> 1));
+        s_sub[t] = (uint8_t)((y & 1) * 2 + (xx & 1));
+    }
+    __syncthreads();
+    auto pack8 = [](const float (&v)[8]) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+        return make_uint4(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b), *reinterpret_cast<uint32_t *>(&c), *reinterpret_cast<uint32_t *>(&d));
+    };
+    // conv2 dB partial of this crop (LConv::update, cnn.h:277): sum over the 36 windows
+    if (t < C2_CO) {
+        float a = 0.f;
+#pragma unroll 4
+        for (int pp = 0; pp < 36; pp++) a += sg[pp * 64 + t];
+        db_partial[crop * C2_CO + t] = a;
+    }
+    // E: row (crop*144 + pos) = 64 co = 8 x 16 B
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(E + crop * (int64_t)(C2_POS * C2_CO));
+        for (int i = t; i < C2_POS * 8; i += 256) {
+            const int pos = i >> 3, co0 = (i & 7) * 8;
+            const int pp = s_pp[pos], sub = s_sub[pos];
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = (si[(co0 + e) * 36 + pp] == sub) ? sg[pp * 64 + co0 + e] : 0.f;
+            dst[i] = pack8(v);
+        }
+    }
+    // E^T: row co, columns crop*144 + pos: 18 x 16 B per row
+    for (int i = t; i < C2_CO * 18; i += 256) {
+        const int co = i / 18, j = i - co * 18;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int pos = j * 8 + e, pp = s_pp[pos];
+            v[e] = (si[co * 36 + pp] == s_sub[pos]) ? sg[pp * 64 + co] : 0.f;
+        }
+        *reinterpret_cast<uint4 *>(ET + co * ld + crop * C2_POS + j * 8) = pack8(v);
+    }
+    // col^T: row k = tap*16 + ci, columns crop*144 + pos: 18 x 16 B per row
+    for (int i = t; i < C2_KDIM * 18; i += 256) {
+        const int k = i / 18, j = i - k * 18;
+        const int ci = k & 15, ky = k >> 6, kx = (k >> 4) & 3;
+        const float *src = sp1 + ci * (P1_W * P1_H) + ky * P1_W + kx;
+        const uint2 o8 = *reinterpret_cast<const uint2 *>(s_off + j * 8);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = src[((e < 4 ? o8.x : o8.y) >> (8 * (e & 3))) & 0xff];
+        *reinterpret_cast<uint4 *>(colT + k * ld + crop * C2_POS + j * 8) = pack8(v);
+    }
+    if (crop == n - 1) {
+        const int64_t R = (int64_t)n * C2_POS, R64 = (R + 63) / 64 * 64;
+        const int tail = (int)(R64 - R);
+        for (int i = t; i < (C2_CO + C2_KDIM) * tail; i += 256) {
+            const int row = i / tail, c = i - row * tail;
+            if (row < C2_CO) ET[row * ld + R + c] = __float2bfloat16_rn(0.f);
+            else colT[(row - C2_CO) * ld + R + c] = __float2bfloat16_rn(0.f);
+        }
+    }
+}
+
+// col2im of dL/dcol [(n,pos)][k = tap*16 + ci] (LConv::backward, cnn.h:258-268, as a gather) fused with TanH::df of the
+// conv1 stage: g1[n][ci][Y][X] = (1 - p1^2) * sum_{ky,kx} dcol[(Y-ky, X-kx)][(ky,kx,ci)].  One crop per CTA; a thread
+// owns 4 consecutive ci of one pixel, so every load is 16 B and a warp reads 8 x 64 contiguous bytes per tap.
+__global__ void __launch_bounds__(256) col2im_g1_vec(const float *__restrict__ colgrad, const float *__restrict__ p1, float *__restrict__ g1)
+{
+    __shared__ float so[P1_N];
+    const int64_t crop = blockIdx.x;
+    const float *cg = colgrad + crop * (int64_t)(C2_POS * C2_KDIM);
+    for (int i = threadIdx.x; i < P1_W * P1_H * 4; i += 256) {
+        const int r = i >> 2, c4 = (i & 3) * 4;
+        const int Y = r / P1_W, X = r - Y * P1_W;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 4; ky++) {
+            const int y = Y - ky;
+            if (y < 0 || y >= C2_H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; kx++) {
+                const int xx = X - kx;
+                if (xx < 0 || xx >= C2_W) continue;
+                const float4 v = *reinterpret_cast<const float4 *>(cg + (y * C2_W + xx) * C2_KDIM + (ky * 4 + kx) * 16 + c4);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+        }
+        so[(c4 + 0) * 225 + r] = a.x;
+        so[(c4 + 1) * 225 + r] = a.y;
+        so[(c4 + 2) * 225 + r] = a.z;
+        so[(c4 + 3) * 225 + r] = a.w;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P1_N / 4; i += 256) {
+        const float4 pv = reinterpret_cast<const float4 *>(p1 + crop * P1_N)[i];
+        const float4 d = reinterpret_cast<const float4 *>(so)[i];
+        reinterpret_cast<float4 *>(g1 + crop * P1_N)[i] =
+            make_float4((1.0f - pv.x * pv.x) * d.x, (1.0f - pv.y * pv.y) * d.y, (1.0f - pv.z * pv.z) * d.z, (1.0f - pv.w * pv.w) * d.w);
+    }
+}
+
+// fp32 W2[co][ci*16+tap] (.cnnb OIHW) -> bf16 w2kt[k = tap*16+ci][co]: the K-major B operand of the dL/dcol GEMM
+__global__ void __launch_bounds__(256) build_w2kt(const float *__restrict__ params, __nv_bfloat16 *__restrict__ w2kt)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;   // = k*64 + co
+    const int co = i & 63, k = i >> 6, ci = k & 15, tap = k >> 4;
+    w2kt[i] = __float2bfloat16_rn(params[OFF_C2W + co * C2_KDIM + ci * 16 + tap]);
+}
+
+// dW2[co][ci*16+tap] (+)= sum_s partial[s][k = tap*16+ci][co]   (s ascending: deterministic)
+__global__ void __launch_bounds__(256) reduce_c2w_t(float *__restrict__ dst, const float *__restrict__ partial, int S, int accumulate)
+{
+    __shared__ float red[4][64];
+    const int k = blockIdx.x, co = threadIdx.x & 63, q = threadIdx.x >> 6;
+    float a = 0.f;
+    for (int s = q; s < S; s += 4) a += partial[(size_t)s * (C2_KDIM * C2_CO) + k * C2_CO + co];
+    red[q][co] = a;
+    __syncthreads();
+    if (q == 0) {
+        const int ci = k & 15, tap = k >> 4;
+        float *d = dst + co * C2_KDIM + ci * 16 + tap;
+        const float v = (red[0][co] + red[1][co]) + (red[2][co] + red[3][co]);
+        *d = accumulate ? *d + v : v;
+    }
+}
+
 // Train's loss (cnn.h:566-569) and LSoftMaxChunked::backward (cnn.h:512-526) from the softmax OUTPUT y:
 // e = y - t, mse = sum e^2 / 2304, per span dp = sum e*y, dlogit = y * (e - dp).  fp32 and bf16 copies.
 __global__ void __launch_bounds__(256) loss_from_y(const float *__restrict__ y, const float *__restrict__ t, float *__restrict__ dlog,
@@ -542,6 +706,8 @@ int tc_init(Net &net)
     if (int rc = make_map_bf16(&t->tm_w2b, t->w2b, FC2_IN, FC2_OUT, 256)) return rc;
     if (int rc = make_map_bf16(&t->tm_w1b64, t->w1b, FC1_IN, FC1_OUT, 64)) return rc;
     if (int rc = make_map_bf16(&t->tm_w2b64, t->w2b, FC2_IN, FC2_OUT, 64)) return rc;
+    HP_CUDA_TRY(cudaMalloc((void **)&t->w2kt, (size_t)C2_KDIM * C2_CO * 2));
+    if (int rc = make_map_bf16(&t->tm_w2kt, t->w2kt, C2_KDIM, C2_CO, 256)) return rc;
     return tc_conv_init(net);
 }
 
@@ -551,7 +717,7 @@ void tc_destroy(Net &net)
     if (!t) return;
     if (t->w1t) cudaFree(t->w1t);
     if (t->w2t) cudaFree(t->w2t);
-    void *tb[] = {t->w1b, t->w2b, t->dlog_bf, t->da1_bf, t->h1T, t->dlogT, t->p2T, t->da1T};
+    void *tb[] = {t->w1b, t->w2b, t->dlog_bf, t->da1_bf, t->h1T, t->dlogT, t->p2T, t->da1T, t->e2, t->e2T, t->colT, t->w2kt, t->db2_partial};
     for (void *q : tb)
         if (q) cudaFree(q);
     if (t->b1_img) cudaFree(t->b1_img);
@@ -578,6 +744,8 @@ int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s)
         LAUNCH_CHECK(net);
     } else {
         if (int rc = tc_conv_refresh(net, s)) return rc;
+        build_w2kt<<<C2_KDIM * C2_CO / 256, 256, 0, s>>>(net.params, t->w2kt);
+        LAUNCH_CHECK(net);
     }
     return 0;
 }
@@ -647,7 +815,7 @@ template <int EPI, int BN>
 static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB, const EpiArgs &ea, int M, int N, int K, cudaStream_t s)
 {
     TcState *t = net.tc;
-    const int tiles = ((M + BM - 1) / BM) * (N / BN);
+    const int tiles = ((M + BM - 1) / BM) * (N / BN) * (ea.ksplit > 1 ? ea.ksplit : 1);
     const int grid = tiles < t->num_sms ? tiles : t->num_sms;
     tc_gemm_kernel<EPI, BN><<<grid, GEMM_THREADS, gemm_smem(BN), s>>>(tmA, tmB, ea, M, N, K);
     LAUNCH_CHECK(net);
@@ -688,7 +856,52 @@ static int tc_train_ensure(Net &net)
     if (int rc = make_map_bf16(&t->tm_p2T, t->p2T, FC1_IN, cap, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_dlogT, t->dlogT, N_OUT, cap, 256)) return rc;
     if (int rc = make_map_bf16(&t->tm_da1T, t->da1T, FC1_OUT, cap, 256)) return rc;
+    // conv2 backward operands (conv2_bwd_operands)
+    const int64_t ld = cap * C2_POS;
+    HP_CUDA_TRY(cudaMalloc((void **)&t->e2, (size_t)ld * C2_CO * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->e2T, (size_t)C2_CO * ld * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->colT, (size_t)C2_KDIM * ld * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->db2_partial, (size_t)cap * C2_CO * 4));
+    HP_CUDA_TRY(cudaMemset(t->e2, 0, (size_t)ld * C2_CO * 2));
+    HP_CUDA_TRY(cudaMemset(t->e2T, 0, (size_t)C2_CO * ld * 2));
+    HP_CUDA_TRY(cudaMemset(t->colT, 0, (size_t)C2_KDIM * ld * 2));
+    if (int rc = make_map_bf16(&t->tm_e2, t->e2, ld, C2_CO, BM)) return rc;
+    if (int rc = make_map_bf16(&t->tm_e2T, t->e2T, C2_CO, ld, 64)) return rc;
+    if (int rc = make_map_bf16(&t->tm_colT, t->colT, C2_KDIM, ld, BM)) return rc;
     return 0;
+}
+
+// hp_fp32.cu kernels reused by the tensor-core conv backward
+int fp32_reduce_warp(Net &net, float *dst, const float *partial, int S, int len, bool accumulate, cudaStream_t s);
+int fp32_conv1_wgrad(Net &net, const float *x, int64_t n, bool accumulate, cudaStream_t s);
+
+// conv stages backward of the tensor path: conv2 dL/dp1 and dW2 as tcgen05 GEMMs (see conv2_bwd_operands), conv2 dB as a
+// column sum, conv1 dW/dB winners-only on FFMA (its contraction has 25 taps x 1 input channel: no GEMM shape worth the name).
+static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    Workspace &w = net.ws;
+    float *G = net.grads;
+    const int64_t ld = TRAIN_CAP * C2_POS;
+    const int R = (int)(n * C2_POS);
+    conv2_bwd_operands<<<(unsigned)n, 256, 0, s>>>(g2_hwc, w.idx2, w.p1, t->e2, t->e2T, t->colT, t->db2_partial, (int)n, ld);
+    LAUNCH_CHECK(net);
+    if (int rc = fp32_reduce_warp(net, G + OFF_C2B, t->db2_partial, (int)n, C2_CO, accumulate, s)) return rc;
+    // dW2^T partials: split-K over about half the SMs' worth of ranges x 2 M tiles
+    const int kb_total = (R + BK - 1) / BK;
+    int target = t->num_sms / 2;
+    if (target < 1) target = 1;
+    const int kb_per = (kb_total + target - 1) / target;
+    const int S = (kb_total + kb_per - 1) / kb_per;
+    if ((size_t)S * C2_KDIM * C2_CO > w.partial_floats) { set_error("partial buffer too small for %d K ranges", S); return 1; }
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 64>(net, t->tm_colT, t->tm_e2T, EpiArgs{nullptr, w.partial, nullptr, nullptr, 0, S}, C2_KDIM, C2_CO, R, s)) return rc;
+    reduce_c2w_t<<<C2_KDIM, 256, 0, s>>>(G + OFF_C2W, w.partial, S, accumulate ? 1 : 0);
+    LAUNCH_CHECK(net);
+    // dL/dcol, then col2im fused with the conv1-stage tanh'
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_e2, t->tm_w2kt, EpiArgs{nullptr, w.colgrad, nullptr, nullptr, 0, 0}, R, C2_KDIM, C2_CO, s)) return rc;
+    col2im_g1_vec<<<(unsigned)n, 256, 0, s>>>(w.colgrad, w.p1, w.g1);
+    LAUNCH_CHECK(net);
+    return fp32_conv1_wgrad(net, x, n, accumulate, s);
 }
 
 // Forward + backward of one pass (n <= TRAIN_CAP) with every FC contraction on tcgen05:
@@ -756,7 +969,12 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[1], s));
     // ---- conv stages backward (winners-only weight gradients; FFMA)
-    if (int rc = tc_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
+    static const bool ffma_conv_bwd = getenv("HP_CONV_BWD_FFMA") != nullptr;   // A/B switch for the previous FFMA kernels
+    if (ffma_conv_bwd) {
+        if (int rc = tc_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
+    } else {
+        if (int rc = tc_conv_backward_gemm(net, x, n, w.g2, accumulate, s)) return rc;
+    }
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));
     return 0;
 }

@@ -16,6 +16,11 @@ struct TcState {
     // training activations (TRAIN_CAP samples per pass)
     __nv_bfloat16 *dlog_bf = nullptr, *da1_bf = nullptr;            // [cap][2304], [cap][2048]
     __nv_bfloat16 *h1T = nullptr, *dlogT = nullptr, *p2T = nullptr, *da1T = nullptr;  // [features][cap]: batch-contiguous (K-major for dW)
+    // conv2 backward as GEMMs: dense error rows / its transpose / transposed im2col of p1, (n,pos) padded to TRAIN_CAP*144
+    __nv_bfloat16 *e2 = nullptr, *e2T = nullptr, *colT = nullptr;   // [cap*144][64], [64][cap*144], [256][cap*144]
+    float *db2_partial = nullptr;                                    // [cap][64] per-crop conv2 bias-gradient sums
+    __nv_bfloat16 *w2kt = nullptr;                                   // [256 k = tap*16+ci][64 co] = conv2.W, K-major over co
+    CUtensorMap tm_e2, tm_e2T, tm_colT, tm_w2kt;
     CUtensorMap tm_w1t64, tm_w2t64, tm_w1b64, tm_w2b64;   // the same weights with 64-row boxes (small-batch GEMMs)
     CUtensorMap tm_w1b, tm_w2b, tm_dlog, tm_da1, tm_h1T, tm_p2T, tm_dlogT, tm_da1T;
     // activations
