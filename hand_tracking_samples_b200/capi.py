@@ -15,7 +15,7 @@ N_IN = 4096
 N_OUT = 2304
 N_PARAMS = 9458400
 CNNB_BYTES = 37833600
-PEER_HANDLE_BYTES = 192
+PEER_HANDLE_BYTES = 256
 
 # every symbol include/handposedd.h declares
 SYMBOLS = [

@@ -803,14 +803,13 @@ int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world)
     if (!net || !all_handles || world < 2 || rank < 0 || rank >= world) { set_error("bad argument"); return HP_ERR_INVALID; }
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
-    if (int rc = peer_init(N, all_handles, rank, world)) return rc;
+    // the exchange kernels run one 1024-thread CTA on each SM that the persistent tensor-core grids leave free
+    int reserve = 16;
+    if (const char *e = getenv("HP_DP_RESERVE_SMS")) reserve = atoi(e);
+    if (int rc = peer_init(N, all_handles, rank, world, reserve)) return rc;
     N.rank = rank;
     N.world = world;
-    if (N.tc) {   // leave a few SMs out of the persistent grids so the exchange kernel's CTAs become resident at once
-        int reserve = 16;
-        if (const char *e = getenv("HP_DP_RESERVE_SMS")) reserve = atoi(e);
-        tc_set_reserved_sms(N, reserve);
-    }
+    if (N.tc) tc_set_reserved_sms(N, reserve);
     return HP_OK;
 }
 
@@ -820,6 +819,19 @@ int hp_dp_peer_status(hp_net *net, int *timed_out_on_rank_plus_1)
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
     return peer_status(N, timed_out_on_rank_plus_1);
+}
+
+/* diagnostics (tools/dbg/peer_bw.py): one exchange kernel of gradient bucket b (0 fc2, 1 fc1, 2 conv) on `stream`;
+ * max_blocks > 0 overrides the CTA cap first.  All ranks must call it in the same order. */
+HP_API int hp_debug_peer_exchange(hp_net *net, int bucket, float alpha, int max_blocks, void *stream)
+{
+    if (!net || bucket < 0 || bucket > 2 || !net->n.peer) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    const int off[3] = {OFF_F2W, OFF_F1W, 0};
+    const int end[3] = {N_PARAMS, OFF_F2W, OFF_F1W};
+    if (max_blocks > 0) N.peer->max_blocks = max_blocks < PEER_MAX_BLOCKS ? max_blocks : PEER_MAX_BLOCKS;
+    return peer_sgd_bucket(N, alpha, off[bucket], end[bucket] - off[bucket], (cudaStream_t)stream);
 }
 
 int hp_dp_shutdown(hp_net *net)

@@ -8,30 +8,35 @@ namespace hp {
 
 constexpr int PEER_MAX_WORLD = 8;
 constexpr int PEER_MAX_BLOCKS = 128;
-constexpr int PEER_THREADS = 512;
+constexpr int PEER_THREADS = 1024;
+constexpr int PEER_SMALL_FLOATS = 16896;                                // buckets up to this size (the conv bucket: 16,864) go through the inbox
+constexpr int PEER_INBOX_FLOATS = 2 * PEER_MAX_WORLD * PEER_SMALL_FLOATS;   // [parity][source rank][PEER_SMALL_FLOATS]
 constexpr int PEER_FLAG_WORDS = PEER_MAX_BLOCKS * PEER_MAX_WORLD + 32;   // barrier flags + error word
 
 struct PeerPtrs {                        // passed to the kernel by value
     float *params[PEER_MAX_WORLD];       // every rank's FP32 master weights (.cnnb order); [rank] is local
     float *grads[PEER_MAX_WORLD];        // every rank's gradient sums
     uint32_t *flags[PEER_MAX_WORLD];     // every rank's flag array [PEER_MAX_BLOCKS][PEER_MAX_WORLD]
+    float *inbox[PEER_MAX_WORLD];        // every rank's small-bucket inbox
     uint32_t *error;                     // local error word (barrier timeout)
 };
 
 struct PeerState {
     PeerPtrs ptrs;
     uint32_t *my_flags = nullptr;
-    void *mapped[3 * PEER_MAX_WORLD];
+    float *my_inbox = nullptr;
+    void *mapped[4 * PEER_MAX_WORLD];
     int n_mapped = 0;
     int rank = 0, world = 1;
     int max_blocks = PEER_MAX_BLOCKS;
+    uint32_t small_steps = 0;            // launches of the small-bucket kernel so far (inbox parity)
     uint32_t epoch = 0;                  // identical on all ranks: every rank makes the same sequence of launches
     bool ready = false;
 };
 
 struct Net;
 int peer_export(Net &net, void *out192);
-int peer_init(Net &net, const void *handles, int rank, int world);
+int peer_init(Net &net, const void *handles, int rank, int world, int reserved_sms);
 int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s);
 int peer_status(Net &net, int *err);
 void peer_shutdown(Net &net);

@@ -208,7 +208,7 @@ HP_API int hp_dp_set_bf16_gradients(hp_net *net, int enable);
  * the world*HP_PEER_HANDLE_BYTES concatenation.  All ranks must then make the same sequence of training calls.
  * Takes precedence over hp_dp_init's NCCL all-reduce when both are set up.  Call hp_dp_shutdown on all ranks
  * (after a host-side barrier) before destroying the nets. */
-#define HP_PEER_HANDLE_BYTES 192
+#define HP_PEER_HANDLE_BYTES 256
 HP_API int hp_dp_peer_export(hp_net *net, void *handle_out);
 HP_API int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world);
 /* 0, or 1 + the rank an exchange kernel gave up waiting for (4 s); the weights are then undefined. */

@@ -41,8 +41,8 @@ def _worker(rank, world, port, out):
         # the peer-memory exchange (csrc/hp_peer.cu) restated on the host: IPC handles all-gathered in rank order;
         # rank r sums ITS slice of every rank's gradient store in rank order, updates its slice of the weights and
         # publishes the new weights to everybody
-        handles = dp.all_gather_bytes(bytes([rank + 1]) * 192)
-        out["handles_ok_%d" % rank] = handles == b"".join(bytes([r + 1]) * 192 for r in range(world))
+        handles = dp.all_gather_bytes(bytes([rank + 1]) * 256)
+        out["handles_ok_%d" % rank] = handles == b"".join(bytes([r + 1]) * 256 for r in range(world))
         stores = [torch.zeros_like(g) for _ in range(world)]
         dist.all_gather(stores, torch.from_numpy(g_local.copy()))     # "peer-mapped gradient stores"
         w_new = torch.zeros(len(p0), dtype=torch.float64)
