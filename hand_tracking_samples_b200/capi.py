@@ -26,12 +26,20 @@ SYMBOLS = [
     "hp_train_batch", "hp_train_batch_device", "hp_grad_batch_device", "hp_get_grads", "hp_device_ptrs",
     "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_set_bf16_gradients", "hp_dp_peer_export", "hp_dp_peer_init", "hp_dp_peer_status", "hp_dp_shutdown", "hp_launch_count", "hp_debug_step_times", "hp_profile", "hp_profile_read",
     "hp_peek", "hp_last_error", "hp_version",
+    "hp_dataset_open", "hp_dataset_get_info", "hp_dataset_read", "hp_dataset_eval_depth", "hp_dataset_close",
 ]
 
 
 class LayerDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("in_dims", C.c_int * 3), ("w_dims", C.c_int * 4),
                 ("out_dims", C.c_int * 3), ("n_spans", C.c_int), ("spans", C.POINTER(C.c_int))]
+
+
+class DatasetInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("focal", C.c_float * 2), ("principal", C.c_float * 2),
+                ("depth_scale", C.c_float), ("mplane", C.c_float * 4), ("hasir", C.c_int32), ("rgb_dim", C.c_int32 * 2),
+                ("feye_dim", C.c_int32 * 2), ("segment_scale", C.c_float), ("camtype", C.c_char * 32), ("n_frames", C.c_int64),
+                ("pose_array_size", C.c_int32), ("has_ir_file", C.c_int32), ("has_pose_file", C.c_int32)]
 
 
 class HpError(RuntimeError):
@@ -94,6 +102,12 @@ def lib():
     L.hp_profile.argtypes = [vp, C.c_int]
     L.hp_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     L.hp_peek.argtypes = [vp, C.c_int, i64, vp]
+    L.hp_dataset_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.hp_dataset_get_info.argtypes = [vp, C.POINTER(DatasetInfo)]
+    L.hp_dataset_read.argtypes = [vp, i64, i64, vp, vp, vp]
+    L.hp_dataset_eval_depth.argtypes = [vp, vp, i64, i64, fp, fp, vp, vp, C.c_int]
+    L.hp_dataset_close.argtypes = [vp]
+    L.hp_dataset_close.restype = None
     L.hp_last_error.restype = C.c_char_p
     L.hp_version.restype = C.c_char_p
     _lib = L

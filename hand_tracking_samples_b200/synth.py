@@ -52,3 +52,18 @@ def heatmap_labels(n, seed=4321):
             q = np.floor(g / g.sum() * 255.0)
             t[i, 2048 + s * 16:2048 + (s + 1) * 16] = q / 255.0
     return t
+
+
+def depth_frames(n, h, w, seed, np_=17):
+    """Recorded-dataset-shaped frames: 16-bit depth with a hand-range blob, 8-bit IR, np_ poses (xyz + unit quaternion) per frame."""
+    rng = np.random.default_rng(seed)
+    depth = np.zeros((n, h, w), np.uint16)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for i in range(n):   # a blob of hand-range depth (0.2 .. 0.6 m at depth_scale 0.001) on an empty background
+        cy, cx, r = rng.uniform(0.3, 0.7) * h, rng.uniform(0.3, 0.7) * w, rng.uniform(0.2, 0.4) * min(h, w)
+        m = (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+        depth[i][m] = (rng.uniform(200, 600) + 40 * np.sin(xx[m] * 0.3) + rng.uniform(-5, 5, m.sum())).astype(np.uint16)
+    ir = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    poses = rng.normal(0, 0.2, (n, np_, 7)).astype(np.float32)
+    poses[..., 3:] /= np.linalg.norm(poses[..., 3:], axis=-1, keepdims=True)
+    return depth, ir, poses

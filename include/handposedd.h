@@ -156,6 +156,41 @@ HP_API int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int
 HP_API int hp_render_labels(hp_net *net, const float *points, const float *vals, int64_t n, float *t);
 HP_API int hp_render_labels_device(hp_net *net, const float *points_dev, const float *vals_dev, int64_t n, float *t_dev, void *stream);
 
+/* ---- recorded datasets (host side) ---------------------------------------- */
+
+/* Replaces: load_dataset (include/dataset.h:109-163) for the parallel files DepthDataStreamOut writes
+ * (dataset.h:62-105): <base>.json (DatasetInfo, dataset.h:21-37), <base>.rs (headerless 16-bit depth frames; with
+ * "hasir" each frame is followed by its 8-bit IR image, dataset.h:135), optional <base>.ir and <base>.pose
+ * (pose_array_size x 7 ASCII floats per frame: position xyz, orientation xyzw; 17 bones for the hand model,
+ * train-cnn.cpp:75).  The binary files are memory-mapped; frames are copied on request straight into the caller's
+ * batch buffers.  Same observable results as the reference: a trailing partial frame is dropped, a short .ir file
+ * fills a prefix and leaves zeros, poses past the end of the .pose text are the default Pose, fields missing from
+ * the .json read as 0 / false / "".  Errors instead of the reference's exceptions: HP_ERR_IO when .rs or .json
+ * cannot be opened or dcamera.dims is not positive.  No GPU is needed for these calls. */
+typedef struct hp_dataset hp_dataset;
+typedef struct hp_dataset_info {
+    int32_t width, height;           /* dcamera.dims */
+    float focal[2], principal[2];    /* dcamera.focal, dcamera.principal */
+    float depth_scale;               /* metres per depth unit */
+    float mplane[4];
+    int32_t hasir;                   /* .rs interleaves depth and IR (deprecated in the reference) */
+    int32_t rgb_dim[2], feye_dim[2];
+    float segment_scale;
+    char camtype[32];
+    int64_t n_frames;                /* complete frames in <base>.rs */
+    int32_t pose_array_size;
+    int32_t has_ir_file, has_pose_file;
+} hp_dataset_info;
+HP_API int hp_dataset_open(const char *basename, int pose_array_size, hp_dataset **out);
+HP_API int hp_dataset_get_info(const hp_dataset *ds, hp_dataset_info *info);
+/* Frames [first, first+count): depth[count][h][w], ir[count][h][w], poses[count][pose_array_size][7]; each may be NULL. */
+HP_API int hp_dataset_read(hp_dataset *ds, int64_t first, int64_t count, uint16_t *depth, uint8_t *ir, float *poses);
+/* Datasets already reduced to 64x64 hand crops (compress, train-cnn.cpp:31-50): frames go from the page cache through
+ * hp_eval_depth_batch (depth_scale from the .json); other frame sizes -> HP_ERR_UNSUPPORTED (HandSegmentVR stays host). */
+HP_API int hp_dataset_eval_depth(hp_net *net, hp_dataset *ds, int64_t first, int64_t count, float dmin, float dmax, float *y, float *decoded,
+                                 int precision);
+HP_API void hp_dataset_close(hp_dataset *ds);
+
 /* ---- training ------------------------------------------------------------ */
 
 /* Replaces: CNN::Train (cnn.h:558-580), batched.  One optimiser step on a

@@ -182,6 +182,45 @@ class PostRef:
         return out
 
 
+def have_datasetref() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libdatasetref.so"))
+
+
+class DatasetRef:
+    """The reference's load_dataset / DepthDataStreamOut (oracle/_ref/libdatasetref.so, ref_dataset_shim.cpp)."""
+
+    def __init__(self):
+        L = C.CDLL(os.path.join(HERE, "_ref", "libdatasetref.so"))
+        L.ref_dataset_load.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+        L.ref_dataset_load.restype = C.c_long
+        L.ref_dataset_frame.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_dataset_frame.restype = None
+        L.ref_dataset_save.argtypes = [C.c_char_p, C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L = L
+
+    def load(self, basename, pose_array_size):
+        """-> None when the reference throws, else (info[17], depth [n][h][w], ir [n][h][w], poses [n][np][7])."""
+        info = np.zeros(17, np.float32)
+        n = self.L.ref_dataset_load(str(basename).encode(), pose_array_size, info.ctypes.data)
+        if n < 0:
+            return None
+        w, h = int(info[0]), int(info[1])
+        depth = np.zeros((n, h, w), np.uint16)
+        ir = np.zeros((n, h, w), np.uint8)
+        poses = np.zeros((n, pose_array_size, 7), np.float32)
+        for i in range(n):
+            self.L.ref_dataset_frame(i, depth[i].ctypes.data, ir[i].ctypes.data, poses[i].ctypes.data)
+        return info, depth, ir, poses
+
+    def save(self, basename, cam, depth, ir, poses, segment_scale=0.17):
+        """cam = (fx, fy, px, py, depth_scale); writes <basename>.json/.rs/.ir/.pose with the reference's writer."""
+        n, h, w = depth.shape
+        depth, ir, poses = np.ascontiguousarray(depth, np.uint16), np.ascontiguousarray(ir, np.uint8), np.ascontiguousarray(poses, np.float32)
+        rc = self.L.ref_dataset_save(str(basename).encode(), w, h, *[float(v) for v in cam], float(segment_scale), n, poses.shape[1],
+                                     depth.ctypes.data, ir.ctypes.data, poses.ctypes.data)
+        assert rc == 0
+
+
 class Ref:
     """The unmodified reference cnn.h (handposedd) behind a C ABI."""
 
