@@ -524,16 +524,31 @@ __global__ void __launch_bounds__(256) conv1_wgrad(const float *__restrict__ x, 
 #pragma unroll
         for (int i = 0; i < 4; i++) reinterpret_cast<float4 *>(img)[tid + 256 * i] = src[tid + 256 * i];
         __syncthreads();
-        for (int pp = sub; pp < P1_W * P1_H; pp += 16) {
-            const float g = g1[crop * P1_N + co * 225 + pp];
-            const int id = idx1[crop * P1_N + co * 225 + pp];
-            const int py = pp / P1_W, px = pp % P1_W;
-            const float *ip = img + (4 * py + (id >> 2)) * IN_W + 4 * px + (id & 3);
+        // all 15 (gradient, winner) pairs of this thread are fetched before the first is used: one round of global-load
+        // latency per crop instead of fifteen
+        float gv[15];
+        int iv[15];
 #pragma unroll
-            for (int ky = 0; ky < 5; ky++)
+        for (int j = 0; j < 15; j++) {
+            const int pp = sub + 16 * j;
+            const bool ok = pp < P1_W * P1_H;
+            gv[j] = ok ? g1[crop * P1_N + co * 225 + pp] : 0.f;
+            iv[j] = ok ? idx1[crop * P1_N + co * 225 + pp] : 0;
+        }
 #pragma unroll
-                for (int kx = 0; kx < 5; kx++) acc[ky * 5 + kx] = fmaf(ip[ky * IN_W + kx], g, acc[ky * 5 + kx]);
-            acc[25] += g;
+        for (int j = 0; j < 15; j++) {
+            const int pp = sub + 16 * j;
+            if (pp < P1_W * P1_H) {
+                const float g = gv[j];
+                const int id = iv[j];
+                const int py = pp / P1_W, px = pp % P1_W;
+                const float *ip = img + (4 * py + (id >> 2)) * IN_W + 4 * px + (id & 3);
+#pragma unroll
+                for (int ky = 0; ky < 5; ky++)
+#pragma unroll
+                    for (int kx = 0; kx < 5; kx++) acc[ky * 5 + kx] = fmaf(ip[ky * IN_W + kx], g, acc[ky * 5 + kx]);
+                acc[25] += g;
+            }
         }
     }
 #pragma unroll
@@ -790,8 +805,41 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
     return 0;
 }
 
+// column sums of in[R][ncols] for short R in ONE launch: thread (cx, ry) adds rows ry, ry+32, ... of its column, the
+// 32 row-lanes are combined in a fixed order (deterministic).  Minibatch bias gradients: R = 256 rows.
+__global__ void __launch_bounds__(1024) colsum_direct(const float *__restrict__ in, int R, int ncols, float *__restrict__ dst, int accumulate)
+{
+    __shared__ float sm[32][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (col < ncols) {
+        int r = ry;
+        for (; r + 96 < R; r += 128) {
+            a0 += in[(size_t)r * ncols + col];
+            a1 += in[(size_t)(r + 32) * ncols + col];
+            a2 += in[(size_t)(r + 64) * ncols + col];
+            a3 += in[(size_t)(r + 96) * ncols + col];
+        }
+        for (; r < R; r += 32) a0 += in[(size_t)r * ncols + col];
+    }
+    sm[ry][cx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ry == 0 && col < ncols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k++) t += sm[k][cx];
+        dst[col] = accumulate ? dst[col] + t : t;
+    }
+}
+
 static int colsum(Net &net, const float *in, int64_t R, int ncols, float *dst, bool accumulate, cudaStream_t s)
 {
+    if (R <= 512 && ncols >= 1024) {   // enough columns to fill the machine with one CTA per 32 of them
+        colsum_direct<<<(ncols + 31) / 32, 1024, 0, s>>>(in, (int)R, ncols, dst, accumulate ? 1 : 0);
+        LAUNCH_CHECK(net);
+        return 0;
+    }
     int gy = (int)((R + 63) / 64);
     if (gy > 64) gy = 64;
     if (gy < 1) gy = 1;

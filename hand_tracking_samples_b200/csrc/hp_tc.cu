@@ -452,23 +452,30 @@ __global__ void __launch_bounds__(256) convert_rows_bf16(const float *__restrict
 }
 
 // bf16 src[n][C] -> dst[C][ldk] (k contiguous) with zero fill for n <= k < n_pad: the K-major operands of the
-// weight-gradient GEMMs (LFull::update, cnn.h:438-445, is the contraction over the batch)
-__global__ void __launch_bounds__(256) transpose_bf16(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int n, int n_pad,
-                                                      int C, int ldk)
+// weight-gradient GEMMs (LFull::update, cnn.h:438-445, is the contraction over the batch).  Both operands of one GEMM
+// are transposed by one launch (blockIdx.z picks the job).
+struct TransposeJob {
+    const __nv_bfloat16 *src;
+    __nv_bfloat16 *dst;
+    int C;
+};
+__global__ void __launch_bounds__(256) transpose_bf16_pair(TransposeJob j0, TransposeJob j1, int n, int n_pad, int ldk)
 {
     __shared__ __nv_bfloat16 tile[32][34];
+    const TransposeJob j = blockIdx.z ? j1 : j0;
     const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    if (c0 >= j.C) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int k = k0 + ty + 8 * i;
-        tile[ty + 8 * i][tx] = (k < n) ? src[(size_t)k * C + c0 + tx] : __float2bfloat16_rn(0.f);
+        tile[ty + 8 * i][tx] = (k < n) ? j.src[(size_t)k * j.C + c0 + tx] : __float2bfloat16_rn(0.f);
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int k = k0 + tx;
-        if (k < n_pad) dst[(size_t)(c0 + ty + 8 * i) * ldk + k] = tile[tx][ty + 8 * i];
+        if (k < n_pad) j.dst[(size_t)(c0 + ty + 8 * i) * ldk + k] = tile[tx][ty + 8 * i];
     }
 }
 
@@ -937,9 +944,8 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
         LAUNCH_CHECK(net);
     }
     if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
-    transpose_bf16<<<dim3(FC1_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->h1, t->h1T, M, n_pad, FC1_OUT, (int)TRAIN_CAP);
-    LAUNCH_CHECK(net);
-    transpose_bf16<<<dim3(N_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->dlog_bf, t->dlogT, M, n_pad, N_OUT, (int)TRAIN_CAP);
+    transpose_bf16_pair<<<dim3(N_OUT / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->h1, t->h1T, FC1_OUT}, TransposeJob{t->dlog_bf, t->dlogT, N_OUT}, M,
+                                                                                 n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW2[2048][2304] = h1^T * dlog
     if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
@@ -953,9 +959,8 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[0], s));
     // ---- fc1
     if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
-    transpose_bf16<<<dim3(FC1_IN / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->p2, t->p2T, M, n_pad, FC1_IN, (int)TRAIN_CAP);
-    LAUNCH_CHECK(net);
-    transpose_bf16<<<dim3(FC1_OUT / 32, (n_pad + 31) / 32), 256, 0, s>>>(t->da1_bf, t->da1T, M, n_pad, FC1_OUT, (int)TRAIN_CAP);
+    transpose_bf16_pair<<<dim3(FC1_IN / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->p2, t->p2T, FC1_IN}, TransposeJob{t->da1_bf, t->da1T, FC1_OUT}, M,
+                                                                                  n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW1[k'][2048] = p2^T * da1, rows un-permuted from HWC to the reference's CHW flatten on store
     if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
