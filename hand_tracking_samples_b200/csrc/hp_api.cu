@@ -209,7 +209,8 @@ static int finish_step(Net &net, float alpha, int precision, cudaStream_t s)
             // Peers store into this rank's FP32 master weights, so on the FP32 path (whose dX GEMMs read them) the
             // kernel must also wait for the dX GEMM of the bucket; the tensor path only reads the bf16 shadows.
             HP_CUDA_TRY(cudaStreamWaitEvent(cs, net.ev_bucket[b], 0));
-            if (b < 2 && precision != HP_PRECISION_TENSOR) HP_CUDA_TRY(cudaStreamWaitEvent(cs, net.ev_dx[b], 0));
+            static const bool after_dx = getenv("HP_DP_EXCH_AFTER_DX") != nullptr;   // experiment: start the exchange after the bucket's dX GEMM
+            if (b < 2 && (precision != HP_PRECISION_TENSOR || after_dx)) HP_CUDA_TRY(cudaStreamWaitEvent(cs, net.ev_dx[b], 0));
             if (int rc = peer_sgd_bucket(net, alpha, off[b], end[b] - off[b], cs)) return rc;
             HP_CUDA_TRY(cudaEventRecord(net.ev_ar[b], cs));
             HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_ar[b], 0));

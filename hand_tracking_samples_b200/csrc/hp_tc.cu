@@ -694,6 +694,10 @@ int tc_init(Net &net)
     cudaDeviceProp prop;
     HP_CUDA_TRY(cudaGetDeviceProperties(&prop, net.device));
     t->num_sms = t->total_sms = prop.multiProcessorCount;
+    if (const char *e = getenv("HP_TC_RESERVE_SMS")) {   // experiments: single-GPU runs with the data-parallel SM reservation
+        const int r = atoi(e);
+        if (r > 0 && r < t->total_sms / 2) t->num_sms = t->total_sms - r;
+    }
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1t, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2t, (size_t)FC2_OUT * FC2_IN * 2));
     if (int rc = make_map_bf16(&t->tm_w1t, t->w1t, FC1_OUT, FC1_IN, 256)) return rc;
@@ -706,6 +710,7 @@ int tc_init(Net &net)
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(128)));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1b, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2b, (size_t)FC2_OUT * FC2_IN * 2));
@@ -863,6 +868,8 @@ static int tc_train_ensure(Net &net)
     if (int rc = make_map_bf16(&t->tm_p2T, t->p2T, FC1_IN, cap, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_dlogT, t->dlogT, N_OUT, cap, 256)) return rc;
     if (int rc = make_map_bf16(&t->tm_da1T, t->da1T, FC1_OUT, cap, 256)) return rc;
+    if (int rc = make_map_bf16(&t->tm_dlogT128, t->dlogT, N_OUT, cap, 128)) return rc;
+    if (int rc = make_map_bf16(&t->tm_da1T128, t->da1T, FC1_OUT, cap, 128)) return rc;
     // conv2 backward operands (conv2_bwd_operands)
     const int64_t ld = cap * C2_POS;
     HP_CUDA_TRY(cudaMalloc((void **)&t->e2, (size_t)ld * C2_CO * 2));
@@ -948,6 +955,12 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
                                                                                  n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW2[2048][2304] = h1^T * dlog
+    // 16 x 9 = 144 tiles of 128x256 are one wave on 148 SMs but two on the 132 left when SMs are reserved for the
+    // data-parallel exchange CTAs: 128-wide tiles (288 of them) then waste a fifth of a wave instead of most of one
+    const bool half_tiles = t->num_sms < 144;
+    if (half_tiles) {
+        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128>(net, t->tm_h1T, t->tm_dlogT128, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
+    } else
     if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
     // da1 = (dlog * W2^T) .* (1 - h1^2)
@@ -963,6 +976,10 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
                                                                                   n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW1[k'][2048] = p2^T * da1, rows un-permuted from HWC to the reference's CHW flatten on store
+    if (half_tiles) {
+        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128>(net, t->tm_p2T, t->tm_da1T128, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW},
+                                                        FC1_IN, FC1_OUT, n_pad, s)) return rc;
+    } else
     if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
                                                     FC1_OUT, n_pad, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));

@@ -23,6 +23,7 @@ struct TcState {
     CUtensorMap tm_e2, tm_e2T, tm_colT, tm_w2kt;
     CUtensorMap tm_w1t64, tm_w2t64, tm_w1b64, tm_w2b64;   // the same weights with 64-row boxes (small-batch GEMMs)
     CUtensorMap tm_w1b, tm_w2b, tm_dlog, tm_da1, tm_h1T, tm_p2T, tm_dlogT, tm_da1T;
+    CUtensorMap tm_dlogT128, tm_da1T128;                  // 128-row boxes: half-width weight-gradient tiles in data-parallel mode
     // activations
     __nv_bfloat16 *p2 = nullptr;   // [cap][2304] pooled conv2 stage (fc1 input), HWC flatten
     __nv_bfloat16 *h1 = nullptr;   // [cap][2048] tanh(fc1)
