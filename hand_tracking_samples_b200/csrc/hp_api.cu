@@ -414,6 +414,7 @@ int hp_destroy(hp_net *net)
     cudaSetDevice(n.device);
     cudaDeviceSynchronize();
     if (n.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n.nccl_comm);
+    if (n.peer) peer_shutdown(n);   // normally done by hp_dp_shutdown after a host-side barrier
     tc_destroy(n);
     Workspace &w = n.ws;
     void *bufs[] = {n.params, n.grads, w.p1, w.idx1, w.col, w.c2, w.p2, w.idx2, w.h1, w.logits, w.y, w.dlog, w.da1, w.g2, w.colgrad,
@@ -804,6 +805,7 @@ int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world)
     if (!net || !all_handles || world < 2 || rank < 0 || rank >= world) { set_error("bad argument"); return HP_ERR_INVALID; }
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
+    if (N.peer && N.peer->ready) { set_error("peer exchange already initialised on this net; call hp_dp_shutdown first"); return HP_ERR_INVALID; }
     // the exchange kernels run one 1024-thread CTA on each SM that the persistent tensor-core grids leave free
     int reserve = 16;
     if (const char *e = getenv("HP_DP_RESERVE_SMS")) reserve = atoi(e);
