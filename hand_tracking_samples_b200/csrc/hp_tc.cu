@@ -40,12 +40,12 @@ constexpr int STG_BYTES = 4096;                 // per-warp output staging tile:
 constexpr int GEMM_THREADS = 256;
 constexpr int gemm_smem(int bn) { return STAGES * (A_BYTES + bn * BK * 2) + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
 
-enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3 };
+enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3, TC_EPI_STORE_BF16 = 4 };
 enum { TC_FLAG_ACCUMULATE = 1, TC_FLAG_ROWS_HWC_TO_CHW = 2 };
 
 struct EpiArgs {
     const float *bias;         // TANH_BF16 / SOFTMAX_F32
-    void *out;                 // TANH_BF16: bf16 [M][N]; SOFTMAX_F32 / STORE_F32 / DTANH: fp32 [M][N] (DTANH: may be null)
+    void *out;                 // TANH_BF16 / STORE_BF16: bf16 [M][N]; SOFTMAX_F32 / STORE_F32 / DTANH: fp32 [M][N] (DTANH: may be null)
     __nv_bfloat16 *out2;       // DTANH: bf16 [M][N]
     const __nv_bfloat16 *H;    // DTANH: layer output h, bf16 [M][N]: result = (1 - h*h) * acc  (TanH::df, cnn.h:32,467)
     int flags;                 // STORE_F32: TC_FLAG_ACCUMULATE (out += acc), TC_FLAG_ROWS_HWC_TO_CHW (row k' -> (k'&63)*36 + (k'>>6))
@@ -258,7 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             };
-            if (EPI == TC_EPI_TANH_BF16) {
+            if (EPI == TC_EPI_TANH_BF16 || EPI == TC_EPI_STORE_BF16) {   // STORE_BF16: the plain product, rounded once
                 uint8_t *gtile = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 2;
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; c++) {   // 64 columns = 128 B of bf16 per row
@@ -271,9 +271,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t packed[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float2 bv = *reinterpret_cast<const float2 *>(bptr + c * 64 + h * 32 + j);
-                            const float v0 = tanh_fast(__uint_as_float(r[j]) + bv.x);
-                            const float v1 = tanh_fast(__uint_as_float(r[j + 1]) + bv.y);
+                            float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+                            if (EPI == TC_EPI_TANH_BF16) {
+                                const float2 bv = *reinterpret_cast<const float2 *>(bptr + c * 64 + h * 32 + j);
+                                v0 = tanh_fast(v0 + bv.x);
+                                v1 = tanh_fast(v1 + bv.y);
+                            }
                             __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
                             packed[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
                         }
@@ -571,12 +574,13 @@ __global__ void __launch_bounds__(256) conv2_bwd_operands(const float *__restric
 
 // col2im of dL/dcol [(n,pos)][k = tap*16 + ci] (LConv::backward, cnn.h:258-268, as a gather) fused with TanH::df of the
 // conv1 stage: g1[n][ci][Y][X] = (1 - p1^2) * sum_{ky,kx} dcol[(Y-ky, X-kx)][(ky,kx,ci)].  One crop per CTA; a thread
-// owns 4 consecutive ci of one pixel, so every load is 16 B and a warp reads 8 x 64 contiguous bytes per tap.
-__global__ void __launch_bounds__(256) col2im_g1_vec(const float *__restrict__ colgrad, const float *__restrict__ p1, float *__restrict__ g1)
+// owns 4 consecutive ci of one pixel; dL/dcol is stored as bf16 (half the bytes of this memory-bound pair of kernels: the
+// GEMM that writes it and this gather), every load is 8 B and a warp reads 8 x 32 contiguous bytes per tap.
+__global__ void __launch_bounds__(256) col2im_g1_vec(const __nv_bfloat16 *__restrict__ colgrad, const float *__restrict__ p1, float *__restrict__ g1)
 {
     __shared__ float so[P1_N];
     const int64_t crop = blockIdx.x;
-    const float *cg = colgrad + crop * (int64_t)(C2_POS * C2_KDIM);
+    const __nv_bfloat16 *cg = colgrad + crop * (int64_t)(C2_POS * C2_KDIM);
     for (int i = threadIdx.x; i < P1_W * P1_H * 4; i += 256) {
         const int r = i >> 2, c4 = (i & 3) * 4;
         const int Y = r / P1_W, X = r - Y * P1_W;
@@ -589,8 +593,10 @@ __global__ void __launch_bounds__(256) col2im_g1_vec(const float *__restrict__ c
             for (int kx = 0; kx < 4; kx++) {
                 const int xx = X - kx;
                 if (xx < 0 || xx >= C2_W) continue;
-                const float4 v = *reinterpret_cast<const float4 *>(cg + (y * C2_W + xx) * C2_KDIM + (ky * 4 + kx) * 16 + c4);
-                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                const uint2 v = *reinterpret_cast<const uint2 *>(cg + (y * C2_W + xx) * C2_KDIM + (ky * 4 + kx) * 16 + c4);
+                const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.x));
+                const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.y));
+                a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
             }
         }
         so[(c4 + 0) * 225 + r] = a.x;
@@ -711,6 +717,7 @@ int tc_init(Net &net)
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(128)));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_BF16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1b, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2b, (size_t)FC2_OUT * FC2_IN * 2));
@@ -912,8 +919,9 @@ static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const floa
     reduce_c2w_t<<<C2_KDIM, 256, 0, s>>>(G + OFF_C2W, w.partial, S, accumulate ? 1 : 0);
     LAUNCH_CHECK(net);
     // dL/dcol, then col2im fused with the conv1-stage tanh'
-    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_e2, t->tm_w2kt, EpiArgs{nullptr, w.colgrad, nullptr, nullptr, 0, 0}, R, C2_KDIM, C2_CO, s)) return rc;
-    col2im_g1_vec<<<(unsigned)n, 256, 0, s>>>(w.colgrad, w.p1, w.g1);
+    __nv_bfloat16 *dcol = reinterpret_cast<__nv_bfloat16 *>(w.colgrad);   // the FP32 path's [n*144][256] fp32 buffer, half used
+    if (int rc = launch_gemm<TC_EPI_STORE_BF16, 256>(net, t->tm_e2, t->tm_w2kt, EpiArgs{nullptr, dcol, nullptr, nullptr, 0, 0}, R, C2_KDIM, C2_CO, s)) return rc;
+    col2im_g1_vec<<<(unsigned)n, 256, 0, s>>>(dcol, w.p1, w.g1);
     LAUNCH_CHECK(net);
     return fp32_conv1_wgrad(net, x, n, accumulate, s);
 }

@@ -252,7 +252,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                 for (int half = 0; half < 2; half++) {
                     ptx::mbar_wait(&acc1_full[e * 2 + half], it & 1);
                     ptx::tc_fence_after();
-                    if (ew == 0) TRACE(2 + 3 * e, it, 2 + 2 * (e * 2 + half));
+                    if (ew == 0 || e == 1) TRACE(e ? 5 + ew : 2, it, 2 + 2 * (e * 2 + half));
                     const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC1 + half * 128;
 #pragma unroll
                     for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
@@ -278,7 +278,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
-                    if (ew == 0) TRACE(2 + 3 * e, it, 3 + 2 * (e * 2 + half));
+                    if (ew == 0 || e == 1) TRACE(e ? 5 + ew : 2, it, 3 + 2 * (e * 2 + half));
                 }
                 const int px = 2 * pxh + e;
                 if (py < 15 && px < 15) {
@@ -306,7 +306,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
             ptx::fence_proxy_async();   // generic-proxy stores -> visible to the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
-            if (ew == 0) TRACE(2 + 3 * my_e, it, 10);
+            if (ew == 0 || my_e == 1) TRACE(my_e ? 5 + ew : 2, it, 10);
         }
     } else if (warp >= 12 && warp < 16) {
         // ===================== epilogue 2: conv2 accumulators -> pooled features =====================
