@@ -236,6 +236,16 @@ static int finish_step(Net &net, float alpha, int precision, cudaStream_t s)
                                          /*ncclSum*/ 0, net.nccl_comm, cs));
             HP_CUDA_TRY(cudaEventRecord(net.ev_ar[b], cs));
             HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_ar[b], 0));
+        } else if (b == 2) {
+            // one GPU: the conv bucket is the exposed end of the step and backward has just finished on the caller's
+            // stream, so its update runs right there (no cross-stream hops); the side stream's FC work is joined after it
+            HP_CUDA_TRY(cudaEventRecord(net.ev_tail, us));
+            if (int rc = sgd_apply_range(net, alpha, off[b], end[b] - off[b], s)) return rc;
+            if (precision == HP_PRECISION_TENSOR)
+                if (int rc = tc_refresh_bucket(net, b, s)) return rc;
+            HP_CUDA_TRY(cudaStreamWaitEvent(s, net.ev_tail, 0));
+            net.tc_dirty = (precision != HP_PRECISION_TENSOR);
+            return 0;
         } else {
             HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_bucket[b], 0));
         }

@@ -613,14 +613,6 @@ __global__ void __launch_bounds__(256) col2im_g1_vec(const __nv_bfloat16 *__rest
     }
 }
 
-// fp32 W2[co][ci*16+tap] (.cnnb OIHW) -> bf16 w2kt[k = tap*16+ci][co]: the K-major B operand of the dL/dcol GEMM
-__global__ void __launch_bounds__(256) build_w2kt(const float *__restrict__ params, __nv_bfloat16 *__restrict__ w2kt)
-{
-    const int i = blockIdx.x * 256 + threadIdx.x;   // = k*64 + co
-    const int co = i & 63, k = i >> 6, ci = k & 15, tap = k >> 4;
-    w2kt[i] = __float2bfloat16_rn(params[OFF_C2W + co * C2_KDIM + ci * 16 + tap]);
-}
-
 // dW2[co][ci*16+tap] (+)= sum_s partial[s][k = tap*16+ci][co]   (s ascending: deterministic)
 __global__ void __launch_bounds__(256) reduce_c2w_t(float *__restrict__ dst, const float *__restrict__ partial, int S, int accumulate)
 {
@@ -762,9 +754,7 @@ int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s)
         convert_rows_bf16<true><<<FC1_IN, 256, 0, s>>>(net.params + OFF_F1W, t->w1b, FC1_OUT);
         LAUNCH_CHECK(net);
     } else {
-        if (int rc = tc_conv_refresh(net, s)) return rc;
-        build_w2kt<<<C2_KDIM * C2_CO / 256, 256, 0, s>>>(net.params, t->w2kt);
-        LAUNCH_CHECK(net);
+        if (int rc = tc_conv_refresh(net, s)) return rc;   // b1/b2 images and w2kt (the dL/dcol GEMM's B operand)
     }
     return 0;
 }

@@ -450,9 +450,9 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
 //  b1: row nrow = pos*16 + co (pos = hierarchical pool-scan index of window offset (dy,dx)), 64 k = (r,c) of the 8x8 patch; value = w1[co][r-dy][c-dx]
 //      inside the 5x5 support, else 0; 128-byte rows, 16-byte chunk r stored at chunk (r ^ (nrow & 7)).
 //  b2: [tap][kchunk][co][8 ci] bf16 (16-byte rows): the un-swizzled K-major core-matrix order.
-__global__ void __launch_bounds__(256) build_conv_images(const float *__restrict__ params, uint8_t *__restrict__ b1, uint8_t *__restrict__ b2)
+__device__ __forceinline__ void build_conv_image_elem(int i, const float *__restrict__ params, uint8_t *__restrict__ b1, uint8_t *__restrict__ b2,
+                                                      __nv_bfloat16 *__restrict__ w2kt)
 {
-    const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < 256 * 64) {
         const int nrow = i >> 6, k = i & 63;
         const int pos = nrow >> 4, co = nrow & 15;
@@ -468,6 +468,17 @@ __global__ void __launch_bounds__(256) build_conv_images(const float *__restrict
         const int ci = kc * 8 + ci8;
         reinterpret_cast<__nv_bfloat16 *>(b2)[i] = __float2bfloat16_rn(params[OFF_C2W + co * 256 + ci * 16 + tap]);
     }
+    if (i < C2_KDIM * C2_CO) {
+        // w2kt[k = tap*16+ci][co] = conv2.W[co][ci][tap]: the K-major B operand of the training dL/dcol GEMM (hp_tc.cu)
+        const int co = i & 63, k = i >> 6, ci = k & 15, tap = k >> 4;
+        w2kt[i] = __float2bfloat16_rn(params[OFF_C2W + co * C2_KDIM + ci * 16 + tap]);
+    }
+}
+
+__global__ void __launch_bounds__(256) build_conv_images(const float *__restrict__ params, uint8_t *__restrict__ b1, uint8_t *__restrict__ b2,
+                                                         __nv_bfloat16 *__restrict__ w2kt)
+{
+    build_conv_image_elem(blockIdx.x * 256 + threadIdx.x, params, b1, b2, w2kt);
 }
 
 #ifdef HP_CONV_TRACE
@@ -490,7 +501,7 @@ int tc_conv_init(Net &net)
 int tc_conv_refresh(Net &net, cudaStream_t s)
 {
     TcState *t = net.tc;
-    build_conv_images<<<64, 256, 0, s>>>(net.params, t->b1_img, t->b2_img);
+    build_conv_images<<<64, 256, 0, s>>>(net.params, t->b1_img, t->b2_img, t->w2kt);
     LAUNCH_CHECK(net);
     return 0;
 }
