@@ -57,9 +57,10 @@ DROPIN_BIN = os.path.join(ROOT, "tests", "_bin", "dropin_main")
 
 def build_dropin_test(reference_root="/root/reference"):
     """g++-compile the C++ drop-in checks against include/handposedd/cnn.h (no CUDA needed to build):
-    tests/_bin/dropin_main (the PoseInitializerCNN call sequence, always) and tests/_bin/ht_dropin (the
-    reference's own include/handtrack.h compiled UNMODIFIED against the drop-in header, only where the
-    reference tree is present).  The binaries travel to the GPU box; the reference tree does not."""
+    tests/_bin/dropin_main (the PoseInitializerCNN call sequence, always), tests/_bin/ht_dropin (the
+    reference's own include/handtrack.h compiled UNMODIFIED against the drop-in header) and tests/_bin/dataset_dropin
+    (load_dataset rebuilt on hp_dataset_* beside the reference's own loader) -- the last two only where the
+    reference tree is present.  The binaries travel to the GPU box; the reference tree does not."""
     os.makedirs(os.path.dirname(DROPIN_BIN), exist_ok=True)
     common = ["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "include"), "-L" + HERE, "-lhandposedd",
               "-Wl,-rpath,$ORIGIN/../../hand_tracking_samples_b200"]
@@ -70,6 +71,11 @@ def build_dropin_test(reference_root="/root/reference"):
         subprocess.check_call(common[:4] + ["-fpermissive", "-Wno-narrowing", "-w", "-I" + reference_root,
                                             os.path.join(ROOT, "tests", "cpp", "handtrack_dropin.cpp"), "-o", ht] + common[4:] + ["-lpthread"])
         out.append(ht)
+        # the reference-side load_dataset binding of INTEGRATION.md next to the reference's own loader (host-only program)
+        dsb = os.path.join(ROOT, "tests", "_bin", "dataset_dropin")
+        subprocess.check_call(common[:4] + ["-fpermissive", "-Wno-narrowing", "-w", "-I" + reference_root,
+                                            os.path.join(ROOT, "tests", "cpp", "dataset_dropin.cpp"), "-o", dsb] + common[4:])
+        out.append(dsb)
     return out
 
 

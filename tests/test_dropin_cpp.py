@@ -18,6 +18,28 @@ def test_dropin_sources_compile():
     if os.path.isdir("/root/reference"):
         # the reference's unmodified handtrack.h compiled against the drop-in CNN class
         assert os.path.exists(os.path.join(BIN, "ht_dropin"))
+        assert os.path.exists(os.path.join(BIN, "dataset_dropin"))
+
+
+def test_reference_side_load_dataset_binding_matches_reference_loader(tmp_path):
+    """INTEGRATION.md's load_dataset stub (on hp_dataset_*) vs the reference's own load_dataset, same binary, same files:
+    identical Frames (depth, ir, poses, camera, fid) for the golden dataset and for a ragged one.  Host-only."""
+    exe = os.path.join(BIN, "dataset_dropin")
+    if not os.path.exists(exe):
+        if not os.path.isdir("/root/reference"):
+            pytest.skip("tests/_bin/dataset_dropin needs /root/reference at build time")
+        _build.build_dropin_test()
+    r = subprocess.run([exe, os.path.join(GOLDEN, "dataset", "crops64"), "17"], capture_output=True, text=True)
+    assert r.returncode == 0 and "6 frames" in r.stdout, r.stdout + r.stderr
+    # ragged copy: partial last frame, short .ir, pose text cut mid-frame, more poses requested than recorded
+    import shutil
+    for ext in (".json", ".rs", ".ir", ".pose"):
+        shutil.copy(os.path.join(GOLDEN, "dataset", "crops64" + ext), tmp_path / ("r" + ext))
+    for ext, keep in ((".rs", 8192 * 4 + 100), (".ir", 4096 * 2 + 7), (".pose", 700)):
+        data = open(tmp_path / ("r" + ext), "rb").read()
+        open(tmp_path / ("r" + ext), "wb").write(data[:keep])
+    r = subprocess.run([exe, str(tmp_path / "r"), "19"], capture_output=True, text=True)
+    assert r.returncode == 0 and "4 frames" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.gpu
