@@ -36,9 +36,10 @@ void set_error(const char *fmt, ...)
 constexpr int64_t FP32_CHUNK = 2048;   // crops per pass of the FP32 path (im2col workspace bound)
 constexpr int64_t STAGE_CHUNK = 8192;  // crops per host<->device staging chunk
 // Crops per chunk of the pipelined host-buffer Eval.  The uploads run back to back on PCIe; what the pipeline cannot hide
-// is the LAST chunk's compute + download, so the chunk is kept small (64 MiB up, 36 MiB down): at 8,192 the exposed tail
-// was 1.6 ms of a 22 ms call over 65,536 crops.
-constexpr int64_t PIPE_CHUNK = 4096;
+// is the LAST chunk's compute + download, so the chunk is kept small.  Measured per 65,536 crops, tensor path, pinned
+// buffers (tools/dbg/e2e_chunks.py): 8,192 -> 21.96 ms, 4,096 -> 21.23, 2,048 -> 20.78, 1,024 -> 20.63 (the bare 1 GiB upload
+// takes 19.3 ms).  2,048 keeps the FP32 path's kernels at the batch size they are tiled for.
+constexpr int64_t PIPE_CHUNK = 2048;
 
 static std::mutex g_ref_mutex;
 
@@ -540,7 +541,12 @@ int hp_eval_batch_device(hp_net *net, const float *x_dev, int64_t n, float *y_de
 struct DepthNorm { float scale, dmin, dmax; };
 static int eval_host_pipeline(Net &N, const void *x, int elem, const DepthNorm *norm, int64_t n, float *y, float *dec, int precision)
 {
-    const int64_t chunk = std::min<int64_t>(n, PIPE_CHUNK);
+    static const int64_t pipe_chunk = [] {   // HP_PIPE_CHUNK: tuning override (tools/dbg/e2e_chunks.py)
+        const char *e = getenv("HP_PIPE_CHUNK");
+        const int64_t v = e ? atoll(e) : 0;
+        return (v >= 256 && v <= STAGE_CHUNK) ? v : PIPE_CHUNK;
+    }();
+    const int64_t chunk = std::min<int64_t>(n, pipe_chunk);
     const bool pin_x = is_pinned_host(x), pin_y = y ? is_pinned_host(y) : true, pin_d = dec ? is_pinned_host(dec) : true;
     if (int rc = ensure_staging(N, chunk, !pin_x, !pin_y)) return rc;
     cudaStream_t s = N.stream, h2d = N.comm_stream, d2h = N.d2h_stream;
