@@ -220,7 +220,9 @@ HP_API int hp_grad_batch_device(hp_net *net, const float *x_dev, const float *t_
 HP_API int hp_get_grads(const hp_net *net, float *grads_host);
 /* Device address of the weight / gradient stores (HP_N_PARAMS floats each). */
 HP_API int hp_device_ptrs(hp_net *net, float **params_dev, float **grads_dev);
-/* W <- W - alpha * grads (the SGD epilogue on its own).  DEVICE, caller's stream. */
+/* W <- W - alpha * grads (the SGD epilogue on its own) from THIS rank's gradient store: for single-GPU custom optimisers.
+ * (hp_grad_batch_device does not exchange gradients; data-parallel steps go through hp_train_batch_device.)
+ * DEVICE, caller's stream. */
 HP_API int hp_apply_grads_device(hp_net *net, float alpha, void *stream);
 
 /* ---- data parallelism (new; the reference is single-process) ------------ */
@@ -232,8 +234,9 @@ HP_API int hp_dp_unique_id(void *id128);
  * step, bucketed fc2 | fc1 | conv, launched as each bucket's weight gradient
  * finishes, and applies the identical update on every rank. */
 HP_API int hp_dp_init(hp_net *net, const void *id128, int rank, int world);
-/* Opt-in: steps run with HP_PRECISION_TENSOR send the two FC gradient buckets (99.8 % of the bytes) over NVLink as
- * bf16 and sum them in bf16 (18.9 MB instead of 37.8 MB per step).  FP32 steps always travel as fp32. */
+/* Opt-in, NCCL exchange only (ignored once hp_dp_peer_init is in effect): steps run with HP_PRECISION_TENSOR send the two
+ * FC gradient buckets (99.8 % of the bytes) over NVLink as bf16 and sum them in bf16 (18.9 MB instead of 37.8 MB per step).
+ * FP32 steps always travel as fp32. */
 HP_API int hp_dp_set_bf16_gradients(hp_net *net, int enable);
 /* NVLink peer-memory exchange (one process per GPU of one NVSwitch box, 2..8 ranks): the reduce-scatter of the
  * gradient sums, the SGD update (cnn.h:438-445, 269-279) and the all-gather of the updated weights run as ONE kernel
