@@ -161,8 +161,9 @@ struct hp_dataset {
 };
 
 // `in >> float` over the whole .pose text in file order (geometric.h:133,139), with the stream's failure behaviour:
-// the element at which extraction first fails becomes 0 (C++11 num_get) and everything after it keeps the value a
-// default-constructed Pose has -- position (0,0,0), orientation (0,0,0,1).
+// at end of file nothing more is stored; at a token that is not a number the element being read becomes 0 (C++11
+// num_get) -- and in both cases everything after it keeps the value a default-constructed Pose has: position (0,0,0),
+// orientation (0,0,0,1).
 static void parse_poses(const Mapped &m, int64_t n_frames, int np, std::vector<float> &out)
 {
     out.assign((size_t)n_frames * np * 7, 0.f);
@@ -172,6 +173,7 @@ static void parse_poses(const Mapped &m, int64_t n_frames, int np, std::vector<f
     const char *s = text.c_str();
     for (size_t i = 0; i < out.size(); i++) {
         while (*s == ' ' || *s == '\t' || *s == '\n' || *s == '\r' || *s == '\v' || *s == '\f') s++;
+        if (*s == 0) return;   // end of file: the stream's sentry fails before num_get runs, the element keeps its default
         // num_get only accumulates characters a decimal float can contain, so "nan", "inf" and hex floats fail (or stop
         // early) exactly as they do for the reference's `in >> v[i]`
         char tok[64];
@@ -180,7 +182,7 @@ static void parse_poses(const Mapped &m, int64_t n_frames, int np, std::vector<f
         tok[len] = 0;
         char *tend = nullptr;
         const float v = strtof(tok, &tend);
-        if (tend == tok) {   // end of file or a token that is not a number: failbit
+        if (tend == tok) {   // a token that is not a number: failbit, zero stored
             out[i] = 0.f;
             return;
         }
