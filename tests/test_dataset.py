@@ -123,6 +123,13 @@ def test_ragged_and_missing_companions(tmp_path):
     open(base + ".pose", "w").write(text[:cut] + " oops 1 2 3")   # a non-numeric token: failbit, the rest stays default
     same_as_reference(base, 2)
     same_as_reference(base, 5)                  # caller asks for more poses per frame than were recorded
+    # end of file exactly where an orientation.w is due: the stream's sentry fails BEFORE num_get, so the element keeps its
+    # default 1 (a non-numeric token there would store 0) -- found by tests/test_dataset_fuzz.py
+    vals = text.split()
+    open(base + ".pose", "w").write(" ".join(vals[:2 * 7 + 6]))
+    same_as_reference(base, 2)
+    open(base + ".pose", "w").write(" ".join(vals[:2 * 7 + 6]) + " zzz")
+    same_as_reference(base, 2)
     os.remove(base + ".ir")
     os.remove(base + ".pose")
     ds = same_as_reference(base, 2)
