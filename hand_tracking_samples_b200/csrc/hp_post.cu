@@ -78,10 +78,17 @@ __global__ void __launch_bounds__(256) decode_kernel(const float *__restrict__ y
             }
         const float px = (wsum == 0) ? (float)bx : __fdiv_rn(vx, wsum);
         const float py = (wsum == 0) ? (float)by : __fdiv_rn(vy, wsum);
-        const int rx = (int)__fadd_rn(px, 0.5f), ry = (int)__fadd_rn(py, 0.5f);   // PeakVolume, misc_image.h:330
+        // PeakVolume, misc_image.h:330: `int2 p(pf + float2(0.5f))`.  When pixel (0,0) is NaN the sub-pixel peak is NaN and
+        // the reference's float->int conversion is undefined behaviour; the pinned x86 build (cvttss2si) yields INT_MIN
+        // for NaN and out-of-range values, which empties both loops (volume 0), whereas CUDA's conversion yields 0 and
+        // would sum a window.  Follow the pinned reference.
+        const float fx = __fadd_rn(px, 0.5f), fy = __fadd_rn(py, 0.5f);
+        const bool x_ok = fx >= -2147483648.0f && fx < 2147483648.0f, y_ok = fy >= -2147483648.0f && fy < 2147483648.0f;
+        const int rx = x_ok ? (int)fx : 0, ry = y_ok ? (int)fy : 0;
         float vol = 0.0f;
-        for (int sy_ = max(0, ry - 1); sy_ < min(16, ry + 2); sy_++)
-            for (int sx = max(0, rx - 1); sx < min(16, rx + 2); sx++) vol = __fadd_rn(vol, m[sy_ * 16 + sx]);
+        if (x_ok && y_ok)
+            for (int sy_ = max(0, ry - 1); sy_ < min(16, ry + 2); sy_++)
+                for (int sx = max(0, rx - 1); sx < min(16, rx + 2); sx++) vol = __fadd_rn(vol, m[sy_ * 16 + sx]);
         float *o = out + crop * 48 + 4 * warp;
         o[0] = px;
         o[1] = py;
