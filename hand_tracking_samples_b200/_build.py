@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhandposedd.so")
-SOURCES = ["hp_api.cu", "hp_fp32.cu", "hp_tc.cu", "hp_tc_conv.cu", "hp_post.cu", "hp_peer.cu", "hp_dataset.cu"]
+SOURCES = ["hp_api.cu", "hp_fp32.cu", "hp_tc.cu", "hp_tc_conv.cu", "hp_tc_conv2.cu", "hp_post.cu", "hp_peer.cu", "hp_dataset.cu"]
 HEADERS = ["hp_common.cuh", "hp_ptx.cuh", "hp_tc.cuh", "hp_peer.cuh", os.path.join("..", "..", "include", "handposedd.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"] + (["-DHP_CONV_TRACE"] if os.environ.get("HP_CONV_TRACE") else [])

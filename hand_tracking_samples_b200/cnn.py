@@ -187,6 +187,11 @@ class CNN:
         capi.check(self.L.hp_eval_batch_device(self.h, x_ptr, n, y_ptr,
                                                self.precision if precision is None else precision, stream))
 
+    def eval_depth_batch_device(self, depth_ptr, n, y_ptr, dec_ptr=None, depth_scale=0.001, dmin=0.1, dmax=0.7, precision=None, stream=0):
+        """handtrack.h:700-702 on device buffers: uint16 depth[n][4096] -> y[n][2304] (+ decoded[n][48])."""
+        capi.check(self.L.hp_eval_depth_batch_device(self.h, depth_ptr, n, depth_scale, dmin, dmax, y_ptr, dec_ptr,
+                                                     self.precision if precision is None else precision, stream))
+
     def train_batch_device(self, x_ptr, t_ptr, n, alpha, mse_ptr=None, precision=None, stream=0):
         capi.check(self.L.hp_train_batch_device(self.h, x_ptr, t_ptr, n, alpha, mse_ptr,
                                                 self.precision if precision is None else precision, stream))

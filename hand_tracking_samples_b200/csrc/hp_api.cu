@@ -56,7 +56,8 @@ int ensure_workspace(Net &net, int64_t n)
     Workspace &w = net.ws;
     if (n <= w.cap) return 0;
     int64_t cap = std::max<int64_t>(n, std::min<int64_t>(FP32_CHUNK, std::max<int64_t>(2 * w.cap, 64)));
-    HP_CUDA_TRY(cudaStreamSynchronize(net.stream));
+    HP_CUDA_TRY(cudaDeviceSynchronize());   // the workspace may be in use on a caller's stream
+    w.cap = 0;                              // a failed reallocation must not leave the old capacity behind
     int rc = 0;
     rc |= dev_alloc(w.p1, cap * P1_N);
     rc |= dev_alloc(w.idx1, cap * P1_N);
@@ -86,6 +87,7 @@ static int ensure_staging(Net &net, int64_t n, bool pin_in, bool pin_out)
 {
     if (n > net.stage_cap) {
         HP_CUDA_TRY(cudaDeviceSynchronize());
+        net.stage_cap = 0;   // committed again only after every allocation below has succeeded
         for (int b = 0; b < 2; b++) {
             if (dev_alloc(net.dev_in[b], n * N_IN)) return HP_ERR_CUDA;
             if (dev_alloc(net.dev_out[b], n * N_OUT)) return HP_ERR_CUDA;
@@ -103,6 +105,7 @@ static int ensure_staging(Net &net, int64_t n, bool pin_in, bool pin_out)
     }
     // pinned bounce buffers only when the caller's memory is pageable
     if (pin_in && n > net.pin_in_cap) {
+        net.pin_in_cap = 0;
         for (int b = 0; b < 2; b++) {
             if (net.pin_in[b]) cudaFreeHost(net.pin_in[b]);
             net.pin_in[b] = nullptr;
@@ -111,6 +114,7 @@ static int ensure_staging(Net &net, int64_t n, bool pin_in, bool pin_out)
         net.pin_in_cap = n;
     }
     if (pin_out && n > net.pin_out_cap) {
+        net.pin_out_cap = 0;
         for (int b = 0; b < 2; b++) {
             if (net.pin_out[b]) cudaFreeHost(net.pin_out[b]);
             net.pin_out[b] = nullptr;
@@ -261,6 +265,18 @@ static int finish_step(Net &net, float alpha, int precision, cudaStream_t s)
     return 0;
 }
 
+// An exchange kernel of the peer-memory data-parallel path gave up waiting for a rank (hp_peer.cu): the ranks' weights
+// can no longer be trusted to be in step, so training calls fail from here on instead of silently diverging.
+static int check_peer(const Net &net)
+{
+    if (const int e = peer_failed(net)) {
+        set_error("data-parallel exchange aborted: rank %d did not reach the barrier within the timeout (HP_PEER_TIMEOUT_S); "
+                  "the weights were left at their last consistent state -- shut down and re-initialise the group", e - 1);
+        return HP_ERR_PEER;
+    }
+    return 0;
+}
+
 static int check_precision(int precision)
 {
     if (precision != HP_PRECISION_FP32 && precision != HP_PRECISION_TENSOR) {
@@ -271,14 +287,17 @@ static int check_precision(int precision)
 }
 
 // forward over device buffers, chunked to the workspace
-static int eval_device(Net &net, const float *x, int64_t n, float *y, int precision, cudaStream_t s)
+// call_n: crops of the whole API call this chunk belongs to (the host pipeline feeds 2,048-crop chunks)
+static int eval_device(Net &net, const float *x, int64_t n, float *y, int precision, cudaStream_t s, int64_t call_n = -1)
 {
+    if (call_n < 0) call_n = n;
     if (precision == HP_PRECISION_TENSOR) {
         if (net.tc_dirty) {
             if (int rc = tc_refresh_weights(net, s)) return rc;
         }
         return tc_forward(net, x, n, y, s);
     }
+    net.fp32_small_call = call_n <= 64;   // one FC summation order per call, not per chunk (hp_fp32.cu, fc_small)
     for (int64_t b = 0; b < n; b += FP32_CHUNK) {
         const int64_t m = std::min<int64_t>(FP32_CHUNK, n - b);
         if (int rc = ensure_workspace(net, m)) return rc;
@@ -288,21 +307,23 @@ static int eval_device(Net &net, const float *x, int64_t n, float *y, int precis
     return 0;
 }
 
-static int grad_device(Net &net, const float *x, const float *t, int64_t n, float *mse, int precision, cudaStream_t s)
+// accumulate_first: add to the gradient sums already in the store (a batch that arrives in several host chunks)
+static int grad_device(Net &net, const float *x, const float *t, int64_t n, float *mse, int precision, cudaStream_t s, bool accumulate_first = false)
 {
     if (precision == HP_PRECISION_TENSOR) {
         for (int64_t b = 0; b < n; b += FP32_CHUNK) {
             const int64_t m = std::min<int64_t>(FP32_CHUNK, n - b);
-            if (int rc = tc_train_grad(net, x + b * N_IN, t + b * N_OUT, m, mse ? mse + b : nullptr, b > 0, s)) return rc;
+            if (int rc = tc_train_grad(net, x + b * N_IN, t + b * N_OUT, m, mse ? mse + b : nullptr, accumulate_first || b > 0, s)) return rc;
         }
         net.last_n = std::min<int64_t>(n, FP32_CHUNK);
         return 0;
     }
+    net.fp32_small_call = n <= 64 && !accumulate_first;
     for (int64_t b = 0; b < n; b += FP32_CHUNK) {
         const int64_t m = std::min<int64_t>(FP32_CHUNK, n - b);
         if (int rc = ensure_workspace(net, m)) return rc;
         if (int rc = fp32_forward(net, x + b * N_IN, m, nullptr, true, s)) return rc;
-        if (int rc = fp32_backward(net, x + b * N_IN, t + b * N_OUT, m, mse ? mse + b : nullptr, b > 0, s)) return rc;
+        if (int rc = fp32_backward(net, x + b * N_IN, t + b * N_OUT, m, mse ? mse + b : nullptr, accumulate_first || b > 0, s)) return rc;
     }
     net.last_n = std::min<int64_t>(n, FP32_CHUNK);
     return 0;
@@ -358,17 +379,8 @@ static bool is_handposedd(const hp_layer_desc *L, int n)
     return true;
 }
 
-extern "C" {
-
-int hp_create_handposedd(int device, hp_net **out)
+static int create_resources(Net &n)
 {
-    if (!out) { set_error("out is NULL"); return HP_ERR_INVALID; }
-    *out = nullptr;
-    if (int rc = check_device(device)) return rc;
-    HP_CUDA_TRY(cudaSetDevice(device));
-    hp_net *h = new hp_net;
-    Net &n = h->n;
-    n.device = device;
     HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.stream, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;   // NCCL's CTAs must win SM slots against the compute kernels as soon as any CTA retires
@@ -396,6 +408,28 @@ int hp_create_handposedd(int device, hp_net **out)
     HP_CUDA_TRY(cudaMemset(n.grads, 0, (size_t)N_PARAMS * sizeof(float)));
     if (int rc = fp32_init_attributes()) return rc;
     if (int rc = tc_init(n)) return rc;
+    return HP_OK;
+}
+
+
+extern "C" {
+
+int hp_create_handposedd(int device, hp_net **out)
+{
+    if (!out) { set_error("out is NULL"); return HP_ERR_INVALID; }
+    *out = nullptr;
+    if (int rc = check_device(device)) return rc;
+    HP_CUDA_TRY(cudaSetDevice(device));
+    hp_net *h = new hp_net;
+    h->n.device = device;
+    const int rc = create_resources(h->n);
+    if (rc) {   // release whatever was created before the failure (hp_destroy tolerates a half-built net)
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        hp_destroy(h);
+        memcpy(g_err, keep, sizeof keep);
+        return rc;
+    }
     *out = h;
     return HP_OK;
 }
@@ -482,7 +516,8 @@ int hp_load_cnnb(hp_net *net, const void *bytes, size_t n_bytes)
     // like loadvb's istream::read (cnn.h:97) a short stream fills a prefix; a float torn by
     // the end of the stream is dropped here rather than half-written
     take -= take % sizeof(float);
-    HP_CUDA_TRY(cudaStreamSynchronize(n.stream));
+    // the *_device entry points run on caller streams and side streams that a legacy-stream memcpy does not order against
+    HP_CUDA_TRY(cudaDeviceSynchronize());
     if (take) HP_CUDA_TRY(cudaMemcpy(n.params, bytes, take, cudaMemcpyHostToDevice));
     n.tc_dirty = true;
     return HP_OK;
@@ -495,6 +530,7 @@ int hp_save_cnnb(const hp_net *net, void *bytes, size_t capacity, size_t *n_writ
     const Net &n = net->n;
     HP_CUDA_TRY(cudaSetDevice(n.device));
     HP_CUDA_TRY(cudaDeviceSynchronize());
+    if (int rc = check_peer(n)) return rc;
     HP_CUDA_TRY(cudaMemcpy(bytes, n.params, (size_t)HP_CNNB_BYTES, cudaMemcpyDeviceToHost));
     if (n_written) *n_written = (size_t)HP_CNNB_BYTES;
     return HP_OK;
@@ -575,11 +611,18 @@ static int eval_host_pipeline(Net &N, const void *x, int elem, const DepthNorm *
         HP_CUDA_TRY(cudaEventRecord(N.ev_in[b], h2d));
         HP_CUDA_TRY(cudaStreamWaitEvent(s, N.ev_in[b], 0));
         const float *xin = N.dev_in[b];
-        if (norm) {
-            if (int rc = post_normalize_depth(N, (const uint16_t *)N.dev_in[b], m, norm->scale, norm->dmin, norm->dmax, N.dev_norm[b], s)) return rc;
-            xin = N.dev_norm[b];
+        if (norm && precision == HP_PRECISION_TENSOR && !N.tc->conv_v1) {
+            // tensor path: the 16-bit depth goes straight into the conv kernel, which normalises in its loader
+            if (N.tc_dirty)
+                if (int rc = tc_refresh_weights(N, s)) return rc;
+            if (int rc = tc_forward_u16(N, (const uint16_t *)N.dev_in[b], norm->scale, norm->dmin, norm->dmax, m, N.dev_out[b], s)) return rc;
+        } else {
+            if (norm) {
+                if (int rc = post_normalize_depth(N, (const uint16_t *)N.dev_in[b], m, norm->scale, norm->dmin, norm->dmax, N.dev_norm[b], s)) return rc;
+                xin = N.dev_norm[b];
+            }
+            if (int rc = eval_device(N, xin, m, N.dev_out[b], precision, s, n)) return rc;
         }
-        if (int rc = eval_device(N, xin, m, N.dev_out[b], precision, s)) return rc;
         if (dec)
             if (int rc = post_decode(N, N.dev_out[b], m, N.dev_dec[b], s)) return rc;
         HP_CUDA_TRY(cudaEventRecord(N.ev_comp[b], s));
@@ -628,6 +671,33 @@ int hp_eval_depth_batch(hp_net *net, const uint16_t *depth, int64_t n, float dep
     return eval_host_pipeline(net->n, depth, 2, &nm, n, y, decoded, precision);
 }
 
+int hp_eval_depth_batch_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax, float *y_dev,
+                               float *decoded_dev, int precision, void *stream)
+{
+    if (!net || n < 0 || (n && (!depth_dev || !y_dev)) || !(dmax > dmin)) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == HP_PRECISION_TENSOR && !N.tc->conv_v1) {
+        if (N.tc_dirty)
+            if (int rc = tc_refresh_weights(N, s)) return rc;
+        if (int rc = tc_forward_u16(N, depth_dev, depth_scale, dmin, dmax, n, y_dev, s)) return rc;
+    } else {
+        // FP32 path: normalise chunk by chunk into the staging buffer (bit-identical values), then Eval
+        for (int64_t b = 0; b < n; b += STAGE_CHUNK) {
+            const int64_t m = std::min<int64_t>(STAGE_CHUNK, n - b);
+            if (int rc = ensure_staging(N, m, false, false)) return rc;
+            if (int rc = post_normalize_depth(N, depth_dev + b * N_IN, m, depth_scale, dmin, dmax, N.dev_norm[0], s)) return rc;
+            if (int rc = eval_device(N, N.dev_norm[0], m, y_dev + b * N_OUT, precision, s, n)) return rc;
+        }
+    }
+    if (decoded_dev)
+        if (int rc = post_decode(N, y_dev, n, decoded_dev, s)) return rc;
+    return HP_OK;
+}
+
 int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax, float *x_dev, void *stream)
 {
     if (!net || n < 0 || (n && (!depth_dev || !x_dev)) || !(dmax > dmin)) { set_error("bad argument"); return HP_ERR_INVALID; }
@@ -660,15 +730,22 @@ int hp_train_batch_points(hp_net *net, const float *x, const float *points, cons
     if (n == 0) return HP_OK;
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
-    if (int rc = ensure_staging(N, n, false, false)) return rc;
+    if (int rc = check_peer(N)) return rc;
+    const int64_t chunk = std::min<int64_t>(n, STAGE_CHUNK);
+    if (int rc = ensure_staging(N, chunk, false, false)) return rc;
     cudaStream_t s = N.stream;
-    float *dpts = N.dev_dec[0], *dvals = N.dev_dec[1];   // [n][48] scratch each: room for 16 floats per sample
-    HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[0], x, (size_t)n * N_IN * sizeof(float), cudaMemcpyHostToDevice, s));
-    HP_CUDA_TRY(cudaMemcpyAsync(dpts, points, (size_t)n * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
-    HP_CUDA_TRY(cudaMemcpyAsync(dvals, vals, (size_t)n * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (int rc = post_render_labels(N, dpts, dvals, n, N.dev_t, s)) return rc;
-    if (int rc = hp_train_batch_device(net, N.dev_in[0], N.dev_t, n, alpha, N.dev_mse, precision, s)) return rc;
-    if (mse_out) HP_CUDA_TRY(cudaMemcpyAsync(mse_out, N.dev_mse, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    float *dpts = N.dev_dec[0], *dvals = N.dev_dec[1];   // [chunk][48] scratch each: room for 16 floats per sample
+    HP_CUDA_TRY(cudaEventRecord(N.ev_start, s));
+    for (int64_t b = 0; b < n; b += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, n - b);
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[0], x + b * N_IN, (size_t)m * N_IN * sizeof(float), cudaMemcpyHostToDevice, s));
+        HP_CUDA_TRY(cudaMemcpyAsync(dpts, points + b * 16, (size_t)m * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
+        HP_CUDA_TRY(cudaMemcpyAsync(dvals, vals + b * 16, (size_t)m * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (int rc = post_render_labels(N, dpts, dvals, m, N.dev_t, s)) return rc;
+        if (int rc = grad_device(N, N.dev_in[0], N.dev_t, m, N.dev_mse, precision, s, b > 0)) return rc;
+        if (mse_out) HP_CUDA_TRY(cudaMemcpyAsync(mse_out + b, N.dev_mse, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (int rc = finish_step(N, alpha, precision, s)) return rc;
     HP_CUDA_TRY(cudaStreamSynchronize(s));
     return HP_OK;
 }
@@ -731,6 +808,7 @@ int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, i
     if (n == 0) return HP_OK;
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
+    if (int rc = check_peer(N)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     HP_CUDA_TRY(cudaEventRecord(N.ev_start, s));
     if (int rc = grad_device(N, x_dev, t_dev, n, mse_dev, precision, s)) return rc;
@@ -744,12 +822,21 @@ int hp_train_batch(hp_net *net, const float *x, const float *t, int64_t n, float
     if (n == 0) return HP_OK;
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
-    if (int rc = ensure_staging(N, n, false, false)) return rc;
+    if (int rc = check_peer(N)) return rc;
+    // the batch travels in chunks of at most STAGE_CHUNK samples (bounded staging); the gradient sums accumulate
+    // across chunks at frozen weights and ONE update follows
+    const int64_t chunk = std::min<int64_t>(n, STAGE_CHUNK);
+    if (int rc = ensure_staging(N, chunk, false, false)) return rc;
     cudaStream_t s = N.stream;
-    HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[0], x, (size_t)n * N_IN * sizeof(float), cudaMemcpyHostToDevice, s));
-    HP_CUDA_TRY(cudaMemcpyAsync(N.dev_t, t, (size_t)n * N_OUT * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (int rc = hp_train_batch_device(net, N.dev_in[0], N.dev_t, n, alpha, N.dev_mse, precision, s)) return rc;
-    if (mse_out) HP_CUDA_TRY(cudaMemcpyAsync(mse_out, N.dev_mse, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HP_CUDA_TRY(cudaEventRecord(N.ev_start, s));
+    for (int64_t b = 0; b < n; b += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, n - b);
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_in[0], x + b * N_IN, (size_t)m * N_IN * sizeof(float), cudaMemcpyHostToDevice, s));
+        HP_CUDA_TRY(cudaMemcpyAsync(N.dev_t, t + b * N_OUT, (size_t)m * N_OUT * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (int rc = grad_device(N, N.dev_in[0], N.dev_t, m, N.dev_mse, precision, s, b > 0)) return rc;
+        if (mse_out) HP_CUDA_TRY(cudaMemcpyAsync(mse_out + b, N.dev_mse, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (int rc = finish_step(N, alpha, precision, s)) return rc;
     HP_CUDA_TRY(cudaStreamSynchronize(s));
     return HP_OK;
 }

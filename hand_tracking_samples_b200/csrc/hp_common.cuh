@@ -102,6 +102,7 @@ int post_decode(Net &net, const float *y, int64_t n, float *out, cudaStream_t s)
 int post_render_labels(Net &net, const float *points, const float *vals, int64_t n, float *t, cudaStream_t s);
 // ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);
+int tc_forward_u16(Net &net, const uint16_t *depth, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, cudaStream_t s);
 int tc_refresh_weights(Net &net, cudaStream_t s);
 int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s);   // 0: fc2 shadows, 1: fc1 shadows, 2: conv images
 int tc_init(Net &net);
@@ -121,6 +122,7 @@ struct Net {
     Workspace ws;
     TcState *tc = nullptr;
     bool tc_dirty = true;                 // bf16 shadows stale w.r.t. params
+    bool fp32_small_call = true;          // FP32 path: the current call holds <= 64 crops in total (split-K FC kernels allowed)
     // pinned staging for HOST entry points
     float *pin_in[2] = {nullptr, nullptr};
     float *pin_out[2] = {nullptr, nullptr};

@@ -736,6 +736,10 @@ __global__ void __launch_bounds__(256) bias_reduce_act(const float *__restrict__
 
 // LFull::forward for a handful of crops (the reference's own use: one Eval per camera frame): the layer is a
 // stream of 18.9 MB of weights, so K is split 8 ways over the grid to get every SM pulling on HBM.
+// Summation order: 8 partial sums of ascending k, then bias + partials in order -- differs in the last bits from the
+// single ascending-k pass of the large-batch GEMM (both are within 1e-6 of the reference's order).  The choice is made
+// per CALL (Net::fp32_small_call: whole call <= 64 crops), never per workspace chunk, so within one call every crop
+// gets the same arithmetic wherever it sits in the batch (tests: ragged sizes across 63/64/65 and 2048+3).
 constexpr int SMALL_BATCH = 64, SMALL_SPLITS = 8;
 template <bool TANH>
 static int fc_small(Net &net, const float *x, int M, int K, const float *W, const float *bias, int N, float *out, cudaStream_t s)
@@ -778,7 +782,7 @@ int fp32_forward(Net &net, const float *x, int64_t n, float *y_out, bool trainin
         StageTimer st(net, 0, s);
         if (int rc = fp32_conv_stage(net, x, n, nullptr, s)) return rc;
     }
-    if (n <= SMALL_BATCH) {
+    if (n <= SMALL_BATCH && net.fp32_small_call) {
         {
             StageTimer st(net, 1, s);
             if (int rc = fc_small<true>(net, w.p2, (int)n, FC1_IN, P + OFF_F1W, P + OFF_F1B, FC1_OUT, w.h1, s)) return rc;
@@ -912,7 +916,7 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, 1, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
-    if (n <= SMALL_BATCH) {
+    if (n <= SMALL_BATCH && net.fp32_small_call) {
         if (int rc = fc_dx_small(net, w.dlog, (int)n, FC2_OUT, P + OFF_F2W, FC2_IN, w.h1, w.da1, s)) return rc;
     } else {
         GemmArgs g{(int)n, FC2_IN, FC2_OUT, w.dlog, FC2_OUT, P + OFF_F2W, FC2_OUT, w.da1, FC2_IN, nullptr, w.h1, FC2_OUT, 0};
@@ -926,7 +930,7 @@ int fp32_backward(Net &net, const float *x, const float *t, int64_t n, float *ms
         if (int rc = launch_sgemm<128, false, false, EPI_STORE>(net, g, 1, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
-    if (n <= SMALL_BATCH) {
+    if (n <= SMALL_BATCH && net.fp32_small_call) {
         if (int rc = fc_dx_small(net, w.da1, (int)n, FC1_OUT, P + OFF_F1W, FC1_IN, w.p2, w.g2, s)) return rc;
     } else {
         GemmArgs g{(int)n, FC1_IN, FC1_OUT, w.da1, FC1_OUT, P + OFF_F1W, FC1_OUT, w.g2, FC1_IN, nullptr, w.p2, FC1_OUT, 0};

@@ -17,8 +17,14 @@
 // Barriers: flags[b][p] on rank r is written only by CTA b of rank p and holds the last epoch that CTA reached;
 // epochs increase monotonically (2 per launch), so no reset and no double buffering.  A CTA spins only on remote
 // CTAs of the same kernel launch, which become resident as soon as their own rank's stream reaches the launch: no
-// CTA waits on a CTA of its own grid, hence no co-residency requirement.  A spin longer than PEER_TIMEOUT_NS sets an
-// error word (read by hp_dp_peer_status) instead of hanging the GPU.
+// CTA waits on a CTA of its own grid, hence no co-residency requirement.
+//
+// Failure handling: a spin longer than the timeout (HP_PEER_TIMEOUT_S, default 30 s) ABORTS the exchange instead of
+// hanging the GPU or carrying on with incomplete sums: the CTA latches the sticky error word (device + mapped host
+// copy), overwrites its own flags on every rank with PEER_POISON so that a peer arriving late aborts too instead of
+// passing the barrier on stale epochs, and the kernel returns before the reduce / update / store phases -- the master
+// weights are left untouched.  Every later exchange kernel of the rank is a no-op, and the next hp_train_batch* /
+// hp_save_cnnb call on the host returns HP_ERR_PEER.
 #include "hp_common.cuh"
 #include "hp_peer.cuh"
 
@@ -30,7 +36,7 @@ namespace hp {
         HP_CUDA_TRY(cudaGetLastError());                    \
     } while (0)
 
-constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;  // 4 s
+constexpr unsigned long long PEER_TIMEOUT_DEFAULT_NS = 30000000000ull;  // 30 s
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
 {
@@ -51,24 +57,36 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 
 // All CTAs with this blockIdx on all ranks meet here.  Everything the CTA's threads wrote before the call is
 // visible to the peers' CTAs after they return (bar.sync, then a system-scope release by the signalling threads).
+// Returns false (CTA-uniform) when the exchange must be abandoned: a peer did not arrive in time, a peer gave up
+// (poisoned flag), or this rank's error word is already set.
 template <int WORLD>
-__device__ __forceinline__ void peer_barrier(const PeerPtrs &P, int rank, uint32_t epoch)
+__device__ __forceinline__ bool peer_barrier(const PeerPtrs &P, int rank, uint32_t epoch)
 {
     __syncthreads();
+    int bad = 0;
     if (threadIdx.x < WORLD) {
         const int p = threadIdx.x;
         __threadfence_system();
-        st_release_sys(P.flags[p] + blockIdx.x * PEER_MAX_WORLD + rank, epoch);
-        const uint32_t *mine = P.flags[rank] + blockIdx.x * PEER_MAX_WORLD + p;
-        const unsigned long long t0 = globaltimer_ns();
-        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-            if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) {
-                atomicExch(P.error, 1u + (uint32_t)p);
-                break;
+        if (*reinterpret_cast<volatile uint32_t *>(P.error) != 0) bad = 1;   // sticky: an earlier exchange of this rank failed
+        if (!bad) {
+            st_release_sys(P.flags[p] + blockIdx.x * PEER_MAX_WORLD + rank, epoch);
+            const uint32_t *mine = P.flags[rank] + blockIdx.x * PEER_MAX_WORLD + p;
+            const unsigned long long t0 = globaltimer_ns();
+            for (;;) {
+                const uint32_t v = ld_acquire_sys(mine);
+                if (v == PEER_POISON) { bad = 1; break; }
+                if ((int32_t)(v - epoch) >= 0) break;
+                if (globaltimer_ns() - t0 > P.timeout_ns) { bad = 1; break; }
             }
         }
+        if (bad) {
+            atomicCAS(P.error, 0u, 1u + (uint32_t)p);
+            *P.error_host = 1u + (uint32_t)p;
+            for (int q = 0; q < WORLD; q++) st_release_sys(P.flags[q] + blockIdx.x * PEER_MAX_WORLD + rank, PEER_POISON);
+            __threadfence_system();
+        }
     }
-    __syncthreads();
+    return __syncthreads_or(bad) == 0;
 }
 
 __device__ __forceinline__ float4 ld_peer(const float4 *p)
@@ -87,7 +105,7 @@ __device__ __forceinline__ float4 ld_peer(const float4 *p)
 template <int WORLD, int U>
 __global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_kernel(PeerPtrs P, int rank, int off, int count4, float alpha, uint32_t epoch)
 {
-    peer_barrier<WORLD>(P, rank, epoch + 1);
+    if (!peer_barrier<WORLD>(P, rank, epoch + 1)) return;   // incomplete sums: leave the weights alone
     const int lo = (int)((int64_t)count4 * rank / WORLD), hi = (int)((int64_t)count4 * (rank + 1) / WORLD);
     const int stride = gridDim.x * PEER_THREADS;
     for (int base = lo + blockIdx.x * PEER_THREADS + threadIdx.x; base < hi; base += stride * U) {
@@ -134,7 +152,7 @@ __global__ void __launch_bounds__(PEER_THREADS, 1) peer_small_kernel(PeerPtrs P,
 #pragma unroll
         for (int p = 0; p < WORLD; p++) reinterpret_cast<float4 *>(P.inbox[p])[((size_t)parity * PEER_MAX_WORLD + rank) * slot + i] = g;
     }
-    peer_barrier<WORLD>(P, rank, epoch + 1);
+    if (!peer_barrier<WORLD>(P, rank, epoch + 1)) return;
     for (int i = lo + threadIdx.x; i < hi; i += PEER_THREADS) {
         const float4 *in = reinterpret_cast<const float4 *>(P.inbox[rank]) + (size_t)parity * PEER_MAX_WORLD * slot + i;
         float4 s = ld_peer(in);
@@ -195,6 +213,8 @@ int peer_export(Net &net, void *out)
         HP_CUDA_TRY(cudaMemset(ps->my_flags, 0, PEER_FLAG_WORDS * sizeof(uint32_t)));
         HP_CUDA_TRY(cudaMalloc((void **)&ps->my_inbox, PEER_INBOX_FLOATS * sizeof(float)));
         HP_CUDA_TRY(cudaMemset(ps->my_inbox, 0, PEER_INBOX_FLOATS * sizeof(float)));
+        HP_CUDA_TRY(cudaHostAlloc((void **)&ps->host_err, sizeof(uint32_t), cudaHostAllocMapped));
+        *ps->host_err = 0;
         HP_CUDA_TRY(cudaDeviceSynchronize());
         net.peer = ps;
     }
@@ -236,6 +256,16 @@ int peer_init(Net &net, const void *handles, int rank, int world, int reserved_s
         ps->ptrs.inbox[p] = (float *)m[3];
     }
     ps->ptrs.error = ps->my_flags + PEER_MAX_BLOCKS * PEER_MAX_WORLD;
+    {
+        uint32_t *dptr = nullptr;
+        HP_CUDA_TRY(cudaHostGetDevicePointer((void **)&dptr, ps->host_err, 0));
+        ps->ptrs.error_host = dptr;
+    }
+    ps->ptrs.timeout_ns = PEER_TIMEOUT_DEFAULT_NS;
+    if (const char *e = getenv("HP_PEER_TIMEOUT_S")) {
+        const double sec = atof(e);
+        if (sec > 0) ps->ptrs.timeout_ns = (unsigned long long)(sec * 1e9);
+    }
     ps->max_blocks = reserved_sms > 0 ? (reserved_sms < PEER_MAX_BLOCKS ? reserved_sms : PEER_MAX_BLOCKS) : 16;
     if (const char *e = getenv("HP_PEER_BLOCKS")) {
         int b = atoi(e);
@@ -245,6 +275,12 @@ int peer_init(Net &net, const void *handles, int rank, int world, int reserved_s
     ps->small_steps = 0;
     ps->ready = true;
     return 0;
+}
+
+// host-visible latch, no device sync: non-zero once any exchange kernel of this rank has given up
+int peer_failed(const Net &net)
+{
+    return (net.peer && net.peer->host_err) ? (int)*reinterpret_cast<volatile uint32_t *>(net.peer->host_err) : 0;
 }
 
 int peer_status(Net &net, int *err)
@@ -265,6 +301,7 @@ void peer_shutdown(Net &net)
     for (int i = 0; i < ps->n_mapped; i++) cudaIpcCloseMemHandle(ps->mapped[i]);
     if (ps->my_flags) cudaFree(ps->my_flags);
     if (ps->my_inbox) cudaFree(ps->my_inbox);
+    if (ps->host_err) cudaFreeHost(ps->host_err);
     delete ps;
     net.peer = nullptr;
 }

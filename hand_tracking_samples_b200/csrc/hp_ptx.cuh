@@ -145,6 +145,25 @@ __device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t adesc, uint
             "l"(adesc), "l"(bdesc), "r"(idesc)
             : "memory");
 }
+// A operand in tensor memory (row m of A in lane m, two 16-bit K values per 32-bit column), B in shared memory
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc)
+{
+    if (ACC)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(bdesc), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(bdesc), "r"(idesc)
+            : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -194,6 +213,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: this warp's 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors --------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 64 bf16
@@ -229,6 +256,12 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
 {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with A = B = IEEE half (format code 0): 10 mantissa bits instead of 7 at the same tensor rate.  Every forward
+// operand of this net is a tanh output, a [0,1] depth value or a weight, all far inside the fp16 range.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

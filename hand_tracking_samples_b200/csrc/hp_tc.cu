@@ -40,14 +40,14 @@ constexpr int STG_BYTES = 4096;                 // per-warp output staging tile:
 constexpr int GEMM_THREADS = 256;
 constexpr int gemm_smem(int bn) { return STAGES * (A_BYTES + bn * BK * 2) + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
 
-enum { TC_EPI_TANH_BF16 = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3, TC_EPI_STORE_BF16 = 4 };
+enum { TC_EPI_TANH_ACT = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3, TC_EPI_STORE_BF16 = 4 };
 enum { TC_FLAG_ACCUMULATE = 1, TC_FLAG_ROWS_HWC_TO_CHW = 2 };
 
 struct EpiArgs {
-    const float *bias;         // TANH_BF16 / SOFTMAX_F32
-    void *out;                 // TANH_BF16 / STORE_BF16: bf16 [M][N]; SOFTMAX_F32 / STORE_F32 / DTANH: fp32 [M][N] (DTANH: may be null)
+    const float *bias;         // TANH_ACT / SOFTMAX_F32 / STORE_F32 (optional)
+    void *out;                 // TANH_ACT: fp16 [M][N]; STORE_BF16: bf16 [M][N]; SOFTMAX_F32 / STORE_F32 / DTANH: fp32 [M][N] (DTANH: may be null)
     __nv_bfloat16 *out2;       // DTANH: bf16 [M][N]
-    const __nv_bfloat16 *H;    // DTANH: layer output h, bf16 [M][N]: result = (1 - h*h) * acc  (TanH::df, cnn.h:32,467)
+    const act_t *H;            // DTANH: layer output h, fp16 [M][N]: result = (1 - h*h) * acc  (TanH::df, cnn.h:32,467)
     int flags;                 // STORE_F32: TC_FLAG_ACCUMULATE (out += acc), TC_FLAG_ROWS_HWC_TO_CHW (row k' -> (k'&63)*36 + (k'>>6))
     int ksplit;                // STORE_F32 only, 0/1 = off: K is cut into ksplit ranges of whole 64-blocks, every (range, tile) pair is a
                                // work item and range r stores its partial product at out + r*M*N (long-K, small-output weight gradients)
@@ -72,14 +72,14 @@ static int bind_driver()
     return 0;
 }
 
-// 2-D bf16 row-major [rows][cols] tensor, box = box_rows x 64 columns, 128B swizzle.
-static int make_map_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+// 2-D 16-bit row-major [rows][cols] tensor, box = box_rows x 64 columns, 128B swizzle.
+static int make_map_16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMapDataType dt)
 {
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};
     cuuint32_t box[2] = {64, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = g_encode(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -88,26 +88,20 @@ static int make_map_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64
     }
     return 0;
 }
-
-// fast transcendental forms for the tensor path (its bound is 1e-2, bf16 operands dominate the error)
-__device__ __forceinline__ float tanh_fast(float x)
+static int make_map_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
 {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+    return make_map_16(m, base, rows, cols, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
-
-__device__ __forceinline__ float ex2_fast(float x)
+static int make_map_f16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
 {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+    return make_map_16(m, base, rows, cols, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
 }
 
 // ============================================================================
 // C[M x N] = A[M x K] * Bt[N x K]^T  (+ fused epilogue); A, Bt bf16 K-major via TMA.
 // ============================================================================
-template <int EPI, int BN>
+// OPS_F16: both operands are IEEE half (forward GEMMs); otherwise bf16 (backward GEMMs).
+template <int EPI, int BN, bool OPS_F16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs ea, int M, int N, int K)
 {
@@ -176,7 +170,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = OPS_F16 ? ptx::make_idesc_f16(BM, BN) : ptx::make_idesc_bf16(BM, BN);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -258,7 +252,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             };
-            if (EPI == TC_EPI_TANH_BF16 || EPI == TC_EPI_STORE_BF16) {   // STORE_BF16: the plain product, rounded once
+            if (EPI == TC_EPI_TANH_ACT || EPI == TC_EPI_STORE_BF16) {   // STORE_BF16: the plain product, rounded once
                 uint8_t *gtile = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 2;
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; c++) {   // 64 columns = 128 B of bf16 per row
@@ -272,13 +266,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
                             float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
-                            if (EPI == TC_EPI_TANH_BF16) {
+                            if (EPI == TC_EPI_TANH_ACT) {
                                 const float2 bv = *reinterpret_cast<const float2 *>(bptr + c * 64 + h * 32 + j);
-                                v0 = tanh_fast(v0 + bv.x);
-                                v1 = tanh_fast(v1 + bv.y);
+                                packed[j >> 1] = pack_act(tanh_tc(v0 + bv.x), tanh_tc(v1 + bv.y));
+                            } else {
+                                __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+                                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
                             }
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-                            packed[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
                         }
 #pragma unroll
                         for (int q = 0; q < 4; q++) v[h * 4 + q] = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
@@ -357,7 +351,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (EPI == TC_EPI_DTANH) {
                 const int row = m_blk * BM + ew * 32 + lane;
                 const int rowc = row < M ? row : M - 1;   // clamp: rows past M are computed but never stored
-                const __nv_bfloat16 *hrow = ea.H + (size_t)rowc * N + n_blk * BN;
+                const act_t *hrow = ea.H + (size_t)rowc * N + n_blk * BN;
                 uint8_t *gt32 = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 4;
                 uint8_t *gt16 = reinterpret_cast<uint8_t *>(ea.out2) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 2;
                 int fb = 0;
@@ -376,7 +370,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
-                                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&hw[k]));
+                                const float2 hf = unpack_act(hw[k]);
                                 v[q * 8 + 2 * k] = (1.0f - hf.x * hf.x) * __uint_as_float(r[q * 8 + 2 * k]);
                                 v[q * 8 + 2 * k + 1] = (1.0f - hf.y * hf.y) * __uint_as_float(r[q * 8 + 2 * k + 1]);
                             }
@@ -417,11 +411,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-// fp32 W[K][N] (row-major, the .cnnb layout of LFull, cnn.h:417) -> bf16 Wt[N][K]
+// fp32 W[K][N] (row-major, the .cnnb layout of LFull, cnn.h:417) -> fp16 Wt[N][K] (forward B operand)
 // HWC: destination k' = pp*64 + co reads source row co*36 + pp (the conv kernel emits its features
 // pixel-major, the reference flattens channel-major: x + 6y + 36c).
 template <bool HWC>
-__global__ void __launch_bounds__(256) transpose_to_bf16(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wt, int K, int N)
+__global__ void __launch_bounds__(256) transpose_to_act(const float *__restrict__ w, act_t *__restrict__ wt, int K, int N)
 {
     __shared__ float tile[32][33];
     const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -434,7 +428,7 @@ __global__ void __launch_bounds__(256) transpose_to_bf16(const float *__restrict
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; i++) wt[(size_t)(n0 + ty + 8 * i) * K + k0 + tx] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    for (int i = 0; i < 4; i++) wt[(size_t)(n0 + ty + 8 * i) * K + k0 + tx] = __float2half_rn(tile[tx][ty + 8 * i]);
 }
 
 
@@ -454,13 +448,14 @@ __global__ void __launch_bounds__(256) convert_rows_bf16(const float *__restrict
     }
 }
 
-// bf16 src[n][C] -> dst[C][ldk] (k contiguous) with zero fill for n <= k < n_pad: the K-major operands of the
+// 16-bit src[n][C] -> bf16 dst[C][ldk] (k contiguous) with zero fill for n <= k < n_pad: the K-major operands of the
 // weight-gradient GEMMs (LFull::update, cnn.h:438-445, is the contraction over the batch).  Both operands of one GEMM
 // are transposed by one launch (blockIdx.z picks the job).
 struct TransposeJob {
-    const __nv_bfloat16 *src;
+    const void *src;           // 16-bit [n][C]
     __nv_bfloat16 *dst;
     int C;
+    int src_f16;               // source is fp16 (forward activations h1, p2): converted to bf16 on the way
 };
 __global__ void __launch_bounds__(256) transpose_bf16_pair(TransposeJob j0, TransposeJob j1, int n, int n_pad, int ldk)
 {
@@ -472,7 +467,12 @@ __global__ void __launch_bounds__(256) transpose_bf16_pair(TransposeJob j0, Tran
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int k = k0 + ty + 8 * i;
-        tile[ty + 8 * i][tx] = (k < n) ? j.src[(size_t)k * j.C + c0 + tx] : __float2bfloat16_rn(0.f);
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (k < n) {
+            if (j.src_f16) v = __float2bfloat16_rn(__half2float(reinterpret_cast<const __half *>(j.src)[(size_t)k * j.C + c0 + tx]));
+            else v = reinterpret_cast<const __nv_bfloat16 *>(j.src)[(size_t)k * j.C + c0 + tx];
+        }
+        tile[ty + 8 * i][tx] = v;
     }
     __syncthreads();
 #pragma unroll
@@ -698,19 +698,23 @@ int tc_init(Net &net)
     }
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1t, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2t, (size_t)FC2_OUT * FC2_IN * 2));
-    if (int rc = make_map_bf16(&t->tm_w1t, t->w1t, FC1_OUT, FC1_IN, 256)) return rc;
-    if (int rc = make_map_bf16(&t->tm_w2t, t->w2t, FC2_OUT, FC2_IN, 256)) return rc;
-    if (int rc = make_map_bf16(&t->tm_w1t64, t->w1t, FC1_OUT, FC1_IN, 64)) return rc;
-    if (int rc = make_map_bf16(&t->tm_w2t64, t->w2t, FC2_OUT, FC2_IN, 64)) return rc;
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_SOFTMAX_F32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TANH_BF16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_F32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(128)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_STORE_BF16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(256)));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_DTANH, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(64)));
+    if (int rc = make_map_f16(&t->tm_w1t, t->w1t, FC1_OUT, FC1_IN, 256)) return rc;
+    if (int rc = make_map_f16(&t->tm_w2t, t->w2t, FC2_OUT, FC2_IN, 256)) return rc;
+    if (int rc = make_map_f16(&t->tm_w1t64, t->w1t, FC1_OUT, FC1_IN, 64)) return rc;
+    if (int rc = make_map_f16(&t->tm_w2t64, t->w2t, FC2_OUT, FC2_IN, 64)) return rc;
+#define HP_GEMM_ATTR(EPI, BN, F16) \
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(BN)))
+    HP_GEMM_ATTR(TC_EPI_TANH_ACT, 256, true);
+    HP_GEMM_ATTR(TC_EPI_TANH_ACT, 64, true);
+    HP_GEMM_ATTR(TC_EPI_SOFTMAX_F32, 256, true);
+    HP_GEMM_ATTR(TC_EPI_STORE_F32, 64, true);      // fc2 logits at small batch
+    HP_GEMM_ATTR(TC_EPI_STORE_F32, 256, false);    // weight gradients
+    HP_GEMM_ATTR(TC_EPI_STORE_F32, 128, false);
+    HP_GEMM_ATTR(TC_EPI_STORE_F32, 64, false);
+    HP_GEMM_ATTR(TC_EPI_DTANH, 256, false);
+    HP_GEMM_ATTR(TC_EPI_DTANH, 64, false);
+    HP_GEMM_ATTR(TC_EPI_STORE_BF16, 256, false);
+#undef HP_GEMM_ATTR
     HP_CUDA_TRY(cudaMalloc((void **)&t->w1b, (size_t)FC1_OUT * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->w2b, (size_t)FC2_OUT * FC2_IN * 2));
     if (int rc = make_map_bf16(&t->tm_w1b, t->w1b, FC1_IN, FC1_OUT, 256)) return rc;
@@ -733,6 +737,7 @@ void tc_destroy(Net &net)
         if (q) cudaFree(q);
     if (t->b1_img) cudaFree(t->b1_img);
     if (t->b2_img) cudaFree(t->b2_img);
+    if (t->a2_img) cudaFree(t->a2_img);
     if (t->p2) cudaFree(t->p2);
     if (t->h1) cudaFree(t->h1);
     delete t;
@@ -744,12 +749,12 @@ int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s)
 {
     TcState *t = net.tc;
     if (bucket == 0) {
-        transpose_to_bf16<false><<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, t->w2t, FC2_IN, FC2_OUT);
+        transpose_to_act<false><<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, t->w2t, FC2_IN, FC2_OUT);
         LAUNCH_CHECK(net);
         convert_rows_bf16<false><<<FC2_IN, 256, 0, s>>>(net.params + OFF_F2W, t->w2b, FC2_OUT);
         LAUNCH_CHECK(net);
     } else if (bucket == 1) {
-        transpose_to_bf16<true><<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, t->w1t, FC1_IN, FC1_OUT);
+        transpose_to_act<true><<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, t->w1t, FC1_IN, FC1_OUT);
         LAUNCH_CHECK(net);
         convert_rows_bf16<true><<<FC1_IN, 256, 0, s>>>(net.params + OFF_F1W, t->w1b, FC1_OUT);
         LAUNCH_CHECK(net);
@@ -781,22 +786,24 @@ static int tc_ensure(Net &net, int64_t n)
     // rows past n are never stored by the epilogues, but they are loaded by TMA: keep them finite
     HP_CUDA_TRY(cudaMemset(t->p2, 0, (size_t)cap * FC1_IN * 2));
     HP_CUDA_TRY(cudaMemset(t->h1, 0, (size_t)cap * FC1_OUT * 2));
-    if (int rc = make_map_bf16(&t->tm_p2, t->p2, cap, FC1_IN, BM)) return rc;
-    if (int rc = make_map_bf16(&t->tm_h1, t->h1, cap, FC1_OUT, BM)) return rc;
+    if (int rc = make_map_f16(&t->tm_p2, t->p2, cap, FC1_IN, BM)) return rc;
+    if (int rc = make_map_f16(&t->tm_h1, t->h1, cap, FC1_OUT, BM)) return rc;
     t->cap = cap;
     return 0;
 }
 
-int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s)
+// x16 != nullptr: the crops arrive as 16-bit depth and include/handtrack.h:700 runs inside the conv kernel's loader
+static int tc_forward_impl(Net &net, const float *x, const uint16_t *x16, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, cudaStream_t s)
 {
     TcState *t = net.tc;
     for (int64_t b = 0; b < n; b += TC_CHUNK) {
         const int64_t m = (n - b < TC_CHUNK) ? n - b : TC_CHUNK;
         if (int rc = tc_ensure(net, m)) return rc;
-        // conv stages (FFMA for now) -> bf16 features
         {
             StageTimer st(net, 0, s);
-            if (int rc = tc_conv_stage(net, x + b * N_IN, m, t->p2, s)) return rc;
+            if (x16) {
+                if (int rc = tc_conv2_stage_u16(net, x16 + b * N_IN, m, depth_scale, dmin, dmax, t->p2, s)) return rc;
+            } else if (int rc = tc_conv_stage(net, x + b * N_IN, m, t->p2, s)) return rc;
         }
         const int m_tiles = (int)((m + BM - 1) / BM);
         {
@@ -804,7 +811,7 @@ int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s
             const int tiles = m_tiles * (FC1_OUT / 256);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
             EpiArgs ea{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0};
-            tc_gemm_kernel<TC_EPI_TANH_BF16, 256><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_p2, t->tm_w1t, ea, (int)m, FC1_OUT, FC1_IN);
+            tc_gemm_kernel<TC_EPI_TANH_ACT, 256, true><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_p2, t->tm_w1t, ea, (int)m, FC1_OUT, FC1_IN);
             LAUNCH_CHECK(net);
         }
         {
@@ -812,21 +819,30 @@ int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s
             const int tiles = m_tiles * (FC2_OUT / 256);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
             EpiArgs ea{net.params + OFF_F2B, y_out + b * N_OUT, nullptr, nullptr, 0};
-            tc_gemm_kernel<TC_EPI_SOFTMAX_F32, 256><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
+            tc_gemm_kernel<TC_EPI_SOFTMAX_F32, 256, true><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
             LAUNCH_CHECK(net);
         }
     }
     return 0;
 }
 
+int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s)
+{
+    return tc_forward_impl(net, x, nullptr, 0.f, 0.f, 1.f, n, y_out, s);
+}
 
-template <int EPI, int BN>
+int tc_forward_u16(Net &net, const uint16_t *depth, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, cudaStream_t s)
+{
+    return tc_forward_impl(net, nullptr, depth, depth_scale, dmin, dmax, n, y_out, s);
+}
+
+template <int EPI, int BN, bool OPS_F16>
 static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB, const EpiArgs &ea, int M, int N, int K, cudaStream_t s)
 {
     TcState *t = net.tc;
     const int tiles = ((M + BM - 1) / BM) * (N / BN) * (ea.ksplit > 1 ? ea.ksplit : 1);
     const int grid = tiles < t->num_sms ? tiles : t->num_sms;
-    tc_gemm_kernel<EPI, BN><<<grid, GEMM_THREADS, gemm_smem(BN), s>>>(tmA, tmB, ea, M, N, K);
+    tc_gemm_kernel<EPI, BN, OPS_F16><<<grid, GEMM_THREADS, gemm_smem(BN), s>>>(tmA, tmB, ea, M, N, K);
     LAUNCH_CHECK(net);
     return 0;
 }
@@ -905,12 +921,12 @@ static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const floa
     const int kb_per = (kb_total + target - 1) / target;
     const int S = (kb_total + kb_per - 1) / kb_per;
     if ((size_t)S * C2_KDIM * C2_CO > w.partial_floats) { set_error("partial buffer too small for %d K ranges", S); return 1; }
-    if (int rc = launch_gemm<TC_EPI_STORE_F32, 64>(net, t->tm_colT, t->tm_e2T, EpiArgs{nullptr, w.partial, nullptr, nullptr, 0, S}, C2_KDIM, C2_CO, R, s)) return rc;
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 64, false>(net, t->tm_colT, t->tm_e2T, EpiArgs{nullptr, w.partial, nullptr, nullptr, 0, S}, C2_KDIM, C2_CO, R, s)) return rc;
     reduce_c2w_t<<<C2_KDIM, 256, 0, s>>>(G + OFF_C2W, w.partial, S, accumulate ? 1 : 0);
     LAUNCH_CHECK(net);
     // dL/dcol, then col2im fused with the conv1-stage tanh'
     __nv_bfloat16 *dcol = reinterpret_cast<__nv_bfloat16 *>(w.colgrad);   // the FP32 path's [n*144][256] fp32 buffer, half used
-    if (int rc = launch_gemm<TC_EPI_STORE_BF16, 256>(net, t->tm_e2, t->tm_w2kt, EpiArgs{nullptr, dcol, nullptr, nullptr, 0, 0}, R, C2_KDIM, C2_CO, s)) return rc;
+    if (int rc = launch_gemm<TC_EPI_STORE_BF16, 256, false>(net, t->tm_e2, t->tm_w2kt, EpiArgs{nullptr, dcol, nullptr, nullptr, 0, 0}, R, C2_KDIM, C2_CO, s)) return rc;
     col2im_g1_vec<<<(unsigned)n, 256, 0, s>>>(dcol, w.p1, w.g1);
     LAUNCH_CHECK(net);
     return fp32_conv1_wgrad(net, x, n, accumulate, s);
@@ -939,17 +955,17 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     // small batches: 64-wide N tiles so that the GEMMs spread over the SMs (256-wide tiles give 2 x 8 CTAs at n = 256)
     const bool narrow = ((M + BM - 1) / BM) * (FC1_OUT / 256) < 74;
     if (narrow) {
-        if (int rc = launch_gemm<TC_EPI_TANH_BF16, 64>(net, t->tm_p2, t->tm_w1t64, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
-        if (int rc = launch_gemm<TC_EPI_STORE_F32, 64>(net, t->tm_h1, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, w.logits, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_TANH_ACT, 64, true>(net, t->tm_p2, t->tm_w1t64, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_STORE_F32, 64, true>(net, t->tm_h1, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, w.logits, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
         if (int rc = fp32_softmax_loss(net, w.logits, w.y, t_dev, w.dlog, t->dlog_bf, mse, n, s)) return rc;
     } else {
-        if (int rc = launch_gemm<TC_EPI_TANH_BF16, 256>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
-        if (int rc = launch_gemm<TC_EPI_SOFTMAX_F32, 256>(net, t->tm_h1, t->tm_w2t, EpiArgs{net.params + OFF_F2B, w.y, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_TANH_ACT, 256, true>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_SOFTMAX_F32, 256, true>(net, t->tm_h1, t->tm_w2t, EpiArgs{net.params + OFF_F2B, w.y, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
         loss_from_y<<<(unsigned)n, 256, 0, s>>>(w.y, t_dev, w.dlog, t->dlog_bf, mse);
         LAUNCH_CHECK(net);
     }
     if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
-    transpose_bf16_pair<<<dim3(N_OUT / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->h1, t->h1T, FC1_OUT}, TransposeJob{t->dlog_bf, t->dlogT, N_OUT}, M,
+    transpose_bf16_pair<<<dim3(N_OUT / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->h1, t->h1T, FC1_OUT, 1}, TransposeJob{t->dlog_bf, t->dlogT, N_OUT, 0}, M,
                                                                                  n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW2[2048][2304] = h1^T * dlog
@@ -957,35 +973,35 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     // data-parallel exchange CTAs: 128-wide tiles (288 of them) then waste a fifth of a wave instead of most of one
     const bool half_tiles = t->num_sms < 144;
     if (half_tiles) {
-        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128>(net, t->tm_h1T, t->tm_dlogT128, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128, false>(net, t->tm_h1T, t->tm_dlogT128, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
     } else
-    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256, false>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
     // da1 = (dlog * W2^T) .* (1 - h1^2)
     if (narrow) {
-        if (int rc = launch_gemm<TC_EPI_DTANH, 64>(net, t->tm_dlog, t->tm_w2b64, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_dlog, t->tm_w2b64, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
     } else {
-        if (int rc = launch_gemm<TC_EPI_DTANH, 256>(net, t->tm_dlog, t->tm_w2b, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_DTANH, 256, false>(net, t->tm_dlog, t->tm_w2b, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[0], s));
     // ---- fc1
     if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
-    transpose_bf16_pair<<<dim3(FC1_IN / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->p2, t->p2T, FC1_IN}, TransposeJob{t->da1_bf, t->da1T, FC1_OUT}, M,
+    transpose_bf16_pair<<<dim3(FC1_IN / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->p2, t->p2T, FC1_IN, 1}, TransposeJob{t->da1_bf, t->da1T, FC1_OUT, 0}, M,
                                                                                   n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW1[k'][2048] = p2^T * da1, rows un-permuted from HWC to the reference's CHW flatten on store
     if (half_tiles) {
-        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128>(net, t->tm_p2T, t->tm_da1T128, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW},
+        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128, false>(net, t->tm_p2T, t->tm_da1T128, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW},
                                                         FC1_IN, FC1_OUT, n_pad, s)) return rc;
     } else
-    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256, false>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
                                                     FC1_OUT, n_pad, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
     // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order
     if (narrow) {
-        if (int rc = launch_gemm<TC_EPI_DTANH, 64>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     } else {
-        if (int rc = launch_gemm<TC_EPI_DTANH, 256>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_DTANH, 256, false>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[1], s));
     // ---- conv stages backward (winners-only weight gradients; FFMA)

@@ -1,16 +1,55 @@
 // hp_tc.cuh -- state shared by the tensor-core kernel files (hp_tc.cu: FC GEMMs, hp_tc_conv.cu: conv stages).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "hp_common.cuh"
 
 namespace hp {
 
+// ---- arithmetic of the tensor-core path --------------------------------------------------------------------------
+// Forward operands (crop, conv weights, p1, p2, h1, FC weights) are IEEE half: the same tcgen05 rate as bf16 with
+// 8x less rounding error (2^-11 vs 2^-8 relative), which is what keeps peaky softmax outputs (logits x30, the regime of
+// a trained net) inside the 1e-2 bound of BASELINE.json.  Every one of these values is a tanh output, a [0,1] depth value
+// or a weight, so the fp16 range is no constraint; the float -> half conversions saturate to +-65504 (NaN stays NaN).
+// Backward operands (dL/dlogits, dL/da1, dense conv2 error) stay bf16: gradients need the exponent range.
+typedef __half act_t;
+
+__device__ __forceinline__ uint32_t pack_act(float a, float b)   // a -> low half, b -> high half
+{
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_act(uint32_t v)
+{
+    return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
+__device__ __forceinline__ float ex2_fast(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// TanH::f (cnn.h:31) as the reference writes it, (e - 1) / (e + 1) with e = exp(2t), on the MUFU units: ex2.approx
+// (2 ulp) and rcp.approx (1 ulp, subnormal results kept).  Absolute error ~1e-7, and -- unlike tanh.approx (2^-11
+// relative) or tanhf -- it keeps the reference's quirk: e overflows for t > 44.36 and inf * rcp(inf) = NaN
+// (SURVEY.md 8a note 2), -1 for very negative t.
+__device__ __forceinline__ float tanh_tc(float t)
+{
+    float e, r;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(e) : "f"(t * 2.8853900817779268f));
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return (e - 1.0f) * r;
+}
+
 struct TcState {
-    // bf16 shadows of the weights, in the layouts the MMAs consume (rebuilt by tc_refresh_weights)
-    __nv_bfloat16 *w1t = nullptr;  // [2048][2304] = fc1.W^T, k contiguous, k in HWC flatten order (pp*64+co)
-    __nv_bfloat16 *w2t = nullptr;  // [2304][2048] = fc2.W^T
-    uint8_t *b1_img = nullptr;     // 32 KB: conv1 as pooled-window GEMM, B operand [256 (pos,co)][64 (r,c)] bf16, 128B-swizzled image
-    uint8_t *b2_img = nullptr;     // 32 KB: conv2 taps, [16 taps][2 k-chunks][64 co][8 ci] bf16 (no-swizzle core matrices)
+    // 16-bit shadows of the weights (fp16 for the forward operands, bf16 for the backward ones), in the layouts the MMAs consume (rebuilt by tc_refresh_weights)
+    act_t *w1t = nullptr;          // [2048][2304] = fc1.W^T, k contiguous, k in HWC flatten order (pp*64+co)
+    act_t *w2t = nullptr;          // [2304][2048] = fc2.W^T
+    uint8_t *b1_img = nullptr;     // 32 KB: conv1 as pooled-window GEMM, B operand [256 (pos,co)][64 (r,c)] fp16, 128B-swizzled image
+    uint8_t *a2_img = nullptr;     // 32 KB: conv2 weights as the TMEM-resident A operand of the v2 conv kernel, [128 (2co+g)][128 k] fp16
+    bool conv_v1 = false;          // HP_CONV_V1=1: run the round-1 conv kernel (hp_tc_conv.cu) instead of hp_tc_conv2.cu
+    uint8_t *b2_img = nullptr;     // 32 KB: conv2 taps, [16 taps][2 k-chunks][64 co][8 ci] fp16 (no-swizzle core matrices)
     __nv_bfloat16 *w1b = nullptr;  // [2304 (k' HWC)][2048] = fc1.W as stored (B operand of the fc1 dX GEMM)
     __nv_bfloat16 *w2b = nullptr;  // [2048][2304] = fc2.W as stored
     // training activations (TRAIN_CAP samples per pass)
@@ -25,8 +64,8 @@ struct TcState {
     CUtensorMap tm_w1b, tm_w2b, tm_dlog, tm_da1, tm_h1T, tm_p2T, tm_dlogT, tm_da1T;
     CUtensorMap tm_dlogT128, tm_da1T128;                  // 128-row boxes: half-width weight-gradient tiles in data-parallel mode
     // activations
-    __nv_bfloat16 *p2 = nullptr;   // [cap][2304] pooled conv2 stage (fc1 input), HWC flatten
-    __nv_bfloat16 *h1 = nullptr;   // [cap][2048] tanh(fc1)
+    act_t *p2 = nullptr;           // [cap][2304] pooled conv2 stage (fc1 input), HWC flatten
+    act_t *h1 = nullptr;           // [cap][2048] tanh(fc1)
     int64_t cap = 0;
     CUtensorMap tm_w1t, tm_w2t, tm_p2, tm_h1;
     int num_sms = 148;     // CTAs of the persistent grids (SM count minus the SMs reserved for NCCL in data-parallel mode)
@@ -37,7 +76,13 @@ int tc_conv_init(Net &net);
 void tc_set_reserved_sms(Net &net, int reserve);
 int tc_conv_refresh(Net &net, cudaStream_t s);
 int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float *mse, bool accumulate, cudaStream_t s);
-int tc_conv_stage_train(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
-int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
+int tc_conv_stage_train(Net &net, const float *x, int64_t n, act_t *p2_bf, cudaStream_t s);
+int tc_conv_stage(Net &net, const float *x, int64_t n, act_t *p2_bf, cudaStream_t s);
+// hp_tc_conv2.cu: the transposed / tap-paired conv2 formulation (default)
+int tc_conv2_init(Net &net);
+int tc_conv2_refresh(Net &net, cudaStream_t s);
+int tc_conv2_stage(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t s);
+int tc_conv2_stage_u16(Net &net, const uint16_t *depth, int64_t n, float depth_scale, float dmin, float dmax, act_t *p2, cudaStream_t s);
+int tc_conv2_stage_train(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t s);
 
 }  // namespace hp

@@ -33,6 +33,8 @@
 #include "hp_ptx.cuh"
 #include "hp_tc.cuh"
 
+#include <stdlib.h>
+
 namespace hp {
 
 #define LAUNCH_CHECK(net)                \
@@ -62,18 +64,6 @@ constexpr int ACC1 = 0;    // two 128-column conv1 accumulators (window-position
 constexpr int ACC2 = 256;  // two conv2 accumulator sets of 2 x 64 columns
 }  // namespace cv
 
-__device__ __forceinline__ float tanh_fast(float x)
-{
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
-{
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
-
 #ifdef HP_CONV_TRACE
 __device__ long long g_conv_trace[64 * 1024];
 #define TRACE(role, it, ev)                                                                       \
@@ -90,7 +80,7 @@ __device__ long long g_conv_trace[64 * 1024];
 template <bool TRAIN>
 __global__ void __launch_bounds__(cv::THREADS, 1)
 tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, const uint8_t *__restrict__ b2_img,
-               const float *__restrict__ params, __nv_bfloat16 *__restrict__ p2_out, int n, float *__restrict__ p1_out,
+               const float *__restrict__ params, act_t *__restrict__ p2_out, int n, float *__restrict__ p1_out,
                uint8_t *__restrict__ idx1_out, uint8_t *__restrict__ idx2_out)
 {
     using namespace cv;
@@ -151,7 +141,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
         // ===================== conv1 MMA issuer =====================
         // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform
         // registers; one elected lane issues.  16 MMAs per crop, fully unrolled.
-        constexpr uint32_t idesc1 = ptx::make_idesc_bf16(128, 128);
+        constexpr uint32_t idesc1 = ptx::make_idesc_f16(128, 128);
         ptx::mbar_wait(wgt_full, 0);
         const uint32_t sB1 = ptx::smem_u32(smem + OFF_B1);
         const uint64_t bd0 = ptx::make_desc_sw128(sB1);
@@ -193,7 +183,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
         }
     } else if (warp == 2) {
         // ===================== conv2 MMA issuer: 2 M tiles x 16 taps per crop =====================
-        constexpr uint32_t idesc2 = ptx::make_idesc_bf16(128, 64), idesc2_m64 = ptx::make_idesc_bf16(64, 64);
+        constexpr uint32_t idesc2 = ptx::make_idesc_f16(128, 64), idesc2_m64 = ptx::make_idesc_f16(64, 64);
         ptx::mbar_wait(wgt_full, 0);
         const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_B2), 1024, 128);
         for (int it = 0; it < my_crops; it++) {
@@ -285,7 +275,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++)
-                        pk[j] = pack_bf16(tanh_fast(mx[2 * j] + bias1[2 * j]), tanh_fast(mx[2 * j + 1] + bias1[2 * j + 1]));
+                        pk[j] = pack_act(tanh_tc(mx[2 * j] + bias1[2 * j]), tanh_tc(mx[2 * j + 1] + bias1[2 * j + 1]));
                     const int q = py * 15 + px;
                     *reinterpret_cast<uint4 *>(planes + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4 *>(planes + P1_PLANE + q * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -294,7 +284,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
                             // the bf16-rounded value conv2 actually consumed, in the reference's [c][y][x] layout
-                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&pk[j >> 1]);
+                            const __half2 h = *reinterpret_cast<const __half2 *>(&pk[j >> 1]);
                             p1_out[crop * P1_N + j * 225 + q] = (j & 1) ? __high2float(h) : __low2float(h);
                             const int blk = am[j] >> 2, sub = am[j] & 3;   // hierarchical position -> (dy, dx)
                             const int dy = 2 * (blk >> 1) + (sub >> 1), dx = 2 * (blk & 1) + (sub & 1);
@@ -338,10 +328,10 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                         for (int k = 0; k < 4; k++) {   // 16-byte chunk index c*4+k, swizzled by the row to avoid bank conflicts
                             const int chunk = c * 4 + k;
                             *reinterpret_cast<uint4 *>(S + q * 128 + ((chunk ^ (q & 7)) << 4)) =
-                                make_uint4(pack_bf16(__uint_as_float(r[8 * k + 0]), __uint_as_float(r[8 * k + 1])),
-                                           pack_bf16(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3])),
-                                           pack_bf16(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
-                                           pack_bf16(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
+                                make_uint4(pack_act(__uint_as_float(r[8 * k + 0]), __uint_as_float(r[8 * k + 1])),
+                                           pack_act(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3])),
+                                           pack_act(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
+                                           pack_act(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
                         }
                     }
                     if (valid && TRAIN) {   // fp32 staging: the pool winners are decided on unrounded pre-activations
@@ -370,11 +360,11 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     const uint32_t *pa = &a.x, *pb2 = &b.x, *pc = &c.x, *pd = &d.x;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const __nv_bfloat162 m01 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pa + k), *reinterpret_cast<const __nv_bfloat162 *>(pb2 + k));
-                        const __nv_bfloat162 m23 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(pc + k), *reinterpret_cast<const __nv_bfloat162 *>(pd + k));
-                        const float2 f = __bfloat1622float2(__hmax2(m01, m23));
+                        const __half2 m01 = __hmax2(*reinterpret_cast<const __half2 *>(pa + k), *reinterpret_cast<const __half2 *>(pb2 + k));
+                        const __half2 m23 = __hmax2(*reinterpret_cast<const __half2 *>(pc + k), *reinterpret_cast<const __half2 *>(pd + k));
+                        const float2 f = __half22float2(__hmax2(m01, m23));
                         const int co = chunk * 8 + 2 * k;
-                        o[k] = pack_bf16(tanh_fast(f.x + bias2[co]), tanh_fast(f.y + bias2[co + 1]));
+                        o[k] = pack_act(tanh_tc(f.x + bias2[co]), tanh_tc(f.y + bias2[co + 1]));
                     }
                     *reinterpret_cast<uint4 *>(p2_out + crop * P2_N + pp * 64 + chunk * 8) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -396,10 +386,10 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                         if (vc[k] > m) { m = vc[k]; arg = 2; }
                         if (vd[k] > m) { m = vd[k]; arg = 3; }
                         const int co = chunk * 4 + k;
-                        o[k] = tanh_fast(m + bias2[co]);
+                        o[k] = tanh_tc(m + bias2[co]);
                         idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg;
                     }
-                    *reinterpret_cast<uint2 *>(p2_out + crop * P2_N + pp * 64 + chunk * 4) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+                    *reinterpret_cast<uint2 *>(p2_out + crop * P2_N + pp * 64 + chunk * 4) = make_uint2(pack_act(o[0], o[1]), pack_act(o[2], o[3]));
                 }
             }
             ptx::named_bar_sync(1, 128);
@@ -427,9 +417,9 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int j = t + 128 * k;
-                const uint32_t lo0 = pack_bf16(v[k][0].x, v[k][0].y), lo1 = pack_bf16(v[k][0].z, v[k][0].w);
-                const uint32_t mi0 = pack_bf16(v[k][1].x, v[k][1].y), mi1 = pack_bf16(v[k][1].z, v[k][1].w);
-                const uint32_t hi0 = pack_bf16(v[k][2].x, v[k][2].y), hi1 = pack_bf16(v[k][2].z, v[k][2].w);
+                const uint32_t lo0 = pack_act(v[k][0].x, v[k][0].y), lo1 = pack_act(v[k][0].z, v[k][0].w);
+                const uint32_t mi0 = pack_act(v[k][1].x, v[k][1].y), mi1 = pack_act(v[k][1].z, v[k][1].w);
+                const uint32_t hi0 = pack_act(v[k][2].x, v[k][2].y), hi1 = pack_act(v[k][2].z, v[k][2].w);
                 *reinterpret_cast<uint4 *>(img + j * 16) = make_uint4(lo0, lo1, mi0, mi1);             // pixels 8j .. 8j+7
                 *reinterpret_cast<uint4 *>(img + IMG_COPY + j * 16) = make_uint4(mi0, mi1, hi0, hi1);  // pixels 8j+4 .. 8j+11
             }
@@ -461,12 +451,12 @@ __device__ __forceinline__ void build_conv_image_elem(int i, const float *__rest
         const int r = k >> 3, c = k & 7;
         const int ky = r - dy, kx = c - dx;
         const float v = (ky >= 0 && ky < 5 && kx >= 0 && kx < 5) ? params[OFF_C1W + co * 25 + ky * 5 + kx] : 0.f;
-        reinterpret_cast<__nv_bfloat16 *>(b1 + nrow * 128 + ((r ^ (nrow & 7)) << 4))[c] = __float2bfloat16_rn(v);
+        reinterpret_cast<__half *>(b1 + nrow * 128 + ((r ^ (nrow & 7)) << 4))[c] = __float2half_rn(v);
     }
     if (i < 16 * 2 * 64 * 8) {
         const int ci8 = i & 7, co = (i >> 3) & 63, kc = (i >> 9) & 1, tap = i >> 10;
         const int ci = kc * 8 + ci8;
-        reinterpret_cast<__nv_bfloat16 *>(b2)[i] = __float2bfloat16_rn(params[OFF_C2W + co * 256 + ci * 16 + tap]);
+        reinterpret_cast<__half *>(b2)[i] = __float2half_rn(params[OFF_C2W + co * 256 + ci * 16 + tap]);
     }
     if (i < C2_KDIM * C2_CO) {
         // w2kt[k = tap*16+ci][co] = conv2.W[co][ci][tap]: the K-major B operand of the training dL/dcol GEMM (hp_tc.cu)
@@ -495,7 +485,8 @@ int tc_conv_init(Net &net)
     HP_CUDA_TRY(cudaMalloc((void **)&t->b2_img, 32768));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
-    return 0;
+    t->conv_v1 = getenv("HP_CONV_V1") != nullptr;
+    return tc_conv2_init(net);
 }
 
 int tc_conv_refresh(Net &net, cudaStream_t s)
@@ -503,12 +494,13 @@ int tc_conv_refresh(Net &net, cudaStream_t s)
     TcState *t = net.tc;
     build_conv_images<<<64, 256, 0, s>>>(net.params, t->b1_img, t->b2_img, t->w2kt);
     LAUNCH_CHECK(net);
-    return 0;
+    return tc_conv2_refresh(net, s);
 }
 
-int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s)
+int tc_conv_stage(Net &net, const float *x, int64_t n, act_t *p2_bf, cudaStream_t s)
 {
     TcState *t = net.tc;
+    if (!t->conv_v1) return tc_conv2_stage(net, x, n, p2_bf, s);
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
     tc_conv_kernel<false><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, nullptr, nullptr, nullptr);
     LAUNCH_CHECK(net);
@@ -516,9 +508,10 @@ int tc_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cud
 }
 
 // training forward: also writes p1 (fp32 CHW), idx1, idx2 into the FP32 workspace layouts the backward kernels read
-int tc_conv_stage_train(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s)
+int tc_conv_stage_train(Net &net, const float *x, int64_t n, act_t *p2_bf, cudaStream_t s)
 {
     TcState *t = net.tc;
+    if (!t->conv_v1) return tc_conv2_stage_train(net, x, n, p2_bf, s);
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
     tc_conv_kernel<true><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2);
     LAUNCH_CHECK(net);

@@ -1,0 +1,456 @@
+// hp_tc_conv2.cu -- both convolution stages of handposedd on tcgen05 tensor cores, second formulation
+// ("v2", the default; hp_tc_conv.cu keeps the round-1 kernel for A/B runs, HP_CONV_V1=1):
+//   crop (fp32, or 16-bit depth normalised on the fly, include/handtrack.h:700)
+//     -> [conv1 5x5 + 2 x (2x2 max-pool) + tanh] -> [conv2 4x4 + tanh + 2x2 max-pool] -> 2304 fp16 features (fc1's A operand).
+// Reference layers: LConv::forward (cnn.h:205-257), LActivation<TanH> (cnn.h:460), LMaxPool::forward (cnn.h:141-148),
+// instantiated at include/handtrack.h:108-114.
+//
+// Why a second formulation.  The round-1 kernel is bound by shared-memory operand bandwidth (128 B/clk/SM): per crop its
+// MMAs read 256 KB of operands (conv2 alone 160 KB: sixteen M128xN64 taps are A-operand bound at 192 B/clk) and its conv2
+// epilogue stages 41 KB more for the 2x2 pool -- ~2.6 k of the measured 2.78 k cycles per crop (profiles/r1_v4_summary.md).
+// conv1 is unchanged here (pooled-window GEMM, see hp_tc_conv.cu); conv2 is TRANSPOSED AND TAP-PAIRED:
+//
+//     D[m = 2 co + g][n = pixel 16 y + x]  +=  A_j[m][ci] * P[n + 16 ky + kxh][ci]        j = (ky, kxh), 8 MMAs M128 x N192 x K16
+//
+//   * A = the conv2 weights, resident in TENSOR MEMORY for the whole kernel (tcgen05.mma with the A operand in TMEM): row
+//     2co+g of MMA j holds W[co][ci][ky][kxh + 2g].  The 64 output channels fill all 128 datapath lanes by computing two
+//     taps per row pair: lane 2co accumulates the kx in {0,1} half of output pixel n, lane 2co+1 the kx in {2,3} half of
+//     output pixel n-2, so  conv2[co][o] = D[2co][o] + D[2co+1][o+2]  -- one shuffle between adjacent lanes.
+//   * B = a shifted view of the pooled conv1 stage in shared memory (planes [8 ch][pixel], row pitch 16 pixels), the only
+//     operand that streams: 8 x 192 rows x 32 B = 48 KB per crop instead of 160 KB, at 64 B/clk.
+//   * pixels are accumulator COLUMNS, so the 2x2 max-pool, bias, tanh and (training) the first-strict-maximum winner run in
+//     one thread's registers: no staging buffer, no barrier among the epilogue warps.
+//   * tensor time 8 x 96 = 768 cycles per crop (was 1024), 75 % of the issued MACs useful (was 56 %).
+// TMEM: columns 0-255 two conv1 accumulators, 256-447 the conv2 accumulator, 448-511 the conv2 weights.
+//
+// Warp roles (640 threads, 1 CTA/SM, crops strided over the grid):
+//   warp 0      conv1 weight image (cp.async.bulk), TMEM allocation
+//   warp 1      conv1 MMA issuer (12 MMAs M128 N128 K16 per crop)
+//   warp 2      conv2 MMA issuer (8 MMAs M128 N192 K16 per crop, A from TMEM)
+//   warps 4-11  epilogue 1 (two warpgroups, one per pooled-column parity): TMEM -> running max over the 16 window
+//               positions -> +bias, tanh -> p1 planes (smem); training: also p1 and the conv1-stage winners to global
+//   warps 12-15 conv2 weights -> TMEM once; then epilogue 2: TMEM -> pair add -> 2x2 max -> +bias, tanh -> global features
+//   warps 16-19 loader: crop -> two fp16 image copies in smem (double-buffered)
+#include "hp_ptx.cuh"
+#include "hp_tc.cuh"
+
+namespace hp {
+
+#define LAUNCH_CHECK(net)                \
+    do {                                 \
+        (net).launches++;                \
+        HP_CUDA_TRY(cudaGetLastError()); \
+    } while (0)
+
+namespace cv2 {
+constexpr int THREADS = 640;
+constexpr int IMG_COPY = 9216;                 // one fp16 image copy (8 KB) + slack for the pad rows' reads
+constexpr int IMG_BUF = 2 * IMG_COPY;          // aligned copy + copy shifted by 4 pixels
+constexpr int P1_PITCH = 16;                   // pixels per row of the pooled conv1 stage in smem (15 used + 1 zero)
+constexpr int P1_ROWS = 256;                   // 15 x 16 pixel rows + zero rows read by the tap shifts of columns up to 191
+constexpr int P1_PLANE = P1_ROWS * 16;         // 8 channels x fp16 per pixel row
+constexpr int P1_BUF = 2 * P1_PLANE;
+constexpr int OFF_B1 = 0;                      // 32 KB, 1024-aligned (128B swizzle)
+constexpr int OFF_IMG = 32768;                 // 2 x IMG_BUF
+constexpr int OFF_P1 = OFF_IMG + 2 * IMG_BUF;  // 2 x P1_BUF
+constexpr int OFF_BIAS = OFF_P1 + 2 * P1_BUF;  // 16 + 64 floats
+constexpr int OFF_BAR = OFF_BIAS + 512;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+// TMEM columns
+constexpr int ACC1 = 0;     // two 128-column conv1 accumulators (window-position halves)
+constexpr int ACC2 = 256;   // conv2 accumulator: 192 columns (pixels), lanes (co, tap half)
+constexpr int W2 = 448;     // conv2 weights: 8 MMAs x 8 columns (16 fp16 K values each)
+constexpr int N2 = 192;     // conv2 MMA N: output pixels 16 y + x <= 187, + 2 for the tap-pair shift
+}  // namespace cv2
+
+// depth normalisation of include/handtrack.h:700, bit-exact with normalize_depth_kernel (hp_post.cu)
+struct DepthNormArgs {
+    float scale, dmin, range;
+};
+__device__ __forceinline__ float normalize_depth(uint32_t v, const DepthNormArgs &nm)
+{
+    const float z = __fmul_rn((float)v, nm.scale);
+    float a = __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(z, nm.dmin), nm.range));
+    a = (a < 0.0f) ? 0.0f : a;
+    a = (1.0f < a) ? 1.0f : a;
+    return a;
+}
+
+// TRAIN additionally emits what CNN::Train's backward needs (cnn.h:571-575): the pooled conv1 activations p1 (fp32 copy
+// of the fp16 values conv2 consumed, the reference's CHW layout) and the max-pool winners of both stages
+// (LMaxPool::backward, cnn.h:149-164: first strict maximum).  U16: the crop arrives as 16-bit depth.
+template <bool TRAIN, bool U16>
+__global__ void __launch_bounds__(cv2::THREADS, 1)
+tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *__restrict__ b1_img, const uint4 *__restrict__ a2_img,
+                const float *__restrict__ params, act_t *__restrict__ p2_out, int n, float *__restrict__ p1_out,
+                uint8_t *__restrict__ idx1_out, uint8_t *__restrict__ idx2_out)
+{
+    using namespace cv2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *bias1 = reinterpret_cast<float *>(smem + OFF_BIAS);
+    float *bias2 = bias1 + 16;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+    uint64_t *wgt_full = bars + 0;
+    uint64_t *img_full = bars + 1;    // [2]
+    uint64_t *img_empty = bars + 3;   // [2]
+    uint64_t *acc1_full = bars + 5;   // [4]: one per group g = e*2 + half (each completes once per crop)
+    uint64_t *acc1_empty = bars + 9;  // [2]
+    uint64_t *p1_full = bars + 11;    // [2]
+    uint64_t *p1_empty = bars + 13;   // [2]
+    uint64_t *acc2_full = bars + 15;
+    uint64_t *acc2_empty = bars + 16;
+    uint64_t *w2_full = bars + 17;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_crops = (n > (int)blockIdx.x) ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(wgt_full, 1);
+        for (int b = 0; b < 2; b++) {
+            ptx::mbar_init(&img_full[b], 128);
+            ptx::mbar_init(&img_empty[b], 1);
+            ptx::mbar_init(&acc1_full[b], 1);
+            ptx::mbar_init(&acc1_full[2 + b], 1);
+            ptx::mbar_init(&acc1_empty[b], 4);
+            ptx::mbar_init(&p1_full[b], 8);
+            ptx::mbar_init(&p1_empty[b], 1);
+        }
+        ptx::mbar_init(acc2_full, 1);
+        ptx::mbar_init(acc2_empty, 4);
+        ptx::mbar_init(w2_full, 4);
+        ptx::fence_barrier_init();
+    }
+    // zero the p1 planes once (pad pixels x = 15 and rows 240..255 are read by the tap shifts) and the image buffers
+    for (int i = threadIdx.x; i < 2 * P1_BUF / 16; i += THREADS) reinterpret_cast<uint4 *>(smem + OFF_P1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 2 * IMG_BUF / 16; i += THREADS) reinterpret_cast<uint4 *>(smem + OFF_IMG)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 16) bias1[threadIdx.x] = params[OFF_C1B + threadIdx.x];
+    if (threadIdx.x >= 64 && threadIdx.x < 128) bias2[threadIdx.x - 64] = params[OFF_C2B + threadIdx.x - 64];
+    if (warp == 0) ptx::tmem_alloc<512>(tmem_ptr);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(wgt_full, 32768);
+            ptx::bulk_load_1d(smem + OFF_B1, b1_img, 32768, wgt_full);
+        }
+    } else if (warp == 1) {
+        // ===================== conv1 MMA issuer (as in hp_tc_conv.cu) =====================
+        constexpr uint32_t idesc1 = ptx::make_idesc_f16(128, 128);
+        ptx::mbar_wait(wgt_full, 0);
+        const uint32_t sB1 = ptx::smem_u32(smem + OFF_B1);
+        const uint64_t bd0 = ptx::make_desc_sw128(sB1);
+        for (int it = 0; it < my_crops; it++) {
+            const int ib = it & 1;
+            ptx::mbar_wait(&img_full[ib], (it >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint64_t ad0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_IMG + ib * IMG_BUF), 128, 512);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int e = g >> 1, half = g & 1;        // e: pooled-column parity (which image copy)
+                const uint32_t u = (uint32_t)(it * 2 + e);  // use count of accumulator `half`
+                ptx::mbar_wait(&acc1_empty[half], (u & 1) ^ 1);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t d = tmem_base + ACC1 + half * 128;
+                    const uint64_t ad = ad0 + ((e * IMG_COPY) >> 4), bd = bd0 + ((half * 16384) >> 4);
+                    // K step ks covers patch rows 2ks, 2ks+1; the all-zero K step of each window-position half is skipped
+                    if (half == 0) {
+                        ptx::umma_f16_c<false>(d, ad, bd, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (256 >> 4), bd + 2, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
+                    } else {
+                        ptx::umma_f16_c<false>(d, ad + (256 >> 4), bd + 2, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
+                        ptx::umma_f16_c<true>(d, ad + (768 >> 4), bd + 6, idesc1);
+                    }
+                    ptx::umma_commit(&acc1_full[g]);
+                    if (g == 3) ptx::umma_commit(&img_empty[ib]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== conv2 MMA issuer: 8 tap pairs, A (weights) from TMEM =====================
+        constexpr uint32_t idesc2 = ptx::make_idesc_f16(128, N2);
+        ptx::mbar_wait(w2_full, 0);
+        ptx::tc_fence_after();
+        for (int it = 0; it < my_crops; it++) {
+            const int pb = it & 1;
+            ptx::mbar_wait(&p1_full[pb], (it >> 1) & 1);
+            ptx::mbar_wait(acc2_empty, (it & 1) ^ 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF), P1_PLANE, 128);
+                const uint32_t d = tmem_base + ACC2, a0 = tmem_base + W2;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int shift = (j >> 1) * P1_PITCH + (j & 1);   // pixel rows: 16 ky + kxh
+                    if (j == 0) ptx::umma_f16_ts_c<false>(d, a0, bd0, idesc2);
+                    else ptx::umma_f16_ts_c<true>(d, a0 + 8 * j, bd0 + shift, idesc2);
+                }
+                ptx::umma_commit(acc2_full);
+                ptx::umma_commit(&p1_empty[pb]);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== epilogue 1: conv1 accumulators -> p1 planes =====================
+        const int ew = warp & 3;
+        const int my_e = (warp - 4) >> 2;
+        const int m = ew * 32 + lane;           // row of the M tile: (py, px')
+        const int py = m >> 3, pxh = m & 7;
+        const int px = 2 * pxh + my_e;
+        for (int it = 0; it < my_crops; it++) {
+            const int pb = it & 1;
+            uint8_t *planes = smem + OFF_P1 + pb * P1_BUF;
+            ptx::mbar_wait(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
+            float mx[16];
+            int am[16];
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                ptx::mbar_wait(&acc1_full[my_e * 2 + half], it & 1);
+                ptx::tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC1 + half * 128;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
+                    uint32_t r[32];
+                    ptx::tmem_ld32(ta + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    if (TRAIN) {
+                        const int p0 = half * 8 + 2 * c;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[16 + j]);
+                            if ((half == 0 && c == 0) || v0 > mx[j]) { mx[j] = v0; am[j] = p0; }
+                            if (v1 > mx[j]) { mx[j] = v1; am[j] = p0 + 1; }
+                        }
+                    } else if (half == 0 && c == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) mx[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) mx[j] = ptx::max3(mx[j], __uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
+            }
+            if (py < 15 && px < 15) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    pk[j] = pack_act(tanh_tc(mx[2 * j] + bias1[2 * j]), tanh_tc(mx[2 * j + 1] + bias1[2 * j + 1]));
+                const int q = py * P1_PITCH + px;
+                *reinterpret_cast<uint4 *>(planes + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4 *>(planes + P1_PLANE + q * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                if (TRAIN) {
+                    const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                    const int qo = py * 15 + px;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        // the fp16-rounded value conv2 actually consumed, in the reference's [c][y][x] layout
+                        const __half2 h = *reinterpret_cast<const __half2 *>(&pk[j >> 1]);
+                        p1_out[crop * P1_N + j * 225 + qo] = (j & 1) ? __high2float(h) : __low2float(h);
+                        const int blk = am[j] >> 2, sub = am[j] & 3;   // hierarchical position -> (dy, dx)
+                        const int dy = 2 * (blk >> 1) + (sub >> 1), dx = 2 * (blk & 1) + (sub & 1);
+                        idx1_out[crop * P1_N + j * 225 + qo] = (uint8_t)(dy * 4 + dx);
+                    }
+                }
+            }
+            ptx::fence_proxy_async();   // generic-proxy stores -> visible to the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
+        }
+    } else if (warp >= 12 && warp < 16) {
+        // ===================== conv2 weights -> TMEM (once), then epilogue 2 =====================
+        const int ew = warp - 12;               // == warp % 4: the TMEM lane quarter this warp may access
+        const int m = ew * 32 + lane;           // accumulator lane = 2 co + g
+        const int co = m >> 1, g = m & 1;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+        {
+            const uint4 *src = a2_img + m * 16;   // 128 fp16 = 64 words: K = (MMA j, ci)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint4 lo = __ldg(src + 2 * j), hi = __ldg(src + 2 * j + 1);
+                const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                ptx::tmem_st8(lane_base + W2 + 8 * j, r);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(w2_full);
+        }
+        const float b2 = bias2[co];
+        for (int it = 0; it < my_crops; it++) {
+            const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            ptx::mbar_wait(acc2_full, it & 1);
+            ptx::tc_fence_after();
+            // This lane finalises pooled rows py = 3 g + s (s = 0..2): output rows y = 2 py + d, columns 16 y + x.
+            //   window A = D[.][32 s + 16 d + 0..15]       (rows y of the even lanes)
+            //   window B = D[.][96 + 32 s + 16 d + 0..15]  (rows y of the odd lanes)
+            // even lane (kx 0,1 half of pixel n):  own = A[x],     sends B[x]     (the odd lane's pixels, its kx 0,1 half)
+            // odd  lane (kx 2,3 half of pixel n-2): own = B[x + 2], sends A[x + 2] (the even lane's pixels, their kx 2,3 half)
+            float best[3][6];
+            int arg[3][6];
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    uint32_t A[16], B[16];
+                    ptx::tmem_ld16(lane_base + ACC2 + 32 * s + 16 * d, A);
+                    ptx::tmem_ld16(lane_base + ACC2 + 96 + 32 * s + 16 * d, B);
+                    ptx::tmem_ld_wait();
+                    if (s == 2 && d == 1) {   // last read of this crop's accumulator: hand it back to the MMA issuer
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(acc2_empty);
+                    }
+#pragma unroll
+                    for (int xx = 0; xx < 12; xx++) {
+                        const float own = __uint_as_float(g ? B[xx + 2] : A[xx]);
+                        const float send = __uint_as_float(g ? A[xx + 2] : B[xx]);
+                        const float v = own + __shfl_xor_sync(0xffffffffu, send, 1);
+                        const int pxx = xx >> 1, pos = d * 2 + (xx & 1);   // scan order (0,0),(1,0),(0,1),(1,1), cnn.h:157-161
+                        if (pos == 0) {
+                            best[s][pxx] = v;
+                            arg[s][pxx] = 0;
+                        } else if (TRAIN) {
+                            if (v > best[s][pxx]) { best[s][pxx] = v; arg[s][pxx] = pos; }
+                        } else {
+                            best[s][pxx] = fmaxf(best[s][pxx], v);
+                        }
+                    }
+                }
+            }
+            // + bias, tanh (max and the monotone tanh commute in the forward pass), features in HWC order (pp * 64 + co)
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+#pragma unroll
+                for (int pxx = 0; pxx < 6; pxx++) {
+                    const int pp = (3 * g + s) * 6 + pxx;
+                    p2_out[crop * P2_N + pp * 64 + co] = __float2half_rn(tanh_tc(best[s][pxx] + b2));
+                    if (TRAIN) idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg[s][pxx];
+                }
+            }
+        }
+    } else if (warp >= 16) {
+        // ===================== loader: crop -> two fp16 image copies =====================
+        const int t = threadIdx.x - 16 * 32;  // 0..127
+        for (int it = 0; it < my_crops; it++) {
+            const int ib = it & 1;
+            const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            uint32_t lo[4][2], mi[4][2], hi[4][2];   // pixels 8j..8j+3, 8j+4..8j+7, 8j+8..8j+11 of chunk j = t + 128 k, packed fp16x2
+            if (U16) {
+                const uint2 *src = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(x_in) + crop * N_IN);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = t + 128 * k;
+                    const uint2 a = __ldg(src + 2 * j), b = __ldg(src + 2 * j + 1);
+                    const uint2 c = (j < 511) ? __ldg(src + 2 * j + 2) : make_uint2(0, 0);
+                    auto cvt = [&](uint32_t w) { return pack_act(normalize_depth(w & 0xffffu, nm), normalize_depth(w >> 16, nm)); };
+                    lo[k][0] = cvt(a.x); lo[k][1] = cvt(a.y);
+                    mi[k][0] = cvt(b.x); mi[k][1] = cvt(b.y);
+                    if (j < 511) { hi[k][0] = cvt(c.x); hi[k][1] = cvt(c.y); } else { hi[k][0] = hi[k][1] = 0; }
+                }
+            } else {
+                const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(x_in) + crop * N_IN);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = t + 128 * k;  // 8-pixel chunk index
+                    const float4 a = __ldg(src + 2 * j), b = __ldg(src + 2 * j + 1);
+                    const float4 c = (j < 511) ? __ldg(src + 2 * j + 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    lo[k][0] = pack_act(a.x, a.y); lo[k][1] = pack_act(a.z, a.w);
+                    mi[k][0] = pack_act(b.x, b.y); mi[k][1] = pack_act(b.z, b.w);
+                    hi[k][0] = pack_act(c.x, c.y); hi[k][1] = pack_act(c.z, c.w);
+                }
+            }
+            ptx::mbar_wait(&img_empty[ib], ((it >> 1) & 1) ^ 1);
+            uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = t + 128 * k;
+                *reinterpret_cast<uint4 *>(img + j * 16) = make_uint4(lo[k][0], lo[k][1], mi[k][0], mi[k][1]);             // pixels 8j .. 8j+7
+                *reinterpret_cast<uint4 *>(img + IMG_COPY + j * 16) = make_uint4(mi[k][0], mi[k][1], hi[k][0], hi[k][1]);  // pixels 8j+4 .. 8j+11
+            }
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&img_full[ib]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// conv2 weights as the TMEM-resident A operand: row m = 2 co + g, K index k = 16 j + ci with MMA j = (ky, kxh):
+// value = conv2.W[co][ci][ky][kxh + 2 g]  (OIHW, cnn.h:47,201), fp16.  128 rows x 128 K = 32 KB.
+__global__ void __launch_bounds__(256) build_conv2_tmem_image(const float *__restrict__ params, __half *__restrict__ a2)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= 128 * 128) return;
+    const int m = i >> 7, k = i & 127;
+    const int co = m >> 1, g = m & 1, j = k >> 4, ci = k & 15;
+    const int ky = j >> 1, kx = (j & 1) + 2 * g;
+    a2[i] = __float2half_rn(params[OFF_C2W + co * C2_KDIM + ci * 16 + ky * 4 + kx]);
+}
+
+int tc_conv2_init(Net &net)
+{
+    TcState *t = net.tc;
+    HP_CUDA_TRY(cudaMalloc((void **)&t->a2_img, 32768));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    return 0;
+}
+
+int tc_conv2_refresh(Net &net, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    build_conv2_tmem_image<<<64, 256, 0, s>>>(net.params, reinterpret_cast<__half *>(t->a2_img));
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+int tc_conv2_stage(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    const int grid = (int)(n < t->num_sms ? n : t->num_sms);
+    tc_conv2_kernel<false, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
+                                                                       net.params, p2, (int)n, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// 16-bit depth crops in, include/handtrack.h:700 applied in the loader (no fp32 crop buffer in HBM)
+int tc_conv2_stage_u16(Net &net, const uint16_t *depth, int64_t n, float depth_scale, float dmin, float dmax, act_t *p2, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    const int grid = (int)(n < t->num_sms ? n : t->num_sms);
+    tc_conv2_kernel<false, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(depth, DepthNormArgs{depth_scale, dmin, dmax - dmin}, t->b1_img,
+                                                                      reinterpret_cast<const uint4 *>(t->a2_img), net.params, p2, (int)n, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+// training forward: also writes p1 (fp32 CHW), idx1, idx2 into the FP32 workspace layouts the backward kernels read
+int tc_conv2_stage_train(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    const int grid = (int)(n < t->num_sms ? n : t->num_sms);
+    tc_conv2_kernel<true, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
+                                                                      net.params, p2, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+}  // namespace hp

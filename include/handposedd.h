@@ -48,7 +48,8 @@ enum hp_status {
     HP_ERR_CUDA = 3,        /* a CUDA call failed; see hp_last_error() */
     HP_ERR_IO = 4,          /* file could not be opened / short buffer */
     HP_ERR_NCCL = 5,        /* NCCL unavailable or failed */
-    HP_ERR_NO_DEVICE = 6    /* no usable sm_100 device: there is no CPU fallback */
+    HP_ERR_NO_DEVICE = 6,   /* no usable sm_100 device: there is no CPU fallback */
+    HP_ERR_PEER = 7         /* a data-parallel exchange kernel gave up waiting for a rank; weights untouched since */
 };
 
 /* Arithmetic of the contraction layers (conv + FC). */
@@ -101,7 +102,8 @@ HP_API int hp_destroy(hp_net *net);
  * std::default_random_engine (libstdc++: minstd_rand0, default seed) shared
  * across layers; biases 0.  Bit-identical to the reference under libstdc++. */
 HP_API int hp_init_xavier(hp_net *net);
-/* Replaces: CNN::loadb(std::istream&) (cnn.h:590).  Like the reference's
+/* Replaces: CNN::loadb(std::istream&) (cnn.h:590).  Synchronises the whole device first (work in flight on caller
+ * streams may still read the weights).  Like the reference's
  * loadvb (cnn.h:97), a short buffer fills a prefix and leaves the tail of the
  * weights unmodified; n_bytes beyond HP_CNNB_BYTES are ignored. */
 HP_API int hp_load_cnnb(hp_net *net, const void *bytes, size_t n_bytes);
@@ -145,6 +147,11 @@ HP_API int hp_eval_decode_batch(hp_net *net, const float *x, int64_t n, float *y
  * on the device, bit-exactly.  The reference uses drange = {0.1, 0.7} and depth_scale = 0.001. */
 HP_API int hp_eval_depth_batch(hp_net *net, const uint16_t *depth, int64_t n, float depth_scale, float dmin, float dmax, float *y,
                                float *decoded, int precision);
+/* Same chain with DEVICE buffers on the caller's stream: depth_dev[n][4096] uint16 -> y_dev[n][2304] (required) and,
+ * if decoded_dev != NULL, decoded_dev[n][48].  On the tensor path the normalisation runs inside the convolution
+ * kernel's loader: no fp32 crop buffer exists in HBM (8 KB read per crop instead of 8 + 16 + 16). */
+HP_API int hp_eval_depth_batch_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax,
+                                      float *y_dev, float *decoded_dev, int precision, void *stream);
 HP_API int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax,
                                      float *x_dev, void *stream);
 
@@ -249,7 +256,10 @@ HP_API int hp_dp_set_bf16_gradients(hp_net *net, int enable);
 #define HP_PEER_HANDLE_BYTES 256
 HP_API int hp_dp_peer_export(hp_net *net, void *handle_out);
 HP_API int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world);
-/* 0, or 1 + the rank an exchange kernel gave up waiting for (4 s); the weights are then undefined. */
+/* 0, or 1 + the rank an exchange kernel gave up waiting for (HP_PEER_TIMEOUT_S seconds, default 30).  The failing
+ * exchange and every later one skip their reduce / update / store phases, so the weights stay at the last state all
+ * ranks agreed on, and hp_train_batch* / hp_save_cnnb return HP_ERR_PEER from then on (the latch is host-visible:
+ * no polling of this call is needed).  Recover with hp_dp_shutdown + a fresh export/init on all ranks. */
 HP_API int hp_dp_peer_status(hp_net *net, int *timed_out_on_rank_plus_1);
 HP_API int hp_dp_shutdown(hp_net *net);
 

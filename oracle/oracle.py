@@ -148,6 +148,47 @@ class Oracle:
         return out
 
 
+def eval_mt(params, x, threads=None):
+    """Oracle.eval over a thread pool (one Oracle workspace per worker; ctypes releases the GIL): the 1,024-crop
+    slice checks of the full-size tests and of bench.py's parity_check."""
+    from concurrent.futures import ThreadPoolExecutor
+    x = _f32(x).reshape(-1, N_IN)
+    params = _f32(params)
+    threads = max(1, min(threads or (os.cpu_count() or 1), x.shape[0]))
+    bounds = [x.shape[0] * i // threads for i in range(threads + 1)]
+
+    def work(i):
+        return Oracle().eval(params, x[bounds[i]:bounds[i + 1]])
+
+    with ThreadPoolExecutor(threads) as ex:
+        return np.concatenate(list(ex.map(work, range(threads))))
+
+
+def grad_minibatch_mt(params, x, t, threads=None):
+    """sum_b g_b (float64) and the per-sample MSE of a minibatch at frozen weights -- the quantity
+    Oracle.train_minibatch(apply=False) returns -- computed sample-parallel over a thread pool."""
+    from concurrent.futures import ThreadPoolExecutor
+    x = _f32(x).reshape(-1, N_IN)
+    t = _f32(t).reshape(-1, N_OUT)
+    params = _f32(params)
+    n = x.shape[0]
+    threads = max(1, min(threads or (os.cpu_count() or 1), n))
+    bounds = [n * i // threads for i in range(threads + 1)]
+
+    def work(i):
+        o = Oracle()
+        g = np.zeros(N_PARAMS, np.float64)
+        mse = np.empty(bounds[i + 1] - bounds[i], np.float32)
+        for k, b in enumerate(range(bounds[i], bounds[i + 1])):
+            gb, mse[k] = o.grad_sample(params, x[b], t[b])
+            g += gb
+        return g, mse
+
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(work, range(threads)))
+    return sum(p[0] for p in parts), np.concatenate([p[1] for p in parts])
+
+
 class PostRef:
     """The reference's decode / crop-normalisation routines (oracle/_ref/libpostref.so, ref_post_shim.cpp)."""
 

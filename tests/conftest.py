@@ -41,3 +41,17 @@ def maxnorm_err(a, b):
     if denom == 0:
         return float(np.abs(a).max())
     return float(np.abs(a - b).max() / denom)
+
+
+def record(name, value):
+    """Append one measured parity figure to gpurun_out/parity_measured.jsonl (scratch; the GPU box brings it back) so
+    that the numbers behind the asserted bounds can be quoted in DESIGN.md / profiles/."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps({"name": name, "value": value}) + "\n")
+    except OSError:
+        pass
+    print("[measured] %s = %s" % (name, value))

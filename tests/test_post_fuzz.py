@@ -1,8 +1,8 @@
 """Adversarial inputs for the rows either side of the CNN: heatmaps full of ties, NaN, inf and
 negative values for the decode; label parameters off the map, on integer pixels, NaN; random depth ranges for the
-normalisation.  The plain-C oracle against the reference's own routines (oracle/_ref/libpostref.so).  The same generators
-drive tools/dbg/post_fuzz_gpu.py (device kernels against the oracle); that script is not part of the collected suite yet: its
-first run found the NaN-at-(0,0) PeakVolume case (see csrc/hp_post.cu) after this round's GPU budget was spent."""
+normalisation.  The plain-C oracle against the reference's own routines (oracle/_ref/libpostref.so), and -- with the same
+generators -- the device kernels against the oracle, bit for bit (the first device run of these generators found the
+NaN-at-(0,0) PeakVolume case documented in csrc/hp_post.cu)."""
 import numpy as np
 import pytest
 
@@ -70,3 +70,24 @@ def test_oracle_equals_reference_on_adversarial_inputs():
     for seed in range(60):
         d, sc, dmin, dmax = depth_case(seed)
         assert same_bits(o.normalize_depth(d, sc, dmin, dmax), r.normalize_depth(d, sc, dmin, dmax)), ("normalize", seed)
+
+
+@pytest.mark.gpu
+def test_device_kernels_equal_oracle_on_adversarial_inputs():
+    import torch
+    from hand_tracking_samples_b200 import capi, cnn as hp
+    net = hp.PoseInitializerCNN("")
+    o = orc.Oracle()
+    st = torch.cuda.current_stream().cuda_stream
+    for seed in range(48):
+        y = heatmaps(seed)
+        assert same_bits(net.decode_batch(y), o.decode(y)), ("decode", seed)
+        pts, vals = label_params(seed)
+        assert same_bits(net.render_labels(pts, vals), o.render_labels(pts, vals)), ("labels", seed)
+    for seed in range(16):
+        d, sc, dmin, dmax = depth_case(seed)
+        dd = torch.from_numpy(d.view(np.int16)).cuda()
+        x = torch.empty((3, 4096), device="cuda")
+        capi.check(net.L.hp_normalize_depth_device(net.h, dd.data_ptr(), 3, sc, dmin, dmax, x.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert same_bits(x.cpu().numpy(), o.normalize_depth(d, sc, dmin, dmax)), ("normalize", seed)
