@@ -20,7 +20,7 @@ PEER_HANDLE_BYTES = 256
 # every symbol include/handposedd.h declares
 SYMBOLS = [
     "hp_create", "hp_create_handposedd", "hp_retain", "hp_destroy", "hp_init_xavier", "hp_load_cnnb",
-    "hp_save_cnnb", "hp_load_cnnb_file", "hp_save_cnnb_file", "hp_eval_batch", "hp_eval_batch_device",
+    "hp_save_cnnb", "hp_get_params_range", "hp_set_params_range", "hp_load_cnnb_file", "hp_save_cnnb_file", "hp_eval_batch", "hp_eval_batch_device",
     "hp_decode_batch", "hp_decode_batch_device", "hp_eval_decode_batch", "hp_eval_depth_batch", "hp_eval_depth_batch_device", "hp_normalize_depth_device",
     "hp_render_labels", "hp_render_labels_device", "hp_train_batch_points",
     "hp_train_batch", "hp_train_batch_device", "hp_grad_batch_device", "hp_get_grads", "hp_device_ptrs",
@@ -71,6 +71,8 @@ def lib():
     L.hp_init_xavier.argtypes = [vp]
     L.hp_load_cnnb.argtypes = [vp, vp, C.c_size_t]
     L.hp_save_cnnb.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.hp_get_params_range.argtypes = [vp, i64, i64, vp]
+    L.hp_set_params_range.argtypes = [vp, i64, i64, vp]
     L.hp_load_cnnb_file.argtypes = [vp, C.c_char_p]
     L.hp_save_cnnb_file.argtypes = [vp, C.c_char_p]
     L.hp_eval_batch.argtypes = [vp, vp, i64, vp, C.c_int]

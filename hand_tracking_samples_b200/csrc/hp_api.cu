@@ -536,6 +536,28 @@ int hp_save_cnnb(const hp_net *net, void *bytes, size_t capacity, size_t *n_writ
     return HP_OK;
 }
 
+int hp_get_params_range(const hp_net *net, int64_t first, int64_t count, float *host)
+{
+    if (!net || !host || first < 0 || count < 0 || first + count > (int64_t)N_PARAMS) { set_error("bad argument"); return HP_ERR_INVALID; }
+    const Net &n = net->n;
+    HP_CUDA_TRY(cudaSetDevice(n.device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    if (int rc = check_peer(n)) return rc;
+    if (count) HP_CUDA_TRY(cudaMemcpy(host, n.params + first, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+int hp_set_params_range(hp_net *net, int64_t first, int64_t count, const float *host)
+{
+    if (!net || !host || first < 0 || count < 0 || first + count > (int64_t)N_PARAMS) { set_error("bad argument"); return HP_ERR_INVALID; }
+    Net &n = net->n;
+    HP_CUDA_TRY(cudaSetDevice(n.device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    if (count) HP_CUDA_TRY(cudaMemcpy(n.params + first, host, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    n.tc_dirty = true;
+    return HP_OK;
+}
+
 int hp_load_cnnb_file(hp_net *net, const char *path)
 {
     if (!net || !path) { set_error("bad argument"); return HP_ERR_INVALID; }

@@ -30,16 +30,18 @@ __device__ __forceinline__ float ex2_fast(float x)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// TanH::f (cnn.h:31) as the reference writes it, (e - 1) / (e + 1) with e = exp(2t), on the MUFU units: ex2.approx
-// (2 ulp) and rcp.approx (1 ulp, subnormal results kept).  Absolute error ~1e-7, and -- unlike tanh.approx (2^-11
-// relative) or tanhf -- it keeps the reference's quirk: e overflows for t > 44.36 and inf * rcp(inf) = NaN
-// (SURVEY.md 8a note 2), -1 for very negative t.
+// TanH::f (cnn.h:31), (e - 1) / (e + 1) with e = exp(2t), on the MUFU units: ex2.approx (2 ulp) and rcp.approx (1 ulp),
+// evaluated as 1 - 2 / (e + 1).  Absolute error ~2e-7 (tanh.approx has 2^-11 RELATIVE error, which at 30x logits is
+// what broke the 1e-2 bound on peaky outputs).  The reference's overflow quirk is kept: e = inf for t > 44.36 makes
+// (e - 1) / (e + 1) NaN (SURVEY.md 8a note 2); here (e - e) contributes that NaN and is 0 otherwise.  Very negative t
+// gives e = 0 and -1, as in the reference.  The .ftz forms matter: without them ptxas wraps every MUFU in a predicated
+// denormal-rescue sequence on one predicate register, which serialises the epilogue (measured: fc1 110 -> 140 us).
 __device__ __forceinline__ float tanh_tc(float t)
 {
     float e, r;
-    asm("ex2.approx.f32 %0, %1;" : "=f"(e) : "f"(t * 2.8853900817779268f));
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return (e - 1.0f) * r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f) + (e - e);
 }
 
 struct TcState {

@@ -109,6 +109,11 @@ HP_API int hp_init_xavier(hp_net *net);
 HP_API int hp_load_cnnb(hp_net *net, const void *bytes, size_t n_bytes);
 /* Replaces: CNN::saveb(std::ostream&) (cnn.h:591).  *n_written = HP_CNNB_BYTES. */
 HP_API int hp_save_cnnb(const hp_net *net, void *bytes, size_t capacity, size_t *n_written);
+/* Replaces: the per-layer streams LConv/LFull::loada/savea/loadb/saveb (cnn.h:286-289, 452-455) and their
+ * operator>> / operator<< (cnn.h:606-609): one layer's W then B is a contiguous float range of the .cnnb-ordered
+ * store (offsets: SURVEY.md 8c).  HOST buffers; first + count <= HP_N_PARAMS. */
+HP_API int hp_get_params_range(const hp_net *net, int64_t first, int64_t count, float *host);
+HP_API int hp_set_params_range(hp_net *net, int64_t first, int64_t count, const float *host);
 /* Replaces: CNN::loadb(std::string) / CNN::saveb(std::string) (cnn.h:592-593).
  * hp_load_cnnb_file returns HP_ERR_IO if the file cannot be opened (the C++
  * wrapper keeps the reference's silent no-op by ignoring that status). */

@@ -42,6 +42,11 @@ struct LeakyReLU {};
 
 namespace handposedd {
 // accepts brace lists {x,y,z} as well as linalg::vec<int,3> / <int,4> (anything with .x .y .z [.w])
+struct i2 {
+    int x, y;
+    i2(int x_, int y_) : x(x_), y(y_) {}
+    template <class V, class = decltype(V().x + V().y)> i2(const V &v) : x(v.x), y(v.y) {}
+};
 struct i3 {
     int x, y, z;
     i3(int x_, int y_, int z_) : x(x_), y(y_), z(z_) {}
@@ -56,18 +61,75 @@ inline void check(int status)
 {
     if (status != HP_OK) throw std::runtime_error(std::string("handposedd: ") + hp_last_error());
 }
+// which activation tags have device kernels (declared before CNN so that LActivation<F>::describe needs no
+// specialisation after its first use)
+template <class F> struct act_kind { static constexpr int value = 0; };
+template <> struct act_kind<TanH> { static constexpr int value = HP_LAYER_TANH; };
+// The device net behind a CNN and all of its by-value copies.  Allocated when the CNN is constructed -- not when the
+// net is first used -- so that copies made before first use (include/handtrack.h:129 returns the CNN by value right
+// after building it) share one weight store exactly like the reference's copies share their layer pointers.
+struct NetHolder {
+    hp_net *h = nullptr;
+    size_t built_for = 0;
+    ~NetHolder() { if (h) hp_destroy(h); }
+};
 }  // namespace handposedd
 
 struct CNN {
     struct LBase {
         virtual ~LBase() {}
         virtual hp_layer_desc describe() const = 0;
+        // cnn.h:107-110: per-layer streams; layers without weights stream nothing
+        virtual void loada(std::istream &) {}
+        virtual void savea(std::ostream &) const {}
+        virtual void loadb(std::istream &) {}
+        virtual void saveb(std::ostream &) const {}
     };
-    struct LConv final : public LBase {  // cnn.h:194-290
+    // A weighted layer's W then B is one contiguous float range [first, first + count) of the device weight store
+    // (.cnnb order).  The range is bound when the owning CNN builds its device net (CNN::net()); a layer that belongs
+    // to no built net has nowhere to keep weights (there are no host-side vectors here) and its streams throw.
+    struct LWeighted : public LBase {
+        void loada(std::istream &s) override
+        {
+            std::vector<float> p = fetch();
+            for (auto &w : p) s >> w;
+            store(p);
+        }
+        void savea(std::ostream &s) const override
+        {
+            for (float w : fetch()) s << w << ' ';
+        }
+        void loadb(std::istream &s) override
+        {
+            std::vector<float> p = fetch();   // a short stream leaves the tail unmodified, like loadvb (cnn.h:97)
+            s.read((char *)p.data(), (std::streamsize)(p.size() * sizeof(float)));
+            store(p);
+        }
+        void saveb(std::ostream &s) const override
+        {
+            std::vector<float> p = fetch();
+            s.write((const char *)p.data(), (std::streamsize)(p.size() * sizeof(float)));
+        }
+        void bind(std::shared_ptr<handposedd::NetHolder> h, int64_t first, int64_t count) { holder_ = h; first_ = first; count_ = count; }
+
+      private:
+        std::vector<float> fetch() const
+        {
+            if (!holder_ || !holder_->h) throw std::runtime_error("handposedd: layer is not part of a built CNN (its weights live in the net's device store)");
+            std::vector<float> p((size_t)count_);
+            handposedd::check(hp_get_params_range(holder_->h, first_, count_, p.data()));
+            return p;
+        }
+        void store(const std::vector<float> &p) { handposedd::check(hp_set_params_range(holder_->h, first_, count_, p.data())); }
+        std::shared_ptr<handposedd::NetHolder> holder_;
+        int64_t first_ = 0, count_ = 0;
+    };
+    struct LConv final : public LWeighted {  // cnn.h:194-290
         handposedd::i3 indims;
         handposedd::i4 dims;
         handposedd::i3 outdims;
         LConv(handposedd::i3 indims, handposedd::i4 dims, handposedd::i3 outdims) : indims(indims), dims(dims), outdims(outdims) {}
+        int64_t weight_count() const { return (int64_t)dims.x * dims.y * dims.z * dims.w + dims.w; }
         hp_layer_desc describe() const override
         {
             hp_layer_desc d = {};
@@ -81,7 +143,13 @@ struct CNN {
     template <class F> struct LActivation final : public LBase {  // cnn.h:457-470
         int n;
         LActivation(int n) : n(n) {}
-        hp_layer_desc describe() const override;
+        hp_layer_desc describe() const override
+        {
+            hp_layer_desc d = {};
+            d.kind = handposedd::act_kind<F>::value;  // Sigmoid / ReLU / LeakyReLU: 0, no device kernels
+            d.in_dims[0] = n;
+            return d;
+        }
     };
     struct LMaxPool final : public LBase {  // cnn.h:136-165
         handposedd::i3 indims;
@@ -94,9 +162,10 @@ struct CNN {
             return d;
         }
     };
-    struct LFull final : public LBase {  // cnn.h:398-456
+    struct LFull final : public LWeighted {  // cnn.h:398-456
         int M, N;
         LFull(int input_size, int output_size) : M(input_size), N(output_size) {}
+        int64_t weight_count() const { return (int64_t)M * N + N; }
         hp_layer_desc describe() const override
         {
             hp_layer_desc d = {};
@@ -131,6 +200,12 @@ struct CNN {
     };
     struct LAvgPool final : public LUnsupported { LAvgPool(handposedd::i3) {} };
     struct LSparsePool final : public LUnsupported { LSparsePool(handposedd::i3) {} };
+    struct LConvS final : public LUnsupported {  // cnn.h:292-396: same-size convolution with radius / stride
+        handposedd::i2 rdims, radius, stride;
+        int din, dout;
+        LConvS(handposedd::i2 rdims, int din, int dout, handposedd::i2 radius = {1, 1}, handposedd::i2 stride = {1, 1})
+            : rdims(rdims), radius(radius), stride(stride), din(din), dout(dout) {}
+    };
     struct LSoftMax final : public LUnsupported { LSoftMax(int) {} };
     struct LCrossEntropy final : public LUnsupported { LCrossEntropy(int) {} };
 
@@ -138,7 +213,11 @@ struct CNN {
     int precision = HP_PRECISION_FP32;  // new: HP_PRECISION_TENSOR selects the tcgen05 path
     int device = 0;
 
-    CNN(const std::vector<int> &s)  // cnn.h:595-604 ("quick test for simple NNs"): LFull + TanH pairs
+    // cnn.h:595-604 ("quick test for simple NNs": LFull + TanH pairs).  The empty list -- the only use in the
+    // reference, `CNN cnn({})` at include/handtrack.h:107 -- builds nothing; a non-empty list describes an MLP this
+    // library has no kernels for, so Init() throws HP_ERR_UNSUPPORTED from inside the constructor instead of silently
+    // building a CPU network ("What does not carry over").
+    CNN(const std::vector<int> &s) : holder_(std::make_shared<handposedd::NetHolder>())
     {
         for (unsigned int i = 1; i < s.size(); i++) {
             layers.push_back(new LFull(s[i - 1], s[i]));
@@ -216,42 +295,41 @@ struct CNN {
         for (float w : p) s << w << ' ';
     }
 
-    // the device net behind this object, created on first use from `layers`
+    // the device net behind this object and its copies, created on first use from `layers`; binds every weighted
+    // layer to its float range of the store (.cnnb order: layers in order, W then B)
     hp_net *net() const
     {
-        if (!handle_ || built_for_ != layers.size()) {
+        handposedd::NetHolder &H = *holder_;
+        if (!H.h || H.built_for != layers.size()) {
             std::vector<hp_layer_desc> d;
             for (auto *l : layers) d.push_back(l->describe());
             hp_net *h = nullptr;
             handposedd::check(hp_create(d.data(), (int)d.size(), device, &h));
-            handle_ = std::shared_ptr<hp_net>(h, [](hp_net *p) { hp_destroy(p); });
-            built_for_ = layers.size();
+            if (H.h) hp_destroy(H.h);
+            H.h = h;
+            H.built_for = layers.size();
+            int64_t off = 0;
+            for (auto *l : layers) {
+                int64_t cnt = 0;
+                if (auto *c = dynamic_cast<LConv *>(l)) cnt = c->weight_count();
+                else if (auto *f = dynamic_cast<LFull *>(l)) cnt = f->weight_count();
+                if (auto *w = dynamic_cast<LWeighted *>(l)) w->bind(holder_, off, cnt);
+                off += cnt;
+            }
         }
-        return handle_.get();
+        return H.h;
     }
 
   private:
-    mutable std::shared_ptr<hp_net> handle_;  // shared by copies: one weight store
-    mutable size_t built_for_ = 0;
+    std::shared_ptr<handposedd::NetHolder> holder_;  // shared by copies from construction on: one weight store
 };
 
-template <> inline hp_layer_desc CNN::LActivation<TanH>::describe() const
-{
-    hp_layer_desc d = {};
-    d.kind = HP_LAYER_TANH;
-    d.in_dims[0] = n;
-    return d;
-}
-template <class F> inline hp_layer_desc CNN::LActivation<F>::describe() const
-{
-    hp_layer_desc d = {};
-    d.kind = 0;  // Sigmoid / ReLU / LeakyReLU: no device kernels
-    d.in_dims[0] = n;
-    return d;
-}
-
-// cnn.h:606-611 (the per-layer operators of the reference stream one layer's own vectors, which
-// do not exist here; the whole-net operators are kept)
+// cnn.h:606-611.  The per-layer operators stream that layer's W then B range of the device store (the layer must
+// belong to a CNN whose device net has been built: any Eval / Train / Init / load / save call does that).
+inline std::istream &operator>>(std::istream &in, CNN::LConv &cl) { cl.loada(in); return in; }
+inline std::ostream &operator<<(std::ostream &ot, const CNN::LConv &cl) { cl.savea(ot); return ot; }
+inline std::istream &operator>>(std::istream &in, CNN::LFull &cl) { cl.loada(in); return in; }
+inline std::ostream &operator<<(std::ostream &ot, const CNN::LFull &cl) { cl.savea(ot); return ot; }
 inline std::istream &operator>>(std::istream &in, CNN &nn) { nn.loada(in); return in; }
 inline std::ostream &operator<<(std::ostream &ot, const CNN &nn) { nn.savea(ot); return ot; }
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <sstream>
 
 template <class T> std::vector<T> concat(std::vector<T> a, const std::vector<T> &b) { a.insert(a.end(), b.begin(), b.end()); return a; }
 static const int key_angles_count = 16;
@@ -72,6 +73,54 @@ try {
     cnn.saveb(std::string(argv[6]));                  // train-cnn.cpp:115; sees the twin's updates
     cnn.loadb(std::string("/nonexistent/file.cnnb")); // silent no-op
     cnn = PoseInitializerCNN("");                     // train-cnn.cpp:116 reset
+    {
+        // per-layer streams (cnn.h:286-289, 606-609): conv1's W then B is the first 416 floats of the .cnnb order
+        auto *c1 = dynamic_cast<CNN::LConv *>(cnn.layers[0]);
+        std::ostringstream whole, part;
+        cnn.saveb(whole);
+        c1->saveb(part);
+        if (part.str().size() != 416 * 4 || whole.str().compare(0, 416 * 4, part.str()) != 0) throw std::runtime_error("LConv::saveb differs from the net's prefix");
+        std::stringstream txt;
+        txt << *c1;                                   // operator<<, cnn.h:607
+        std::vector<float> v;
+        for (float w; txt >> w;) v.push_back(w);
+        if (v.size() != 416) throw std::runtime_error("operator<< (LConv) wrote a wrong number of values");
+        std::stringstream in;
+        for (size_t i = 0; i < v.size(); i++) in << (float)i << ' ';
+        in >> *c1;                                    // operator>>, cnn.h:606
+        std::ostringstream again;
+        cnn.saveb(again);
+        const float *p = reinterpret_cast<const float *>(again.str().data());
+        for (int i = 0; i < 416; i++)
+            if (p[i] != (float)i) throw std::runtime_error("operator>> (LConv) did not reach the device store");
+        if (again.str().compare(416 * 4, std::string::npos, whole.str(), 416 * 4, std::string::npos) != 0) throw std::runtime_error("operator>> (LConv) touched other layers");
+        auto *f2 = dynamic_cast<CNN::LFull *>(cnn.layers[9]);
+        std::ostringstream fpart;
+        f2->saveb(fpart);                             // fc2: the last (2048 + 1) * 2304 floats
+        if (fpart.str().size() != (size_t)(2048 + 1) * 2304 * 4 ||
+            again.str().compare(again.str().size() - fpart.str().size(), std::string::npos, fpart.str()) != 0)
+            throw std::runtime_error("LFull::saveb differs from the net's suffix");
+    }
+    {
+        // copies taken BEFORE the device net exists share one weight store too (handtrack.h:129 returns by value)
+        CNN a({});
+        a.layers = cnn.layers;
+        CNN b = a;
+        a.Init();
+        std::ostringstream sa, sb;
+        a.saveb(sa);
+        b.saveb(sb);
+        if (sa.str() != sb.str()) throw std::runtime_error("copy made before first use has its own weight store");
+    }
+    {
+        // layer types without kernels keep compiling and are rejected when the net is built (no CPU fallback)
+        CNN m({});
+        m.layers.push_back(new CNN::LConvS({8, 8}, 1, 2));
+        m.layers.push_back(new CNN::LActivation<ReLU>(128));
+        bool threw = false;
+        try { m.Init(); } catch (const std::exception &) { threw = true; }
+        if (!threw) throw std::runtime_error("an unsupported layer list was accepted");
+    }
     std::cout << "dropin ok\n";
     return 0;
 } catch (const std::exception &e) {
