@@ -187,6 +187,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     distributed = world > 1
+    # host threads + pinned buffers of this rank next to its GPU (matters for e2e when several ranks share the box)
+    numa = dp.bind_host_to_gpu(local) if distributed else {"bound": False, "note": "single rank"}
     if distributed:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     W, K, B = max(args.warmup, 3), args.steps, args.batch
@@ -204,6 +206,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def maxr(v):
+        t = torch.tensor([float(v)], device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def timed(fn, steps, warm):
         for _ in range(warm):
             fn()
@@ -214,21 +222,15 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if distributed:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return maxr(e0.elapsed_time(e1))
 
     # ---- headline: tensor-core inference, inputs resident in HBM -------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = net.launch_count()
-    net.profile(True)
-    # (profiling only records events around the three stages; warm-up intervals are excluded below)
     for _ in range(W):
         net.eval_batch_device(x.data_ptr(), B, y.data_ptr(), precision=hp.PRECISION_TENSOR, stream=stream)
     barrier()
-    net.profile(True)
+    net.profile(True)     # CUDA events around the three stages of every chunk, recorded on the launching stream
     l0 = net.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
@@ -241,16 +243,15 @@ def main():
     launches = net.launch_count() - l0
     stage_ms, stage_cnt = net.profile_read(3)
     net.profile(False)
-    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if distributed:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms = float(ms_t.item())
+    ms = maxr(e0.elapsed_time(e1))
     clocks = sampler.summary()
     value = world * B * K / (ms * 1e-3)
 
     pk = peaks()
-    # per-kernel rooflines from the CUDA-event stage timings recorded inside the timed region (hp_profile)
-    names = ["tc_conv_kernel (conv1+pool4+tanh, conv2+tanh+pool2)", "tc_gemm_kernel<fc1 + tanh>", "tc_gemm_kernel<fc2 + chunked softmax>"]
+    # per-kernel rooflines from the CUDA-event stage timings recorded inside the timed region (hp_profile).  `peak` is the
+    # BURST bf16 figure: the whole timed region lasts tens of milliseconds at full clocks (see `clocks`), far from the
+    # seconds-long power-capped regime the sustained figure describes; frac_of_sustained is given beside it.
+    names = ["tc_conv2_kernel (conv1+pool4+tanh, conv2+tanh+pool2)", "tc_gemm_kernel<fc1 + tanh>", "tc_gemm_kernel<fc2 + chunked softmax>"]
     flops = [CONV_FLOP, FC1_FLOP, FC2_FLOP]
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from ncu --set full
@@ -261,25 +262,42 @@ def main():
         launch_ms = stage_ms[i] / max(stage_cnt[i], 1)
         crops_per_launch = B * K / max(stage_cnt[i], 1)
         ach = flops[i] * crops_per_launch / max(launch_ms * 1e-3, 1e-12) / 1e12
-        per_kernel.append({"kernel": names[i], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                           "frac": ach / pk["bf16_tflops_sustained"], "launch_ms": launch_ms, "crops_per_launch": crops_per_launch,
-                           "algorithmic_flop_per_crop": flops[i], "share_of_step": stage_ms[i] / max(sum(stage_ms), 1e-9),
-                           "traffic": traffic.get(("tc_conv_kernel", "tc_gemm_kernel<0>", "tc_gemm_kernel<1>")[i])})
+        per_kernel.append({"kernel": names[i], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                           "frac": ach / pk["bf16_tflops"], "frac_of_sustained": ach / pk["bf16_tflops_sustained"], "launch_ms": launch_ms,
+                           "crops_per_launch": crops_per_launch, "algorithmic_flop_per_crop": flops[i],
+                           "share_of_step": stage_ms[i] / max(sum(stage_ms), 1e-9),
+                           "traffic": traffic.get(("tc_conv2_kernel", "tc_gemm_kernel<0>", "tc_gemm_kernel<1>")[i])})
     dom = max(range(3), key=lambda i: stage_ms[i])
     roofline = dict(per_kernel[dom])
-    roofline["peak_source"] = pk["source"] + ", sustained bf16 (kernels are timed inside a long step)"
+    roofline["peak_source"] = pk["source"] + ", burst bf16 (cuBLAS 8192^3 best of 10); sustained %.1f" % pk["bf16_tflops_sustained"]
     roofline["all_kernels"] = per_kernel
-    roofline["whole_step"] = {"achieved": FLOP_PER_CROP * value / world / 1e12, "unit": "TFLOP/s",
-                              "frac": FLOP_PER_CROP * value / world / 1e12 / pk["bf16_tflops_sustained"]}
+    whole = FLOP_PER_CROP * value / world / 1e12
+    roofline["whole_step"] = {"achieved": whole, "unit": "TFLOP/s", "frac": whole / pk["bf16_tflops"], "frac_of_sustained": whole / pk["bf16_tflops_sustained"]}
 
-    line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+    line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_requested": args.warmup,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate",
+            "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[1]: handposedd batched inference, %d synthetic uniform[0,1) 64x64 crops per GPU "
                                    "per step, Init() weights (assets/handposedd.cnnb absent), tensor-core path" % B,
                        "crops_per_gpu": B, "parallelism": "replicated weights, batch sharded, no collective",
-                       "l2_policy": "inputs (1 GiB/GPU) exceed the 126 MB L2"},
+                       "l2_policy": "inputs (1 GiB/GPU) exceed the 126 MB L2", "host_numa": numa},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
 
+    # ---- parity of the timed batch: a 1,024-crop slice (strided over all 65,536) against the CPU oracle -------------
+    if rank == 0:
+        try:
+            from oracle import oracle as orc
+            pick = torch.arange(0, B, max(B // 1024, 1), device=dev)[:1024]
+            want = orc.eval_mt(net.get_params(), x[pick].cpu().numpy())
+            got = y[pick].cpu().numpy()
+            errs = np.abs(got.astype(np.float64) - want).max(axis=1) / np.abs(want).max(axis=1)
+            line["parity_check"] = {"what": "1,024 crops of the timed 65,536-crop batch vs the CPU oracle (oracle/handposedd_oracle.c, pinned to the "
+                                            "unmodified cnn.h), max-normalised error per crop", "crops": int(len(pick)), "worst": float(errs.max()),
+                                    "median": float(np.median(errs)), "bound": 1e-2, "ok": bool(errs.max() <= 1e-2)}
+        except Exception as e:
+            line["parity_check"] = {"error": str(e)[:200]}
+
+    train_scaling = None
     if not args.no_extras:
         # ---- FP32-exact arm (same workload, fewer steps: it is ~FFMA-bound) ----------------------
         k32 = max(1, min(K, 2))
@@ -298,26 +316,32 @@ def main():
         for _ in range(ke):
             net.eval_batch(xh.numpy(), out=yh.numpy(), precision=hp.PRECISION_TENSOR)
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev)
-        if distributed:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        line["e2e"] = {"value": world * B * ke / float(dt.item()), "unit": "crops/s", "h2d_bytes_per_step": B * 4096 * 4,
+        dt = maxr(time.perf_counter() - t0)
+        line["e2e"] = {"value": world * B * ke / dt, "unit": "crops/s", "h2d_bytes_per_step": B * 4096 * 4,
                        "d2h_bytes_per_step": B * 2304 * 4, "api": "hp_eval_batch (host buffers, pinned; chunked H2D/compute/D2H overlap)"}
-        # the PCIe ceiling this number lives under: a bare pinned H2D copy of the same 1 GiB
+        # the PCIe ceiling this number lives under: a bare pinned H2D copy of the same 1 GiB, ALL ranks at once
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         xdst = torch.empty_like(x)
         xdst.copy_(xh, non_blocking=True)
-        torch.cuda.synchronize()
+        barrier()
         c0.record()
         xdst.copy_(xh, non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
         h2d_gbs = B * 4096 * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        line["e2e"]["pcie_h2d_gbs_measured"] = h2d_gbs
-        line["e2e"]["frac_of_pcie_bound"] = (line["e2e"]["value"] / world) * 4096 * 4 / 1e9 / h2d_gbs
+        per_rank = [h2d_gbs]
+        if distributed:
+            g = torch.zeros(world, device=dev)
+            g[rank] = h2d_gbs
+            dist.all_reduce(g)
+            per_rank = [float(v) for v in g.cpu()]
+        line["e2e"]["pcie_h2d_gbs_measured"] = min(per_rank)
+        line["e2e"]["pcie_h2d_gbs_concurrent_per_rank"] = per_rank
+        line["e2e"]["frac_of_pcie_bound"] = (line["e2e"]["value"] / world) * 4096 * 4 / 1e9 / min(per_rank)
+        line["e2e"]["fabric_ceiling_crops_per_s"] = sum(per_rank) * 1e9 / (4096 * 4)
         del xdst
         # same call chain as handtrack.h:700-702 through the compact entry point: 16-bit depth crops up (8 KB/crop),
-        # normalise + Eval + decode on the device, 48 decoded floats down (192 B/crop)
+        # normalise (inside the conv loader) + Eval + decode on the device, 48 decoded floats down (192 B/crop)
         dh = torch.randint(0, 1200, (B, 4096), dtype=torch.int32).to(torch.int16).pin_memory()
         dech = torch.empty((B, 48), dtype=torch.float32).pin_memory()
         dnp = dh.numpy().view(np.uint16)
@@ -327,71 +351,31 @@ def main():
         for _ in range(ke):
             net.eval_depth_batch(dnp, precision=hp.PRECISION_TENSOR, want_y=False, out_dec=dech.numpy())
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev)
-        if distributed:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        line["e2e_depth_in_decoded_out"] = {"value": world * B * ke / float(dt.item()), "unit": "crops/s", "h2d_bytes_per_step": B * 4096 * 2,
+        dt = maxr(time.perf_counter() - t0)
+        line["e2e_depth_in_decoded_out"] = {"value": world * B * ke / dt, "unit": "crops/s", "h2d_bytes_per_step": B * 4096 * 2,
                                             "d2h_bytes_per_step": B * 48 * 4,
-                                            "api": "hp_eval_depth_batch (u16 depth in, handtrack.h:700 normalisation + Eval + CNNOutputAnalysis decode on device)"}
-        del xh, yh, dh, dech
+                                            "api": "hp_eval_depth_batch (u16 depth in, handtrack.h:700 normalisation in the conv loader + Eval + "
+                                                   "CNNOutputAnalysis decode on device); the documented ingest for multi-GPU boxes",
+                                            "frac_of_fabric_ceiling": (world * B * ke / dt) * 4096 * 2 / 1e9 / sum(per_rank)}
+        # device-resident u16 depth -> y + decoded (what the GPU sustains when PCIe is out of the picture)
+        dd = dh.to(dev)
+        decd = torch.empty((B, 48), device=dev)
+        msd = timed(lambda: net.eval_depth_batch_device(dd.data_ptr(), B, y.data_ptr(), decd.data_ptr(), precision=hp.PRECISION_TENSOR, stream=stream),
+                    max(2, min(K, 10)), 2)
+        line["device_u16_in_decoded_out"] = {"value": world * B * max(2, min(K, 10)) / (msd * 1e-3), "unit": "crops/s",
+                                             "api": "hp_eval_depth_batch_device", "hbm_in_bytes_per_crop": 8192}
+        del xh, yh, dh, dech, dd, decd
 
-        # ---- training arm: minibatch 256 per GPU, FP32 path, NCCL all-reduce when N > 1 ----------
+        # ---- training arm ---------------------------------------------------------------------------
         try:
-            from hand_tracking_samples_b200 import synth
-            TB = args.train_batch
-            tx = torch.rand((TB, 4096), device=dev, generator=gen)
-            tt = torch.from_numpy(synth.heatmap_labels(TB, 4321 + rank)).to(dev)
-            mse = torch.empty(TB, device=dev)
-            exchange = "none (1 GPU)"
-            if distributed:
-                try:
-                    dp.init_data_parallel(net, mode="peer")
-                    exchange = ("one kernel per gradient bucket (fc2 | fc1 | conv) over NVLink peer memory behind backward: reduce-scatter of the "
-                                "9,458,400 fp32 gradient sums + SGD + all-gather of the updated weights (csrc/hp_peer.cu); bf16-shadow refresh "
-                                "per bucket on a third stream")
-                except Exception as e:
-                    dp.init_data_parallel(net, mode="nccl")
-                    exchange = "NCCL all-reduce + local SGD (peer-memory path unavailable: %s)" % str(e)[:120]
-            kt = max(min(K, 200), 20)
-            line["train"] = {}
-            for name, prec in (("tensor", hp.PRECISION_TENSOR), ("fp32", hp.PRECISION_FP32)):
-                mst = timed(lambda: net.train_batch_device(tx.data_ptr(), tt.data_ptr(), TB, 0.001 / (TB * world), mse.data_ptr(),
-                                                           precision=prec, stream=stream), kt, 3)
-                line["train"][name] = {"value": world * TB * kt / (mst * 1e-3), "unit": "samples/s", "batch_per_gpu": TB, "steps": kt,
-                                       "ms_per_step": mst / kt, "tflops": FLOP_PER_TRAIN_SAMPLE * TB * kt / (mst * 1e-3) / 1e12,
-                                       "final_mse": float(mse.mean().item())}
-            line["train"]["exchange"] = exchange
-            # compute-dominated point: 2048 samples per GPU per step
-            TL = 2048
-            txl = torch.rand((TL, 4096), device=dev, generator=gen)
-            ttl = tt.repeat(TL // TB, 1).contiguous()
-            msel = torch.empty(TL, device=dev)
-            ktl = max(kt // 4, 10)
-            mst = timed(lambda: net.train_batch_device(txl.data_ptr(), ttl.data_ptr(), TL, 0.001 / (TL * world), msel.data_ptr(),
-                                                       precision=hp.PRECISION_TENSOR, stream=stream), ktl, 3)
-            line["train"]["tensor_batch2048"] = {"value": world * TL * ktl / (mst * 1e-3), "unit": "samples/s", "batch_per_gpu": TL,
-                                                 "ms_per_step": mst / ktl, "tflops": FLOP_PER_TRAIN_SAMPLE * TL * ktl / (mst * 1e-3) / 1e12}
-            del txl, ttl, msel
-            if distributed:
-                # comparison arm: the same step with NCCL all-reduce + local SGD kernel (fp32 wire, then opt-in bf16 wire)
-                net_n = hp.PoseInitializerCNN("", device=local)
-                dp.init_data_parallel(net_n, mode="nccl")
-                for key, bf in (("tensor_nccl", False), ("tensor_nccl_bf16_wire", True)):
-                    net_n.dp_set_bf16_gradients(bf)
-                    mst = timed(lambda: net_n.train_batch_device(tx.data_ptr(), tt.data_ptr(), TB, 0.001 / (TB * world), mse.data_ptr(),
-                                                                 precision=hp.PRECISION_TENSOR, stream=stream), kt, 3)
-                    line["train"][key] = {"value": world * TB * kt / (mst * 1e-3), "unit": "samples/s", "ms_per_step": mst / kt,
-                                          "note": "baseline exchange: NCCL all-reduce (%s) + local SGD kernel" % ("bf16 wire" if bf else "fp32 wire")}
-                dp.shutdown_data_parallel(net_n)
-                del net_n
-            line["train"]["workload"] = "BASELINE.json configs[2]: forward+backward+SGD, minibatch %d synthetic crops per GPU" % TB
+            line["train"], train_scaling = train_arm(args, net, hp, dp, dist, dev, rank, world, local, stream, gen, timed, maxr, barrier, K)
         except Exception as e:  # the training arm must not take the headline down with it
-            line["train"] = {"error": str(e)[:200]}
+            line["train"] = {"error": str(e)[:300]}
 
         # ---- BASELINE.json configs[0]: one crop at a time through the drop-in call (the reference's own usage pattern) ----
         try:
             from hand_tracking_samples_b200 import synth as _synth
-            x1, t1 = _synth.depthlike_crops(1, 3), _synth.heatmap_labels(1, 4)
+            x1 = _synth.depthlike_crops(1, 3)
             lat = {}
             for name, prec in (("fp32", hp.PRECISION_FP32), ("tensor", hp.PRECISION_TENSOR)):
                 for _ in range(20):
@@ -406,6 +390,7 @@ def main():
 
         # ---- CPU baseline: the reference's own code on this box's host cores (rank 0, bounded sample) ----
         if rank == 0:
+            dp.unbind_host()
             threads = os.cpu_count() or 1
             v1, kind, _, dt1 = cpu_baseline_eval(64, 1)
             vN, kind, used, dtN = cpu_baseline_eval(max(64, 16 * threads), threads)
@@ -413,11 +398,163 @@ def main():
                                     "sample": "%d uniform[0,1) crops, %d threads (one reference net per thread); single-thread: %.1f crops/s on 64 crops"
                                               % (max(64, 16 * threads), used, v1),
                                     "single_thread": v1}
+    if train_scaling is not None:
+        line["train_scaling"] = train_scaling      # LAST key on purpose: it must survive a tail of the line
     if rank == 0:
         emit(line)
     if distributed:
-        dp.shutdown_data_parallel(net)
         dist.destroy_process_group()
+
+
+def train_arm(args, net, hp, dp, dist, dev, rank, world, local, stream, gen, timed, maxr, barrier, K):
+    """BASELINE.json configs[2] (1 GPU) and configs[3] (data parallel): forward + backward + SGD on synthetic samples."""
+    import numpy as np
+    import torch
+    from hand_tracking_samples_b200 import capi, synth
+    distributed = world > 1
+    TB = args.train_batch
+    out = {}
+    tx = torch.rand((TB, 4096), device=dev, generator=gen)
+    tt = torch.from_numpy(synth.heatmap_labels(TB, 4321 + rank)).to(dev)
+    mse = torch.empty(TB, device=dev)
+    kt = max(min(K, 200), 20)
+
+    def step_fn(n_, xs, ts, ms_, nb, prec, scale):
+        return lambda: n_.train_batch_device(xs.data_ptr(), ts.data_ptr(), nb, 0.001 / scale, ms_.data_ptr(), precision=prec, stream=stream)
+
+    # single-GPU step on this GPU (every rank at once when distributed: the denominator of the scaling figures)
+    single = {}
+    for name, prec in (("tensor", hp.PRECISION_TENSOR), ("fp32", hp.PRECISION_FP32)):
+        mst = timed(step_fn(net, tx, tt, mse, TB, prec, TB), kt, 3)
+        single[name] = mst / kt
+        if not distributed:
+            out[name] = {"value": TB * kt / (mst * 1e-3), "unit": "samples/s", "batch_per_gpu": TB, "steps": kt, "ms_per_step": mst / kt,
+                         "tflops": FLOP_PER_TRAIN_SAMPLE * TB * kt / (mst * 1e-3) / 1e12, "final_mse": float(mse.mean().item())}
+    TL = 2048
+    txl = torch.rand((TL, 4096), device=dev, generator=gen)
+    ttl = tt.repeat(TL // TB, 1).contiguous() if TL % TB == 0 else torch.from_numpy(synth.heatmap_labels(TL, 99 + rank)).to(dev)
+    msel = torch.empty(TL, device=dev)
+    ktl = max(kt // 4, 10)
+    mst = timed(step_fn(net, txl, ttl, msel, TL, hp.PRECISION_TENSOR, TL), ktl, 3)
+    single["tensor_b2048"] = mst / ktl
+    if not distributed:
+        out["exchange"] = "none (1 GPU)"
+        out["tensor_batch2048"] = {"value": TL * ktl / (mst * 1e-3), "unit": "samples/s", "batch_per_gpu": TL, "ms_per_step": mst / ktl,
+                                   "tflops": FLOP_PER_TRAIN_SAMPLE * TL * ktl / (mst * 1e-3) / 1e12}
+        out["workload"] = "BASELINE.json configs[2]: forward+backward+SGD, minibatch %d synthetic crops per GPU" % TB
+        return out, None
+
+    # ---- data parallel (configs[3]) ---------------------------------------------------------------------------------
+    mode = "peer"
+    try:
+        dp.init_data_parallel(net, mode="peer")
+        exchange = ("one kernel per gradient bucket (fc2 | fc1 | conv) over NVLink peer memory behind backward: reduce-scatter of the "
+                    "9,458,400 fp32 gradient sums + SGD + all-gather of the updated weights (csrc/hp_peer.cu)")
+    except Exception as e:
+        dp.init_data_parallel(net, mode="nccl")
+        mode = "nccl"
+        exchange = "NCCL all-reduce + local SGD (peer-memory path unavailable: %s)" % str(e)[:120]
+    out["exchange"] = exchange
+    sc = {"n": world, "mode": mode, "single_gpu_step_us": {k: round(v * 1e3, 1) for k, v in single.items()}}
+    # weak scaling: TB and 2048 samples per GPU
+    for key, xs, ts, ms_, nb, k_, ref in (("weak_b%d" % TB, tx, tt, mse, TB, kt, single["tensor"]), ("weak_b2048", txl, ttl, msel, TL, ktl, single["tensor_b2048"])):
+        mst = timed(step_fn(net, xs, ts, ms_, nb, hp.PRECISION_TENSOR, nb * world), k_, 3)
+        sc[key] = {"step_us": round(mst / k_ * 1e3, 1), "samples_s": round(world * nb * k_ / (mst * 1e-3)), "eff": round(ref / (mst / k_), 3)}
+    out["tensor"] = {"value": sc["weak_b%d" % TB]["samples_s"], "unit": "samples/s", "batch_per_gpu": TB, "ms_per_step": sc["weak_b%d" % TB]["step_us"] / 1e3}
+    mst = timed(step_fn(net, tx, tt, mse, TB, hp.PRECISION_FP32, TB * world), max(kt // 4, 10), 2)
+    out["fp32"] = {"value": world * TB * max(kt // 4, 10) / (mst * 1e-3), "unit": "samples/s", "ms_per_step": mst / max(kt // 4, 10)}
+    # strong scaling: the same 256-sample global batch cut over the ranks (SURVEY.md 8d config 4: cannot be near-linear,
+    # the per-GPU compute shrinks to a few tens of microseconds while the exchanged bytes stay)
+    ns = max(TB // world, 1)
+    mst = timed(step_fn(net, tx, tt, mse, ns, hp.PRECISION_TENSOR, ns * world), kt, 3)
+    sc["strong_b%d_global" % (ns * world)] = {"per_gpu": ns, "step_us": round(mst / kt * 1e3, 1), "samples_s": round(world * ns * kt / (mst * 1e-3)),
+                                              "speedup_vs_1gpu": round(single["tensor"] / (mst / kt), 3)}
+    # exchange report from a step timeline (timing-enabled events cost ~20 us per step, hence a separate short run)
+    try:
+        os.environ["HP_STEP_TIMING"] = "1"
+        net_t = hp.PoseInitializerCNN("", device=local)
+        del os.environ["HP_STEP_TIMING"]
+        dp.init_data_parallel(net_t, mode=mode)
+        for _ in range(12):
+            net_t.train_batch_device(tx.data_ptr(), tt.data_ptr(), TB, 0.001 / (TB * world), mse.data_ptr(), precision=hp.PRECISION_TENSOR, stream=stream)
+        torch.cuda.synchronize()
+        tms = np.zeros(9, np.float32)
+        capi.check(net_t.L.hp_debug_step_times(net_t.h, tms.ctypes.data))
+        ready, ar, tail = tms[0:3] * 1e3, tms[5:8] * 1e3, float(tms[8] * 1e3)
+        busy = 0.0
+        prev = 0.0
+        for b in range(3):
+            start = max(float(ready[b]), prev)
+            busy += max(float(ar[b]) - start, 0.0)
+            prev = float(ar[b])
+        exposed = max(tail - float(ready[2]), 0.0)     # what follows the end of backward
+        wire = 2.0 * (world - 1) / world * 37833600
+        sc["exchange"] = {"bucket_ready_us": [round(float(v)) for v in ready], "exchange_done_us": [round(float(v)) for v in ar], "tail_us": round(tail),
+                          "exchange_busy_us": round(busy), "exposed_after_backward_us": round(exposed),
+                          "overlap_frac": round(1.0 - exposed / max(busy, 1e-6), 3),
+                          "wire_MB_per_gpu": round(wire / 1e6, 1), "bus_GBps": round(wire / max(busy, 1e-6) / 1e3, 1)}
+        dp.shutdown_data_parallel(net_t)
+        del net_t
+    except Exception as e:
+        sc["exchange"] = {"error": str(e)[:160]}
+    # comparison arm: NCCL all-reduce + local SGD kernel, same step
+    try:
+        net_n = hp.PoseInitializerCNN("", device=local)
+        dp.init_data_parallel(net_n, mode="nccl")
+        mst = timed(step_fn(net_n, tx, tt, mse, TB, hp.PRECISION_TENSOR, TB * world), kt, 3)
+        sc["nccl_b%d" % TB] = {"step_us": round(mst / kt * 1e3, 1), "samples_s": round(world * TB * kt / (mst * 1e-3))}
+        dp.shutdown_data_parallel(net_n)
+        del net_n
+    except Exception as e:
+        sc["nccl_b%d" % TB] = {"error": str(e)[:120]}
+    # correctness of the exchange, visible to the driver: every rank ends bit-identical, and the step equals the single-GPU
+    # step on the concatenated batch (FP32 path <= 2e-5, tensor path <= 1e-2 of the update)
+    try:
+        sc["dp_check"] = dp_check(hp, dp, dist, dev, local, rank, world, stream, mode)
+    except Exception as e:
+        sc["dp_check"] = {"error": str(e)[:200]}
+    dp.shutdown_data_parallel(net)
+    out["workload"] = "BASELINE.json configs[3]: data-parallel forward+backward+SGD, minibatch %d synthetic crops per GPU (weak) / %d global (strong)" % (TB, ns * world)
+    return out, sc
+
+
+def dp_check(hp, dp, dist, dev, local, rank, world, stream, mode, n_per=32):
+    import numpy as np
+    import torch
+    from hand_tracking_samples_b200 import synth
+    xs = [synth.depthlike_crops(n_per, 700 + r) for r in range(world)]
+    ts = [synth.heatmap_labels(n_per, 800 + r) for r in range(world)]
+    xd, td = torch.from_numpy(xs[rank]).to(dev), torch.from_numpy(ts[rank]).to(dev)
+    xall, tall = np.concatenate(xs), np.concatenate(ts)
+    res = {"samples_per_rank": n_per, "steps": 2}
+    ok_all = True
+    for name, prec, tol in (("fp32", hp.PRECISION_FP32, 2e-5), ("tensor", hp.PRECISION_TENSOR, 1e-2)):
+        net_d = hp.PoseInitializerCNN("", device=local)
+        p0 = net_d.get_params()
+        dp.init_data_parallel(net_d, mode=mode)
+        for _ in range(2):
+            net_d.train_batch_device(xd.data_ptr(), td.data_ptr(), n_per, 0.001, None, precision=prec, stream=stream)
+        torch.cuda.synchronize()
+        p_dp = net_d.get_params()
+        mine = torch.from_numpy(p_dp).to(dev)
+        ref0 = mine.clone()
+        dist.broadcast(ref0, 0)
+        same = torch.tensor([1.0 if torch.equal(mine, ref0) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        ref = hp.PoseInitializerCNN("", device=local)
+        for _ in range(2):
+            ref.train_batch(xall, tall, 0.001, precision=prec)
+        p1 = ref.get_params()
+        rel = float(np.abs((p_dp - p0) - (p1 - p0)).max() / np.abs(p1 - p0).max())
+        relt = torch.tensor([rel], device=dev)
+        dist.all_reduce(relt, op=dist.ReduceOp.MAX)
+        ok = bool(same.item() == 1.0) and float(relt.item()) <= tol
+        ok_all = ok_all and ok
+        res[name] = {"ranks_bit_identical": bool(same.item() == 1.0), "update_err_vs_1gpu": float(relt.item()), "bound": tol}
+        dp.shutdown_data_parallel(net_d)
+        del net_d, ref
+    res["ok"] = ok_all
+    return res
 
 
 if __name__ == "__main__":

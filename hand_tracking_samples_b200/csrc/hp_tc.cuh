@@ -44,12 +44,25 @@ __device__ __forceinline__ float tanh_tc(float t)
     return fmaf(-2.0f, r, 1.0f) + (e - e);
 }
 
+// The conv-stage epilogues sit on the critical ring of the fused conv kernel (accumulator drain -> tanh -> p1 -> conv2
+// MMAs), where two MUFU ops per value are measurable; their outputs are rounded to fp16 (2^-11) anyway, so there the
+// single-MUFU tanh.approx (2^-11 relative) is used, with the reference's overflow-to-NaN quirk kept by a select
+// (t > 44.3614: exp(2t) overflows in fp32, cnn.h:31).  `accurate` (HP_CONV_TANH=accurate) switches back for A/B runs.
+__device__ __forceinline__ float tanh_conv(float t, bool accurate)
+{
+    if (accurate) return tanh_tc(t);
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(t));
+    return (t > 44.3614f) ? __int_as_float(0x7fc00000) : y;
+}
+
 struct TcState {
     // 16-bit shadows of the weights (fp16 for the forward operands, bf16 for the backward ones), in the layouts the MMAs consume (rebuilt by tc_refresh_weights)
     act_t *w1t = nullptr;          // [2048][2304] = fc1.W^T, k contiguous, k in HWC flatten order (pp*64+co)
     act_t *w2t = nullptr;          // [2304][2048] = fc2.W^T
     uint8_t *b1_img = nullptr;     // 32 KB: conv1 as pooled-window GEMM, B operand [256 (pos,co)][64 (r,c)] fp16, 128B-swizzled image
     uint8_t *a2_img = nullptr;     // 32 KB: conv2 weights as the TMEM-resident A operand of the v2 conv kernel, [128 (2co+g)][128 k] fp16
+    bool conv_tanh_accurate = false;   // HP_CONV_TANH=accurate: two-MUFU tanh in the conv epilogues too (A/B runs)
     bool conv_v1 = false;          // HP_CONV_V1=1: run the round-1 conv kernel (hp_tc_conv.cu) instead of hp_tc_conv2.cu
     uint8_t *b2_img = nullptr;     // 32 KB: conv2 taps, [16 taps][2 k-chunks][64 co][8 ci] fp16 (no-swizzle core matrices)
     __nv_bfloat16 *w1b = nullptr;  // [2304 (k' HWC)][2048] = fc1.W as stored (B operand of the fc1 dX GEMM)

@@ -81,9 +81,10 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(cv::THREADS, 1)
 tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, const uint8_t *__restrict__ b2_img,
                const float *__restrict__ params, act_t *__restrict__ p2_out, int n, float *__restrict__ p1_out,
-               uint8_t *__restrict__ idx1_out, uint8_t *__restrict__ idx2_out)
+               uint8_t *__restrict__ idx1_out, uint8_t *__restrict__ idx2_out, int tanh_accurate)
 {
     using namespace cv;
+    const bool acc_tanh = tanh_accurate != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float *bias1 = reinterpret_cast<float *>(smem + OFF_BIAS);
@@ -275,7 +276,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++)
-                        pk[j] = pack_act(tanh_tc(mx[2 * j] + bias1[2 * j]), tanh_tc(mx[2 * j + 1] + bias1[2 * j + 1]));
+                        pk[j] = pack_act(tanh_conv(mx[2 * j] + bias1[2 * j], acc_tanh), tanh_conv(mx[2 * j + 1] + bias1[2 * j + 1], acc_tanh));
                     const int q = py * 15 + px;
                     *reinterpret_cast<uint4 *>(planes + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4 *>(planes + P1_PLANE + q * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -364,7 +365,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                         const __half2 m23 = __hmax2(*reinterpret_cast<const __half2 *>(pc + k), *reinterpret_cast<const __half2 *>(pd + k));
                         const float2 f = __half22float2(__hmax2(m01, m23));
                         const int co = chunk * 8 + 2 * k;
-                        o[k] = pack_act(tanh_tc(f.x + bias2[co]), tanh_tc(f.y + bias2[co + 1]));
+                        o[k] = pack_act(tanh_conv(f.x + bias2[co], acc_tanh), tanh_conv(f.y + bias2[co + 1], acc_tanh));
                     }
                     *reinterpret_cast<uint4 *>(p2_out + crop * P2_N + pp * 64 + chunk * 8) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -386,7 +387,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
                         if (vc[k] > m) { m = vc[k]; arg = 2; }
                         if (vd[k] > m) { m = vd[k]; arg = 3; }
                         const int co = chunk * 4 + k;
-                        o[k] = tanh_tc(m + bias2[co]);
+                        o[k] = tanh_conv(m + bias2[co], acc_tanh);
                         idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg;
                     }
                     *reinterpret_cast<uint2 *>(p2_out + crop * P2_N + pp * 64 + chunk * 4) = make_uint2(pack_act(o[0], o[1]), pack_act(o[2], o[3]));
@@ -486,6 +487,7 @@ int tc_conv_init(Net &net)
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM));
     t->conv_v1 = getenv("HP_CONV_V1") != nullptr;
+    if (const char *e = getenv("HP_CONV_TANH")) t->conv_tanh_accurate = e[0] == 'a';
     return tc_conv2_init(net);
 }
 
@@ -502,7 +504,7 @@ int tc_conv_stage(Net &net, const float *x, int64_t n, act_t *p2_bf, cudaStream_
     TcState *t = net.tc;
     if (!t->conv_v1) return tc_conv2_stage(net, x, n, p2_bf, s);
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv_kernel<false><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, nullptr, nullptr, nullptr);
+    tc_conv_kernel<false><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;
 }
@@ -513,7 +515,7 @@ int tc_conv_stage_train(Net &net, const float *x, int64_t n, act_t *p2_bf, cudaS
     TcState *t = net.tc;
     if (!t->conv_v1) return tc_conv2_stage_train(net, x, n, p2_bf, s);
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv_kernel<true><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2);
+    tc_conv_kernel<true><<<grid, cv::THREADS, cv::SMEM, s>>>(x, t->b1_img, t->b2_img, net.params, p2_bf, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;
 }

@@ -83,9 +83,10 @@ template <bool TRAIN, bool U16>
 __global__ void __launch_bounds__(cv2::THREADS, 1)
 tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *__restrict__ b1_img, const uint4 *__restrict__ a2_img,
                 const float *__restrict__ params, act_t *__restrict__ p2_out, int n, float *__restrict__ p1_out,
-                uint8_t *__restrict__ idx1_out, uint8_t *__restrict__ idx2_out)
+                uint8_t *__restrict__ idx1_out, uint8_t *__restrict__ idx2_out, int tanh_accurate)
 {
     using namespace cv2;
+    const bool acc_tanh = tanh_accurate != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float *bias1 = reinterpret_cast<float *>(smem + OFF_BIAS);
@@ -246,7 +247,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                 uint32_t pk[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++)
-                    pk[j] = pack_act(tanh_tc(mx[2 * j] + bias1[2 * j]), tanh_tc(mx[2 * j + 1] + bias1[2 * j + 1]));
+                    pk[j] = pack_act(tanh_conv(mx[2 * j] + bias1[2 * j], acc_tanh), tanh_conv(mx[2 * j + 1] + bias1[2 * j + 1], acc_tanh));
                 const int q = py * P1_PITCH + px;
                 *reinterpret_cast<uint4 *>(planes + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4 *>(planes + P1_PLANE + q * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -335,7 +336,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
 #pragma unroll
                 for (int pxx = 0; pxx < 6; pxx++) {
                     const int pp = (3 * g + s) * 6 + pxx;
-                    p2_out[crop * P2_N + pp * 64 + co] = __float2half_rn(tanh_tc(best[s][pxx] + b2));
+                    p2_out[crop * P2_N + pp * 64 + co] = __float2half_rn(tanh_conv(best[s][pxx] + b2, acc_tanh));
                     if (TRAIN) idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg[s][pxx];
                 }
             }
@@ -426,7 +427,7 @@ int tc_conv2_stage(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t 
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
     tc_conv2_kernel<false, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
-                                                                       net.params, p2, (int)n, nullptr, nullptr, nullptr);
+                                                                       net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;
 }
@@ -437,7 +438,7 @@ int tc_conv2_stage_u16(Net &net, const uint16_t *depth, int64_t n, float depth_s
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
     tc_conv2_kernel<false, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(depth, DepthNormArgs{depth_scale, dmin, dmax - dmin}, t->b1_img,
-                                                                      reinterpret_cast<const uint4 *>(t->a2_img), net.params, p2, (int)n, nullptr, nullptr, nullptr);
+                                                                      reinterpret_cast<const uint4 *>(t->a2_img), net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;
 }
@@ -448,7 +449,7 @@ int tc_conv2_stage_train(Net &net, const float *x, int64_t n, act_t *p2, cudaStr
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
     tc_conv2_kernel<true, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
-                                                                      net.params, p2, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2);
+                                                                      net.params, p2, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;
 }

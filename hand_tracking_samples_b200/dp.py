@@ -32,6 +32,56 @@ def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+_ORIG_AFFINITY = None
+
+
+def unbind_host():
+    """Undo bind_host_to_gpu (e.g. before a CPU-side job that should use every core)."""
+    if _ORIG_AFFINITY is not None:
+        os.sched_setaffinity(0, _ORIG_AFFINITY)
+
+
+def bind_host_to_gpu(local_rank):
+    """Pin this process's host threads to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging
+    buffers it allocates afterwards (first touch) and the threads that fill them are local to the GPU's PCIe root
+    (matters for the host-buffer entry points when several ranks share one box).  Best effort: returns a small dict
+    describing what was done, never raises."""
+    global _ORIG_AFFINITY
+    info = {"bound": False}
+    try:
+        import torch
+        if _ORIG_AFFINITY is None:
+            _ORIG_AFFINITY = os.sched_getaffinity(0)
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        node_path = "/sys/bus/pci/devices/%s/numa_node" % bus
+        node = int(open(node_path).read().strip())
+        info.update(pci=bus, numa_node=node)
+        if node < 0:
+            return info
+        cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:  # containers without sysfs access, CPU-only hosts, ...
+        info["note"] = str(e)[:80]
+    return info
+
+
 def broadcast_bytes(data, src=0):
     """Broadcast a small bytes object from `src` over the default torch.distributed group
     (works on gloo and nccl)."""

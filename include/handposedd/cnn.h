@@ -113,15 +113,21 @@ struct CNN {
         void bind(std::shared_ptr<handposedd::NetHolder> h, int64_t first, int64_t count) { holder_ = h; first_ = first; count_ = count; }
 
       private:
+        std::shared_ptr<handposedd::NetHolder> owner() const
+        {
+            auto h = holder_.lock();
+            if (!h || !h->h) throw std::runtime_error("handposedd: layer is not part of a live, built CNN (its weights live in the net's device store)");
+            return h;
+        }
         std::vector<float> fetch() const
         {
-            if (!holder_ || !holder_->h) throw std::runtime_error("handposedd: layer is not part of a built CNN (its weights live in the net's device store)");
             std::vector<float> p((size_t)count_);
-            handposedd::check(hp_get_params_range(holder_->h, first_, count_, p.data()));
+            handposedd::check(hp_get_params_range(owner()->h, first_, count_, p.data()));
             return p;
         }
-        void store(const std::vector<float> &p) { handposedd::check(hp_set_params_range(holder_->h, first_, count_, p.data())); }
-        std::shared_ptr<handposedd::NetHolder> holder_;
+        void store(const std::vector<float> &p) { handposedd::check(hp_set_params_range(owner()->h, first_, count_, p.data())); }
+        // weak: the layer objects are never freed (like the reference's), they must not keep a device net alive
+        std::weak_ptr<handposedd::NetHolder> holder_;
         int64_t first_ = 0, count_ = 0;
     };
     struct LConv final : public LWeighted {  // cnn.h:194-290

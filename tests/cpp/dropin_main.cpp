@@ -88,17 +88,18 @@ try {
         std::stringstream in;
         for (size_t i = 0; i < v.size(); i++) in << (float)i << ' ';
         in >> *c1;                                    // operator>>, cnn.h:606
-        std::ostringstream again;
-        cnn.saveb(again);
-        const float *p = reinterpret_cast<const float *>(again.str().data());
+        std::ostringstream again_s;
+        cnn.saveb(again_s);
+        const std::string again_bytes = again_s.str();
+        const float *p = reinterpret_cast<const float *>(again_bytes.data());
         for (int i = 0; i < 416; i++)
             if (p[i] != (float)i) throw std::runtime_error("operator>> (LConv) did not reach the device store");
-        if (again.str().compare(416 * 4, std::string::npos, whole.str(), 416 * 4, std::string::npos) != 0) throw std::runtime_error("operator>> (LConv) touched other layers");
+        if (again_bytes.compare(416 * 4, std::string::npos, whole.str(), 416 * 4, std::string::npos) != 0) throw std::runtime_error("operator>> (LConv) touched other layers");
         auto *f2 = dynamic_cast<CNN::LFull *>(cnn.layers[9]);
         std::ostringstream fpart;
         f2->saveb(fpart);                             // fc2: the last (2048 + 1) * 2304 floats
         if (fpart.str().size() != (size_t)(2048 + 1) * 2304 * 4 ||
-            again.str().compare(again.str().size() - fpart.str().size(), std::string::npos, fpart.str()) != 0)
+            again_bytes.compare(again_bytes.size() - fpart.str().size(), std::string::npos, fpart.str()) != 0)
             throw std::runtime_error("LFull::saveb differs from the net's suffix");
     }
     {
