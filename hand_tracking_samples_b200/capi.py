@@ -21,7 +21,7 @@ PEER_HANDLE_BYTES = 256
 SYMBOLS = [
     "hp_create", "hp_create_handposedd", "hp_retain", "hp_destroy", "hp_init_xavier", "hp_load_cnnb",
     "hp_save_cnnb", "hp_get_params_range", "hp_set_params_range", "hp_load_cnnb_file", "hp_save_cnnb_file", "hp_eval_batch", "hp_eval_batch_device",
-    "hp_decode_batch", "hp_decode_batch_device", "hp_eval_decode_batch", "hp_eval_depth_batch", "hp_eval_depth_batch_device", "hp_normalize_depth_device",
+    "hp_decode_batch", "hp_decode_batch_device", "hp_eval_decode_batch", "hp_eval_depth_batch", "hp_eval_depth_batch_device", "hp_normalize_depth_device", "hp_resample_depth_device", "hp_eval_frames_device",
     "hp_render_labels", "hp_render_labels_device", "hp_train_batch_points",
     "hp_train_batch", "hp_train_batch_device", "hp_grad_batch_device", "hp_get_grads", "hp_device_ptrs",
     "hp_apply_grads_device", "hp_dp_unique_id", "hp_dp_init", "hp_dp_set_bf16_gradients", "hp_dp_peer_export", "hp_dp_peer_init", "hp_dp_peer_status", "hp_dp_shutdown", "hp_launch_count", "hp_debug_step_times", "hp_profile", "hp_profile_read",
@@ -82,6 +82,8 @@ def lib():
     L.hp_eval_decode_batch.argtypes = [vp, vp, i64, vp, vp, C.c_int]
     L.hp_eval_depth_batch.argtypes = [vp, vp, i64, fp, fp, fp, vp, vp, C.c_int]
     L.hp_eval_depth_batch_device.argtypes = [vp, vp, i64, fp, fp, fp, vp, vp, C.c_int, vp]
+    L.hp_resample_depth_device.argtypes = [vp, vp, C.c_int32, C.c_int32, C.POINTER(fp), vp, vp, i64, C.c_uint16, vp, vp]
+    L.hp_eval_frames_device.argtypes = [vp, vp, C.c_int32, C.c_int32, C.POINTER(fp), vp, vp, i64, C.c_uint16, fp, fp, fp, vp, vp, C.c_int, vp]
     L.hp_normalize_depth_device.argtypes = [vp, vp, i64, fp, fp, fp, vp, vp]
     L.hp_render_labels.argtypes = [vp, vp, vp, i64, vp]
     L.hp_render_labels_device.argtypes = [vp, vp, vp, i64, vp, vp]

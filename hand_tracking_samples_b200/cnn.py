@@ -192,6 +192,18 @@ class CNN:
         capi.check(self.L.hp_eval_depth_batch_device(self.h, depth_ptr, n, depth_scale, dmin, dmax, y_ptr, dec_ptr,
                                                      self.precision if precision is None else precision, stream))
 
+    def resample_depth_device(self, frames_ptr, width, height, src_intr, cams_ptr, n, crops_ptr, frame_of_crop_ptr=None, background=4000, stream=0):
+        """SampleD (misc_image.h:154-162): full frames -> 64x64 uint16 crops for host-computed destination cameras."""
+        intr = (C.c_float * 4)(*[float(v) for v in src_intr])
+        capi.check(self.L.hp_resample_depth_device(self.h, frames_ptr, width, height, intr, frame_of_crop_ptr, cams_ptr, n, background, crops_ptr, stream))
+
+    def eval_frames_device(self, frames_ptr, width, height, src_intr, cams_ptr, n, y_ptr, dec_ptr=None, frame_of_crop_ptr=None, background=4000,
+                           depth_scale=0.001, dmin=0.1, dmax=0.7, precision=None, stream=0):
+        """handtrack.h:698-702 on the device: resample -> normalise -> Eval -> (decode)."""
+        intr = (C.c_float * 4)(*[float(v) for v in src_intr])
+        capi.check(self.L.hp_eval_frames_device(self.h, frames_ptr, width, height, intr, frame_of_crop_ptr, cams_ptr, n, background, depth_scale, dmin,
+                                                dmax, y_ptr, dec_ptr, self.precision if precision is None else precision, stream))
+
     def train_batch_device(self, x_ptr, t_ptr, n, alpha, mse_ptr=None, precision=None, stream=0):
         capi.check(self.L.hp_train_batch_device(self.h, x_ptr, t_ptr, n, alpha, mse_ptr,
                                                 self.precision if precision is None else precision, stream))

@@ -720,6 +720,50 @@ int hp_eval_depth_batch_device(hp_net *net, const uint16_t *depth_dev, int64_t n
     return HP_OK;
 }
 
+int hp_resample_depth_device(hp_net *net, const uint16_t *frames_dev, int32_t width, int32_t height, const float src_intrinsics[4],
+                             const int32_t *frame_of_crop_dev, const float *dst_cams_dev, int64_t n, uint16_t background, uint16_t *crops_dev,
+                             void *stream)
+{
+    if (!net || n < 0 || width <= 0 || height <= 0 || !src_intrinsics || (n && (!frames_dev || !dst_cams_dev || !crops_dev))) {
+        set_error("bad argument");
+        return HP_ERR_INVALID;
+    }
+    if (n == 0) return HP_OK;
+    HP_CUDA_TRY(cudaSetDevice(net->n.device));
+    return post_sample_d(net->n, frames_dev, width, height, src_intrinsics, frame_of_crop_dev, dst_cams_dev, n, background, crops_dev,
+                         (cudaStream_t)stream);
+}
+
+int hp_eval_frames_device(hp_net *net, const uint16_t *frames_dev, int32_t width, int32_t height, const float src_intrinsics[4],
+                          const int32_t *frame_of_crop_dev, const float *dst_cams_dev, int64_t n, uint16_t background, float depth_scale,
+                          float dmin, float dmax, float *y_dev, float *decoded_dev, int precision, void *stream)
+{
+    if (!net || n < 0 || width <= 0 || height <= 0 || !src_intrinsics || (n && (!frames_dev || !dst_cams_dev || !y_dev)) || !(dmax > dmin)) {
+        set_error("bad argument");
+        return HP_ERR_INVALID;
+    }
+    if (int rc = check_precision(precision)) return rc;
+    if (n == 0) return HP_OK;
+    Net &N = net->n;
+    HP_CUDA_TRY(cudaSetDevice(N.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    // crops go through the (float-sized) staging buffer as 16-bit depth, STAGE_CHUNK crops at a time
+    for (int64_t b = 0; b < n; b += STAGE_CHUNK) {
+        const int64_t m = std::min<int64_t>(STAGE_CHUNK, n - b);
+        if (int rc = ensure_staging(N, m, false, false)) return rc;
+        uint16_t *crops = reinterpret_cast<uint16_t *>(N.dev_in[1]);
+        // without an index, crop i samples frame i: the chunk's frames start b frames further on
+        const uint16_t *fr = frame_of_crop_dev ? frames_dev : frames_dev + b * (int64_t)width * height;
+        if (int rc = post_sample_d(N, fr, width, height, src_intrinsics, frame_of_crop_dev ? frame_of_crop_dev + b : nullptr,
+                                   dst_cams_dev + b * HP_RESAMPLE_CAM_FLOATS, m, background, crops, s))
+            return rc;
+        if (int rc = hp_eval_depth_batch_device(net, crops, m, depth_scale, dmin, dmax, y_dev + b * N_OUT, decoded_dev ? decoded_dev + b * 48 : nullptr,
+                                                precision, stream))
+            return rc;
+    }
+    return HP_OK;
+}
+
 int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax, float *x_dev, void *stream)
 {
     if (!net || n < 0 || (n && (!depth_dev || !x_dev)) || !(dmax > dmin)) { set_error("bad argument"); return HP_ERR_INVALID; }

@@ -99,6 +99,8 @@ int fp32_init_attributes();
 // ---- pre/post steps (hp_post.cu) ----------------------------------------------
 int post_normalize_depth(Net &net, const uint16_t *d, int64_t n, float depth_scale, float dmin, float dmax, float *x, cudaStream_t s);
 int post_decode(Net &net, const float *y, int64_t n, float *out, cudaStream_t s);
+int post_sample_d(Net &net, const uint16_t *frames, int w, int h, const float *intr, const int32_t *frame_of_crop, const float *cams, int64_t n,
+                  uint16_t background, uint16_t *out, cudaStream_t s);
 int post_render_labels(Net &net, const float *points, const float *vals, int64_t n, float *t, cudaStream_t s);
 // ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);

@@ -3,6 +3,8 @@
 // 16 KB per crop) and download decoded peaks (192 B instead of 9 KB per crop):
 //   normalize_depth_kernel  include/handtrack.h:700   depth -> [0,1] crop:  clamp(1 - (d*scale - dmin)/(dmax - dmin), 0, 1)
 //   render_labels_kernel    include/handtrack.h:160-173 (label vector of GatherHandExpectedCNN from 8 image points + 16 key values)
+//   sample_d_kernel         include/misc_image.h:154-162 (SampleD: the rotated / scaled point resample HandSegmentVR ends with,
+//                           include/handtrack.h:343) for host-computed destination cameras
 //   decode_kernel           include/handtrack.h:218-241 (numeric core of CNNOutputAnalysis): per 2-D heatmap ImageFindMax,
 //                           PeakSubPixel, PeakVolume, peak value (include/misc_image.h:298-336); per 1-D heatmap
 //                           max_element + PeakSubPixel1D (misc_image.h:340-350, 389-399)
@@ -37,6 +39,59 @@ __global__ void __launch_bounds__(256) normalize_depth_kernel(const uint16_t *__
         }
         reinterpret_cast<float4 *>(x)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
         reinterpret_cast<float4 *>(x)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// SampleD<unsigned short> (misc_image.h:154-162) for 64x64 destination cameras: one crop per CTA, 16 pixels per thread.
+// cam[11] = destination focal xy, principal xy, pose position xyz, orientation xyzw (the data-dependent search that
+// produces it, HandSegmentVR include/handtrack.h:280-341, stays on the host).  Every operation is separately rounded in
+// the reference's order (linalg.h:284-288, misc_image.h:48-50); the float -> int conversions follow the pinned x86
+// build (cvttss2si: INT_MIN for NaN / out of range; low 16 bits for the unsigned short), see oracle/handposedd_oracle.c.
+__device__ __forceinline__ int cvtt_x86(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000u; }
+struct SrcCam {
+    int w, h;
+    float fx, fy, px, py;
+};
+__global__ void __launch_bounds__(256) sample_d_kernel(const uint16_t *__restrict__ frames, SrcCam sc, const int32_t *__restrict__ frame_of_crop,
+                                                       const float *__restrict__ cams, uint16_t background, uint16_t *__restrict__ out)
+{
+    __shared__ float c[11];
+    const int64_t crop = blockIdx.x;
+    if (threadIdx.x < 11) c[threadIdx.x] = cams[crop * 11 + threadIdx.x];
+    __syncthreads();
+    const float dfx = c[0], dfy = c[1], dpx = c[2], dpy = c[3];
+    const float pos[3] = {c[4], c[5], c[6]};
+    const float qx = c[7], qy = c[8], qz = c[9], qw = c[10];
+    auto m = [](float a, float b) { return __fmul_rn(a, b); };
+    auto ad = [](float a, float b) { return __fadd_rn(a, b); };
+    auto sb = [](float a, float b) { return __fsub_rn(a, b); };
+    const float ww = m(qw, qw), xx = m(qx, qx), yy = m(qy, qy), zz = m(qz, qz);
+    const float xd[3] = {sb(sb(ad(ww, xx), yy), zz), m(ad(m(qx, qy), m(qz, qw)), 2.f), m(sb(m(qz, qx), m(qy, qw)), 2.f)};
+    const float yd[3] = {m(sb(m(qx, qy), m(qz, qw)), 2.f), sb(ad(sb(ww, xx), yy), zz), m(ad(m(qy, qz), m(qx, qw)), 2.f)};
+    const float zd[3] = {m(ad(m(qz, qx), m(qy, qw)), 2.f), m(sb(m(qy, qz), m(qx, qw)), 2.f), ad(sb(sb(ww, xx), yy), zz)};
+    auto rot = [&](const float (&v)[3], float (&r)[3]) {   // position + (xd*v.x + yd*v.y) + zd*v.z
+#pragma unroll
+        for (int k = 0; k < 3; k++) r[k] = ad(pos[k], ad(ad(m(xd[k], v[0]), m(yd[k], v[1])), m(zd[k], v[2])));
+    };
+    float ppdir[3];
+    {
+        const float v[3] = {m(__fdiv_rn(sb(dpx, dpx), dfx), 1.0f), m(__fdiv_rn(sb(dpy, dpy), dfy), 1.0f), 1.0f};
+        rot(v, ppdir);
+    }
+    const uint16_t *src = frames + (int64_t)(frame_of_crop ? frame_of_crop[crop] : crop) * sc.w * sc.h;
+    for (int i = threadIdx.x; i < N_IN; i += 256) {
+        const int x = i & 63, y = i >> 6;
+        const float v[3] = {m(__fdiv_rn(sb((float)x, dpx), dfx), 1.0f), m(__fdiv_rn(sb((float)y, dpy), dfy), 1.0f), 1.0f};
+        float p[3];
+        rot(v, p);
+        const int ix = cvtt_x86(ad(m(__fdiv_rn(p[0], p[2]), sc.fx), sc.px)), iy = cvtt_x86(ad(m(__fdiv_rn(p[1], p[2]), sc.fy), sc.py));
+        uint16_t r = background;
+        if (ix >= 0 && ix <= sc.w - 1 && iy >= 0 && iy <= sc.h - 1) {
+            const float d = (float)src[(int64_t)iy * sc.w + ix];
+            const float s0 = m(__fdiv_rn(sb((float)ix, sc.px), sc.fx), d), s1 = m(__fdiv_rn(sb((float)iy, sc.py), sc.fy), d), s2 = m(1.0f, d);
+            r = (uint16_t)(cvtt_x86(ad(ad(m(ppdir[0], s0), m(ppdir[1], s1)), m(ppdir[2], s2))) & 0xffff);
+        }
+        out[crop * N_IN + i] = r;
     }
 }
 
@@ -179,6 +234,14 @@ int post_normalize_depth(Net &net, const uint16_t *d, int64_t n, float depth_sca
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     normalize_depth_kernel<<<blocks, 256, 0, s>>>(d, x, count8, depth_scale, dmin, dmax);
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
+int post_sample_d(Net &net, const uint16_t *frames, int w, int h, const float *intr, const int32_t *frame_of_crop, const float *cams, int64_t n,
+                  uint16_t background, uint16_t *out, cudaStream_t s)
+{
+    sample_d_kernel<<<(unsigned)n, 256, 0, s>>>(frames, SrcCam{w, h, intr[0], intr[1], intr[2], intr[3]}, frame_of_crop, cams, background, out);
     LAUNCH_CHECK(net);
     return 0;
 }

@@ -160,6 +160,26 @@ HP_API int hp_eval_depth_batch_device(hp_net *net, const uint16_t *depth_dev, in
 HP_API int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax,
                                      float *x_dev, void *stream);
 
+/* Replaces: SampleD<unsigned short> (include/misc_image.h:154-162) as HandSegmentVR calls it (include/handtrack.h:343):
+ * the rotated / scaled point resample that turns a full depth frame into the 64x64 hand crop, for destination cameras
+ * the host has already computed (the data-dependent search of HandSegmentVR, handtrack.h:280-341, stays on the host).
+ *   frames[n_frames][height][width] uint16 depth, src_intrinsics = {focal.x, focal.y, principal.x, principal.y};
+ *   dst_cams[n][11] = destination camera of each crop: focal xy, principal xy, pose position xyz, orientation xyzw
+ *                     (dims are 64x64, HandSegmentVR's dstcam);
+ *   frame_of_crop[n] (optional, NULL = crop i samples frame i);  background = HandSegmentVR's 4 m / depth_scale;
+ *   crops[n][4096] uint16, bit-exact with the reference (including its x86 float -> int conversion of NaN / out-of-range
+ *   values).  DEVICE buffers, caller's stream. */
+#define HP_RESAMPLE_CAM_FLOATS 11
+HP_API int hp_resample_depth_device(hp_net *net, const uint16_t *frames_dev, int32_t width, int32_t height, const float src_intrinsics[4],
+                                    const int32_t *frame_of_crop_dev, const float *dst_cams_dev, int64_t n, uint16_t background,
+                                    uint16_t *crops_dev, void *stream);
+/* The tracker's chain from the full frame on (include/handtrack.h:698-702) without leaving the device: resample
+ * (SampleD) -> normalise (handtrack.h:700, inside the convolution kernel's loader on the tensor path) -> Eval ->
+ * optional decode.  y_dev[n][2304] required, decoded_dev[n][48] optional. */
+HP_API int hp_eval_frames_device(hp_net *net, const uint16_t *frames_dev, int32_t width, int32_t height, const float src_intrinsics[4],
+                                 const int32_t *frame_of_crop_dev, const float *dst_cams_dev, int64_t n, uint16_t background,
+                                 float depth_scale, float dmin, float dmax, float *y_dev, float *decoded_dev, int precision, void *stream);
+
 /* Replaces: the label vector of GatherHandExpectedCNN (include/handtrack.h:160-173): RenderHeatMaps +
  * NormalizeHeatMap (include/misc_image.h:248-277) for the 8 image feature points, Render1DHeatMaps
  * (misc_image.h:279-295) for the 16 key values, u8 quantisation and c/255 (misc_image.h:169-171).

@@ -529,6 +529,46 @@ ORC_API void orc_normalize_depth(const unsigned short *d, long count, float dept
     }
 }
 
+/* ---- SURVEY.md 8f row 3, second half: SampleD (include/misc_image.h:154-162) ------------------------------------
+ * The rotated / scaled point resample at the end of HandSegmentVR (include/handtrack.h:343): for every destination
+ * pixel p, v = pose * deprojectz(p, 1) in the source camera's frame, pp = (int2)projectz_src(v) (truncation), and the
+ * sampled depth is re-expressed as distance from the DESTINATION image plane: (T)dot(ppdir, deprojectz_src(pp, d)).
+ * Arithmetic follows the reference expression by expression (third_party/linalg.h:284-288 for the quaternion rotation,
+ * misc_image.h:48-50 for the camera maps), separately rounded, left to right.  The two float -> integer conversions
+ * are undefined behaviour in C++ when out of range; the pinned x86 build resolves them with cvttss2si (INT_MIN for NaN
+ * and out-of-range values, then the low 16 bits for the unsigned short), which is restated explicitly here. */
+static int cvtt_x86(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000u; }
+ORC_API void orc_sample_d(const unsigned short *src, int w, int h, float sfx, float sfy, float spx, float spy, int dw, int dh, float dfx,
+                          float dfy, float dpx, float dpy, const float *pose7, unsigned short background, unsigned short *out)
+{
+    const float px = pose7[0], py = pose7[1], pz = pose7[2];
+    const float qx = pose7[3], qy = pose7[4], qz = pose7[5], qw = pose7[6];
+    /* qxdir / qydir / qzdir, linalg.h:284-286 */
+    const float xd[3] = {qw * qw + qx * qx - qy * qy - qz * qz, (qx * qy + qz * qw) * 2, (qz * qx - qy * qw) * 2};
+    const float yd[3] = {(qx * qy - qz * qw) * 2, qw * qw - qx * qx + qy * qy - qz * qz, (qy * qz + qx * qw) * 2};
+    const float zd[3] = {(qz * qx + qy * qw) * 2, (qy * qz - qx * qw) * 2, qw * qw - qx * qx - qy * qy + qz * qz};
+    const float pos[3] = {px, py, pz};
+    float ppdir[3];
+    {   /* ppdir = pose * deprojectz(principal, 1) */
+        const float c[3] = {(dpx - dpx) / dfx * 1.0f, (dpy - dpy) / dfy * 1.0f, 1.0f * 1.0f};
+        for (int k = 0; k < 3; k++) ppdir[k] = pos[k] + ((xd[k] * c[0] + yd[k] * c[1]) + zd[k] * c[2]);
+    }
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            const float c[3] = {((float)x - dpx) / dfx * 1.0f, ((float)y - dpy) / dfy * 1.0f, 1.0f * 1.0f};
+            float v[3];
+            for (int k = 0; k < 3; k++) v[k] = pos[k] + ((xd[k] * c[0] + yd[k] * c[1]) + zd[k] * c[2]);
+            const int ix = cvtt_x86(v[0] / v[2] * sfx + spx), iy = cvtt_x86(v[1] / v[2] * sfy + spy);
+            unsigned short r = background;
+            if (ix >= 0 && ix <= w - 1 && iy >= 0 && iy <= h - 1) {
+                const float d = (float)src[(long)iy * w + ix];
+                const float s[3] = {((float)ix - spx) / sfx * d, ((float)iy - spy) / sfy * d, 1.0f * d};
+                r = (unsigned short)(cvtt_x86((ppdir[0] * s[0] + ppdir[1] * s[1]) + ppdir[2] * s[2]) & 0xffff);
+            }
+            out[y * dw + x] = r;
+        }
+}
+
 /* ---- label rendering ----------------------------------------------------
  * GatherHandExpectedCNN's label vector (include/handtrack.h:160-173) from 8 image feature points and 16 key
  * values: RenderHeatMap (misc_image.h:259-270: 5x5 window around (int)peak, exp(-d2/(2*0.33)), ToGrayScale =

@@ -31,6 +31,7 @@ LAYOUT = {
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
 
 
 def build(ref: bool = True) -> None:
@@ -73,6 +74,7 @@ class Oracle:
         L.orc_normalize_depth.argtypes = [np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS"), C.c_long, C.c_float, C.c_float,
                                           C.c_float, _f32p]
         L.orc_render_labels.argtypes = [_f32p, _f32p, C.c_long, _f32p]
+        L.orc_sample_d.argtypes = [_u16p, C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + [_f32p, C.c_ushort, _u16p]
         self.L = L
         self.ws = C.c_void_p(L.orc_ws_create())
 
@@ -138,6 +140,17 @@ class Oracle:
         self.L.orc_normalize_depth(d.reshape(-1), d.size, depth_scale, dmin, dmax, out.reshape(-1))
         return out
 
+    def sample_d(self, frame, src_intr, dst_cam, background, dst_dim=(64, 64)):
+        """SampleD (misc_image.h:154-162): frame[h][w] u16, src_intr = (fx, fy, px, py),
+        dst_cam = (fx, fy, px, py, pos xyz, quat xyzw) -> [dh][dw] u16."""
+        frame = np.ascontiguousarray(frame, np.uint16)
+        h, w = frame.shape
+        cam = _f32(dst_cam).reshape(11)
+        out = np.empty((dst_dim[1], dst_dim[0]), np.uint16)
+        self.L.orc_sample_d(frame, w, h, *[float(v) for v in src_intr], dst_dim[0], dst_dim[1], *[float(v) for v in cam[:4]],
+                            np.ascontiguousarray(cam[4:]), int(background), out)
+        return out
+
     _PEEK = {0: 57600, 1: 57600, 3: 3600, 5: 9216, 6: 2304, 8: 2048, 9: 2304, 10: 2304,
              109: 2304, 107: 2048, 106: 2304, 104: 9216, 103: 3600, 100: 57600}
 
@@ -201,6 +214,8 @@ class PostRef:
         L.ref_normalize_depth.argtypes = [np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS"), C.c_long, C.c_float, C.c_float,
                                           C.c_float, _f32p]
         L.ref_render_labels.argtypes = [_f32p, _f32p, C.c_long, _f32p]
+        if hasattr(L, "ref_sample_d"):
+            L.ref_sample_d.argtypes = [_u16p, C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + [_f32p, C.c_ushort, _u16p]
         self.L = L
 
     def render_labels(self, points, vals):
@@ -209,6 +224,15 @@ class PostRef:
         t = np.empty((p.shape[0], N_OUT), np.float32)
         self.L.ref_render_labels(p, v, p.shape[0], t)
         return t
+
+    def sample_d(self, frame, src_intr, dst_cam, background, dst_dim=(64, 64)):
+        frame = np.ascontiguousarray(frame, np.uint16)
+        h, w = frame.shape
+        cam = _f32(dst_cam).reshape(11)
+        out = np.empty((dst_dim[1], dst_dim[0]), np.uint16)
+        self.L.ref_sample_d(frame, w, h, *[float(v) for v in src_intr], dst_dim[0], dst_dim[1], *[float(v) for v in cam[:4]],
+                            np.ascontiguousarray(cam[4:]), int(background), out)
+        return out
 
     def decode(self, y):
         y = _f32(y).reshape(-1, N_OUT)

@@ -6,6 +6,7 @@
 //                         built from the reference's own ImageFindMax / PeakSubPixel / PeakVolume / Peaks1D
 //                         (include/misc_image.h:298-336, 389-399) in the constructor's call order
 //   ref_normalize_depth   the depth -> [0,1] crop normalisation of include/handtrack.h:700
+//   ref_sample_d          SampleD (include/misc_image.h:154-162): the rotated / scaled point resample HandSegmentVR ends with
 //   ref_render_labels     the label vector of GatherHandExpectedCNN (include/handtrack.h:160-173) from feature points + key values
 // handtrack.h itself is not included (it does not compile headless under g++), so the two call
 // sequences are restated here; every arithmetic routine they call is the reference's.
@@ -68,6 +69,21 @@ __attribute__((visibility("default"))) void ref_render_labels(const float *point
             for (int k = 0; k < 256; k++) o[i * 256 + k] = GrayScaleToFloat(hmaps[i].raster[k]);
         for (int k = 0; k < 256; k++) o[2048 + k] = GrayScaleToFloat(vmap.raster[k]);
     }
+}
+
+// SURVEY.md 8f row 3, second half: SampleD<unsigned short> (misc_image.h:154-162) as HandSegmentVR calls it
+// (include/handtrack.h:343).  src[h][w] depth with intrinsics (sfx, sfy, spx, spy); destination camera dw x dh with
+// intrinsics (dfx, dfy, dpx, dpy) and pose7 = position xyz + orientation xyzw; out[dh][dw].
+__attribute__((visibility("default"))) void ref_sample_d(const unsigned short *src, int w, int h, float sfx, float sfy, float spx, float spy,
+                                                         int dw, int dh, float dfx, float dfy, float dpx, float dpy, const float *pose7,
+                                                         unsigned short background, unsigned short *out)
+{
+    DCamera scam(int2(w, h), float2(sfx, sfy), float2(spx, spy), 0.001f);
+    Image<unsigned short> simg(scam, std::vector<unsigned short>(src, src + (size_t)w * h));
+    DCamera dcam(int2(dw, dh), float2(dfx, dfy), float2(dpx, dpy), 0.001f,
+                 Pose(float3(pose7[0], pose7[1], pose7[2]), float4(pose7[3], pose7[4], pose7[5], pose7[6])));
+    Image<unsigned short> r = SampleD(simg, dcam, background);
+    memcpy(out, r.raster.data(), (size_t)dw * dh * sizeof(unsigned short));
 }
 
 }  // extern "C"

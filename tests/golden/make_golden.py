@@ -121,3 +121,39 @@ def main_labels():
 
 if __name__ == "__main__" and "--labels" in sys.argv:
     main_labels()
+
+
+def resample_cases(n=24, seed=314):
+    """Frames + destination cameras for the SampleD row: HandSegmentVR-like cameras (64x64, focal
+    avgdepth*64/diam, principal 32, rotation about the view axis and towards the blob), plus adversarial ones
+    (looking away from the frame, NaN orientation, a shifted position)."""
+    from hand_tracking_samples_b200 import synth
+    rng = np.random.default_rng(seed)
+    frames = synth.depth_frames(n, 240, 320, seed)[0]
+    frames[3] = rng.integers(0, 65536, (240, 320)).astype(np.uint16)
+    cams = np.zeros((n, 11), np.float32)
+    for i in range(n):
+        f = rng.uniform(0.2, 1.0) * 64.0 / 0.17
+        ang = rng.uniform(-np.pi, np.pi)
+        axis = rng.normal(0, 1, 3) * np.array([0.15, 0.15, 1.0])
+        axis /= np.linalg.norm(axis)
+        q = np.concatenate([axis * np.sin(ang / 2), [np.cos(ang / 2)]])
+        cams[i] = [f, f, 32, 32, 0, 0, 0, *q]
+    cams[5, 4:7] = [0.02, -0.01, 0.05]
+    cams[6, 7:] = [1, 0, 0, 0]           # looks backwards: negative z, negative distances
+    cams[7, 9] = np.nan
+    cams[8, 0:2] = 1e-3                  # tiny focal: everything projects far outside
+    return frames, (241.811768, 241.811768, 162.830505, 118.740089), cams
+
+
+def main_resample():
+    """Fixture for the SampleD row (second half), from oracle/_ref/libpostref.so."""
+    from oracle.oracle import PostRef
+    r = PostRef()
+    frames, intr, cams = resample_cases()
+    out = np.stack([r.sample_d(frames[i], intr, cams[i], 4000) for i in range(len(cams))])
+    np.savez_compressed(os.path.join(OUT, "sample_d.npz"), crops=out, frames_seed=314, cams=cams)
+
+
+if __name__ == "__main__" and "--resample" in sys.argv:
+    main_resample()
