@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) normalize_depth_kernel(const uint16_t *__
 // cam[11] = destination focal xy, principal xy, pose position xyz, orientation xyzw (the data-dependent search that
 // produces it, HandSegmentVR include/handtrack.h:280-341, stays on the host).  Every operation is separately rounded in
 // the reference's order (linalg.h:284-288, misc_image.h:48-50); the float -> int conversions follow the pinned x86
-// build (cvttss2si: INT_MIN for NaN / out of range; low 16 bits for the unsigned short), see oracle/handposedd_oracle.c.
+// build (cvttss2si: INT_MIN for NaN / out of range; low 16 bits for the unsigned short).
 __device__ __forceinline__ int cvtt_x86(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000u; }
 struct SrcCam {
     int w, h;

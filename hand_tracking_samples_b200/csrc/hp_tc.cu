@@ -34,11 +34,15 @@ constexpr int64_t TC_CHUNK = 16384;  // crops per pass of the tensor-core path (
 // ---- GEMM tile configuration -----------------------------------------------------------
 // N tile is a template parameter: 256 for the big-batch GEMMs (and required by the fused chunked softmax), 64 for the
 // small-M training GEMMs, where 256-wide tiles would leave most of the 148 SMs without a tile.
-constexpr int BM = 128, BK = 64, STAGES = 4;    // UMMA K = 16 bf16 per instruction
+constexpr int BM = 128, BK = 64;                // UMMA K = 16 bf16 per instruction
+// Depth of the TMA -> smem ring: always 192 KB of operands in flight per SM.  The narrow tiles serve the small-batch
+// GEMMs, which are latency-bound streams of the 9.4 MB weight matrix through few CTAs: bytes in flight per SM, not the
+// tensor pipe, set their pace (Little's law: 4 x 24 KB in flight gave ~60 GB/s per SM at batch 256).
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int STG_BYTES = 4096;                 // per-warp output staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by row
 constexpr int GEMM_THREADS = 256;
-constexpr int gemm_smem(int bn) { return STAGES * (A_BYTES + bn * BK * 2) + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
+constexpr int gemm_smem(int bn) { return stages_for(bn) * (A_BYTES + bn * BK * 2) + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
 
 enum { TC_EPI_TANH_ACT = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3, TC_EPI_STORE_BF16 = 4 };
 enum { TC_FLAG_ACCUMULATE = 1, TC_FLAG_ROWS_HWC_TO_CHW = 2 };
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs ea, int M, int N, int K)
 {
     static_assert(EPI != TC_EPI_SOFTMAX_F32 || BN == 256, "the fused chunked softmax needs whole 256-wide spans in one tile");
+    constexpr int STAGES = stages_for(BN);
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     const float *__restrict__ bias = ea.bias;
