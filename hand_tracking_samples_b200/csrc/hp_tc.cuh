@@ -63,6 +63,7 @@ struct TcState {
     uint8_t *b1_img = nullptr;     // 32 KB: conv1 as pooled-window GEMM, B operand [256 (pos,co)][64 (r,c)] fp16, 128B-swizzled image
     uint8_t *a2_img = nullptr;     // 32 KB: conv2 weights as the TMEM-resident A operand of the v2 conv kernel, [128 (2co+g)][128 k] fp16
     bool conv_tanh_accurate = false;   // HP_CONV_TANH=accurate: two-MUFU tanh in the conv epilogues too (A/B runs)
+    bool conv_serial_drain = false;    // HP_CONV_PIPE=0: v2 conv kernel without the pipelined accumulator drains (A/B runs)
     bool conv_v1 = false;          // HP_CONV_V1=1: run the round-1 conv kernel (hp_tc_conv.cu) instead of hp_tc_conv2.cu
     uint8_t *b2_img = nullptr;     // 32 KB: conv2 taps, [16 taps][2 k-chunks][64 co][8 ci] fp16 (no-swizzle core matrices)
     __nv_bfloat16 *w1b = nullptr;  // [2304 (k' HWC)][2048] = fc1.W as stored (B operand of the fc1 dX GEMM)

@@ -34,6 +34,8 @@
 #include "hp_ptx.cuh"
 #include "hp_tc.cuh"
 
+#include <stdlib.h>
+
 namespace hp {
 
 #define LAUNCH_CHECK(net)                \
@@ -79,7 +81,16 @@ __device__ __forceinline__ float normalize_depth(uint32_t v, const DepthNormArgs
 // TRAIN additionally emits what CNN::Train's backward needs (cnn.h:571-575): the pooled conv1 activations p1 (fp32 copy
 // of the fp16 values conv2 consumed, the reference's CHW layout) and the max-pool winners of both stages
 // (LMaxPool::backward, cnn.h:149-164: first strict maximum).  U16: the crop arrives as 16-bit depth.
-template <bool TRAIN, bool U16>
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// PIPE: the accumulator drains are software-pipelined (the next tcgen05.ld is in flight while the previous chunk is
+// reduced) and the register file is re-divided between the warpgroups with setmaxnreg (96 each at launch ->
+// 40 issue/control | 144 + 144 epilogue 1 | 104 epilogue 2 | 72 loader = 64,512 of the SM's 65,536), so that the two
+// register buffers of the pipelined drain do not spill.  Why: conv1 has two accumulator slots per crop tile pair and its
+// MMA issuer stalls until the epilogue has read a slot back; with load -> wait -> reduce in series each 128-column
+// drain took 450-1500 cycles against 192 cycles of MMAs, which -- not shared memory or the tensor pipe -- set the pace.
+template <bool TRAIN, bool U16, bool PIPE>
 __global__ void __launch_bounds__(cv2::THREADS, 1)
 tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *__restrict__ b1_img, const uint4 *__restrict__ a2_img,
                 const float *__restrict__ params, act_t *__restrict__ p2_out, int n, float *__restrict__ p1_out,
@@ -135,6 +146,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // Roles are dispatched by WARPGROUP first so that each setmaxnreg dominates the code of its role (ptxas allocates
+    // registers per region) and is executed by all four warps of the warpgroup.
+    if (warp < 4) {
+    if (PIPE) reg_dec<40>();
     if (warp == 0) {
         if (lane == 0) {
             ptx::mbar_expect_tx(wgt_full, 32768);
@@ -200,8 +215,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             }
             __syncwarp();
         }
-    } else if (warp >= 4 && warp < 12) {
+    }
+    } else if (warp < 12) {
         // ===================== epilogue 1: conv1 accumulators -> p1 planes =====================
+        if (PIPE) reg_inc<144>();
         const int ew = warp & 3;
         const int my_e = (warp - 4) >> 2;
         const int m = ew * 32 + lane;           // row of the M tile: (py, px')
@@ -213,35 +230,71 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             ptx::mbar_wait(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
             float mx[16];
             int am[16];
-#pragma unroll 1
-            for (int half = 0; half < 2; half++) {
-                ptx::mbar_wait(&acc1_full[my_e * 2 + half], it & 1);
-                ptx::tc_fence_after();
-                const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC1 + half * 128;
+            // one 32-column chunk = 2 window positions x 16 channels: running (first strict) maximum per channel
+            auto reduce_chunk = [&](const uint32_t (&r)[32], int half, int c) {
+                if (TRAIN) {
+                    const int p0 = half * 8 + 2 * c;
 #pragma unroll
-                for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
-                    uint32_t r[32];
-                    ptx::tmem_ld32(ta + c * 32, r);
-                    ptx::tmem_ld_wait();
-                    if (TRAIN) {
-                        const int p0 = half * 8 + 2 * c;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[16 + j]);
-                            if ((half == 0 && c == 0) || v0 > mx[j]) { mx[j] = v0; am[j] = p0; }
-                            if (v1 > mx[j]) { mx[j] = v1; am[j] = p0 + 1; }
-                        }
-                    } else if (half == 0 && c == 0) {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) mx[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[16 + j]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) mx[j] = ptx::max3(mx[j], __uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+                    for (int j = 0; j < 16; j++) {
+                        const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[16 + j]);
+                        if ((half == 0 && c == 0) || v0 > mx[j]) { mx[j] = v0; am[j] = p0; }
+                        if (v1 > mx[j]) { mx[j] = v1; am[j] = p0 + 1; }
                     }
+                } else if (half == 0 && c == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) mx[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) mx[j] = ptx::max3(mx[j], __uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+                }
+            };
+            const uint32_t ta0 = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC1;
+            if (PIPE) {
+                // chunks k = 0..7 (half = k / 4, c = k % 4): load k+1 is issued before chunk k is reduced, and a slot is handed
+                // back to the MMA issuer as soon as its last load has landed (before that chunk's arithmetic)
+                uint32_t ra[32], rb[32];
+                ptx::mbar_wait(&acc1_full[my_e * 2 + 0], it & 1);
+                ptx::tc_fence_after();
+                ptx::tmem_ld32(ta0, ra);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int half = k >> 2, c = k & 3;
+                    if (k == 3) {   // the first slot's last chunk is in registers: the MMAs of the next tile may overwrite it
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&acc1_empty[0]);
+                        ptx::mbar_wait(&acc1_full[my_e * 2 + 1], it & 1);
+                        ptx::tc_fence_after();
+                    }
+                    if (k + 1 < 8) {
+                        const uint32_t ta = ta0 + ((k + 1) >> 2) * 128 + ((k + 1) & 3) * 32;
+                        if (k & 1) ptx::tmem_ld32(ta, ra);
+                        else ptx::tmem_ld32(ta, rb);
+                    }
+                    if (k & 1) reduce_chunk(rb, half, c);
+                    else reduce_chunk(ra, half, c);
+                    if (k + 1 < 8) ptx::tmem_ld_wait();
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
+                if (lane == 0) ptx::mbar_arrive(&acc1_empty[1]);
+            } else {
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+                    ptx::mbar_wait(&acc1_full[my_e * 2 + half], it & 1);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
+                        uint32_t r[32];
+                        ptx::tmem_ld32(ta0 + half * 128 + c * 32, r);
+                        ptx::tmem_ld_wait();
+                        reduce_chunk(r, half, c);
+                    }
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
+                }
             }
             if (py < 15 && px < 15) {
                 uint32_t pk[8];
@@ -269,8 +322,9 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
         }
-    } else if (warp >= 12 && warp < 16) {
+    } else if (warp < 16) {
         // ===================== conv2 weights -> TMEM (once), then epilogue 2 =====================
+        if (PIPE) reg_inc<104>();
         const int ew = warp - 12;               // == warp % 4: the TMEM lane quarter this warp may access
         const int m = ew * 32 + lane;           // accumulator lane = 2 co + g
         const int co = m >> 1, g = m & 1;
@@ -300,33 +354,58 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             // odd  lane (kx 2,3 half of pixel n-2): own = B[x + 2], sends A[x + 2] (the even lane's pixels, their kx 2,3 half)
             float best[3][6];
             int arg[3][6];
+            // one step = one output row y = 2 (3 g + s) + d of this lane's half of the rows: pair add, then the 2x2 pool
+            auto reduce_row = [&](const uint32_t (&A)[16], const uint32_t (&B)[16], int s, int d) {
 #pragma unroll
-            for (int s = 0; s < 3; s++) {
-#pragma unroll
-                for (int d = 0; d < 2; d++) {
-                    uint32_t A[16], B[16];
-                    ptx::tmem_ld16(lane_base + ACC2 + 32 * s + 16 * d, A);
-                    ptx::tmem_ld16(lane_base + ACC2 + 96 + 32 * s + 16 * d, B);
-                    ptx::tmem_ld_wait();
-                    if (s == 2 && d == 1) {   // last read of this crop's accumulator: hand it back to the MMA issuer
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(acc2_empty);
+                for (int xx = 0; xx < 12; xx++) {
+                    const float own = __uint_as_float(g ? B[xx + 2] : A[xx]);
+                    const float send = __uint_as_float(g ? A[xx + 2] : B[xx]);
+                    const float v = own + __shfl_xor_sync(0xffffffffu, send, 1);
+                    const int pxx = xx >> 1, pos = d * 2 + (xx & 1);   // scan order (0,0),(1,0),(0,1),(1,1), cnn.h:157-161
+                    if (pos == 0) {
+                        best[s][pxx] = v;
+                        arg[s][pxx] = 0;
+                    } else if (TRAIN) {
+                        if (v > best[s][pxx]) { best[s][pxx] = v; arg[s][pxx] = pos; }
+                    } else {
+                        best[s][pxx] = fmaxf(best[s][pxx], v);
                     }
+                }
+            };
+            auto release_acc2 = [&]() {   // last read of this crop's accumulator done: hand it back to the MMA issuer
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(acc2_empty);
+            };
+            const uint32_t t2 = lane_base + ACC2;
+            if (PIPE) {
+                uint32_t A0[16], B0[16], A1[16], B1[16];
+                ptx::tmem_ld16(t2, A0);
+                ptx::tmem_ld16(t2 + 96, B0);
+                ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int xx = 0; xx < 12; xx++) {
-                        const float own = __uint_as_float(g ? B[xx + 2] : A[xx]);
-                        const float send = __uint_as_float(g ? A[xx + 2] : B[xx]);
-                        const float v = own + __shfl_xor_sync(0xffffffffu, send, 1);
-                        const int pxx = xx >> 1, pos = d * 2 + (xx & 1);   // scan order (0,0),(1,0),(0,1),(1,1), cnn.h:157-161
-                        if (pos == 0) {
-                            best[s][pxx] = v;
-                            arg[s][pxx] = 0;
-                        } else if (TRAIN) {
-                            if (v > best[s][pxx]) { best[s][pxx] = v; arg[s][pxx] = pos; }
-                        } else {
-                            best[s][pxx] = fmaxf(best[s][pxx], v);
-                        }
+                for (int k = 0; k < 6; k++) {   // k = 2 s + d
+                    if (k + 1 < 6) {
+                        const uint32_t col = 32 * ((k + 1) >> 1) + 16 * ((k + 1) & 1);
+                        if (k & 1) { ptx::tmem_ld16(t2 + col, A0); ptx::tmem_ld16(t2 + 96 + col, B0); }
+                        else { ptx::tmem_ld16(t2 + col, A1); ptx::tmem_ld16(t2 + 96 + col, B1); }
+                    }
+                    if (k & 1) reduce_row(A1, B1, k >> 1, k & 1);
+                    else reduce_row(A0, B0, k >> 1, k & 1);
+                    if (k + 1 < 6) ptx::tmem_ld_wait();
+                    if (k == 4) release_acc2();   // the loads of the last row (k = 5) have landed
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 3; s++) {
+#pragma unroll
+                    for (int d = 0; d < 2; d++) {
+                        uint32_t A[16], B[16];
+                        ptx::tmem_ld16(t2 + 32 * s + 16 * d, A);
+                        ptx::tmem_ld16(t2 + 96 + 32 * s + 16 * d, B);
+                        ptx::tmem_ld_wait();
+                        if (s == 2 && d == 1) release_acc2();
+                        reduce_row(A, B, s, d);
                     }
                 }
             }
@@ -341,8 +420,9 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                 }
             }
         }
-    } else if (warp >= 16) {
+    } else {
         // ===================== loader: crop -> two fp16 image copies =====================
+        if (PIPE) reg_dec<72>();
         const int t = threadIdx.x - 16 * 32;  // 0..127
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1;
@@ -408,9 +488,11 @@ int tc_conv2_init(Net &net)
 {
     TcState *t = net.tc;
     HP_CUDA_TRY(cudaMalloc((void **)&t->a2_img, 32768));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+    t->conv_serial_drain = getenv("HP_CONV_PIPE") != nullptr && getenv("HP_CONV_PIPE")[0] == '0';   // A/B: round-2 first version
     return 0;
 }
 
@@ -426,8 +508,12 @@ int tc_conv2_stage(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t 
 {
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv2_kernel<false, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
-                                                                       net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
+    if (t->conv_serial_drain)
+        tc_conv2_kernel<false, false, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
+                                                                                  net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
+    else
+        tc_conv2_kernel<false, false, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
+                                                                                 net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;
 }
@@ -437,7 +523,7 @@ int tc_conv2_stage_u16(Net &net, const uint16_t *depth, int64_t n, float depth_s
 {
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv2_kernel<false, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(depth, DepthNormArgs{depth_scale, dmin, dmax - dmin}, t->b1_img,
+    tc_conv2_kernel<false, true, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(depth, DepthNormArgs{depth_scale, dmin, dmax - dmin}, t->b1_img,
                                                                       reinterpret_cast<const uint4 *>(t->a2_img), net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;
@@ -448,7 +534,7 @@ int tc_conv2_stage_train(Net &net, const float *x, int64_t n, act_t *p2, cudaStr
 {
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv2_kernel<true, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
+    tc_conv2_kernel<true, false, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
                                                                       net.params, p2, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2, t->conv_tanh_accurate ? 1 : 0);
     LAUNCH_CHECK(net);
     return 0;

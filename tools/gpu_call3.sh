@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout -s KILL 120 tools/dbg/_bin/tmem_bench > gpurun_out/c3_tmem_bench.txt 2>&1; cat gpurun_out/c3_tmem_bench.txt
-for v in "A=1" "HP_CONV_TANH=accurate" "HP_CONV_V1=1" "HP_CONV_V1=1 HP_CONV_TANH=accurate"; do
+for v in "A=1" "HP_CONV_PIPE=0" "HP_CONV_TANH=accurate" "HP_CONV_PIPE=0 HP_CONV_TANH=accurate" "HP_CONV_V1=1" "HP_CONV_V1=1 HP_CONV_TANH=accurate"; do
   echo "== $v"; env $v timeout -s KILL 180 python tools/conv_check.py 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['eval_init_worst'], d['eval_peaky_worst'], d['timing'])"
 done
 timeout -s KILL 300 python -m pytest tests -m gpu -q --timeout 600 -k "dropin or nan_quirk or within_bound" 2>&1 | tail -3
