@@ -83,11 +83,17 @@ __device__ __forceinline__ float normalize_depth(uint32_t v, const DepthNormArgs
 // (LMaxPool::backward, cnn.h:149-164: first strict maximum).  U16: the crop arrives as 16-bit depth.
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+namespace cv2 {
+constexpr int REG_CTRL = 40, REG_EPI1 = 136, REG_EPI2 = 104, REG_LOAD = 64, REG_LAUNCH = 96;
+static_assert(REG_CTRL + 2 * REG_EPI1 + REG_EPI2 + REG_LOAD <= 5 * REG_LAUNCH, "setmaxnreg split exceeds the CTA's launch allocation: .inc would never be granted");
+}  // namespace cv2
 
 // PIPE: the accumulator drains are software-pipelined (the next tcgen05.ld is in flight while the previous chunk is
-// reduced) and the register file is re-divided between the warpgroups with setmaxnreg (96 each at launch ->
-// 40 issue/control | 144 + 144 epilogue 1 | 104 epilogue 2 | 72 loader = 64,512 of the SM's 65,536), so that the two
-// register buffers of the pipelined drain do not spill.  Why: conv1 has two accumulator slots per crop tile pair and its
+// reduced) and the CTA's registers are re-divided between the warpgroups with setmaxnreg (96 per thread at launch ->
+// 40 issue/control | 136 + 136 epilogue 1 | 104 epilogue 2 | 64 loader), so that the two register buffers of the
+// pipelined drain do not spill.  The new sizes must not add up to more than the launch allocation (5 x 96): the pool a
+// setmaxnreg.inc draws from holds only what the CTA's own warpgroups have released -- an over-subscribed split makes
+// the last .inc wait forever (this hung the first version of this kernel).  Why: conv1 has two accumulator slots per crop tile pair and its
 // MMA issuer stalls until the epilogue has read a slot back; with load -> wait -> reduce in series each 128-column
 // drain took 450-1500 cycles against 192 cycles of MMAs, which -- not shared memory or the tensor pipe -- set the pace.
 template <bool TRAIN, bool U16, bool PIPE>
@@ -149,7 +155,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     // Roles are dispatched by WARPGROUP first so that each setmaxnreg dominates the code of its role (ptxas allocates
     // registers per region) and is executed by all four warps of the warpgroup.
     if (warp < 4) {
-    if (PIPE) reg_dec<40>();
+    if (PIPE) reg_dec<REG_CTRL>();
     if (warp == 0) {
         if (lane == 0) {
             ptx::mbar_expect_tx(wgt_full, 32768);
@@ -218,7 +224,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     }
     } else if (warp < 12) {
         // ===================== epilogue 1: conv1 accumulators -> p1 planes =====================
-        if (PIPE) reg_inc<144>();
+        if (PIPE) reg_inc<REG_EPI1>();
         const int ew = warp & 3;
         const int my_e = (warp - 4) >> 2;
         const int m = ew * 32 + lane;           // row of the M tile: (py, px')
@@ -324,7 +330,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         }
     } else if (warp < 16) {
         // ===================== conv2 weights -> TMEM (once), then epilogue 2 =====================
-        if (PIPE) reg_inc<104>();
+        if (PIPE) reg_inc<REG_EPI2>();
         const int ew = warp - 12;               // == warp % 4: the TMEM lane quarter this warp may access
         const int m = ew * 32 + lane;           // accumulator lane = 2 co + g
         const int co = m >> 1, g = m & 1;
@@ -422,7 +428,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         }
     } else {
         // ===================== loader: crop -> two fp16 image copies =====================
-        if (PIPE) reg_dec<72>();
+        if (PIPE) reg_dec<REG_LOAD>();
         const int t = threadIdx.x - 16 * 32;  // 0..127
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1;
@@ -488,10 +494,10 @@ int tc_conv2_init(Net &net)
 {
     TcState *t = net.tc;
     HP_CUDA_TRY(cudaMalloc((void **)&t->a2_img, 32768));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM));
+#define HP_CONV2_ATTR(TR, U, P) HP_CUDA_TRY(cudaFuncSetAttribute(tc_conv2_kernel<TR, U, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, cv2::SMEM))
+    HP_CONV2_ATTR(false, false, true); HP_CONV2_ATTR(false, true, true); HP_CONV2_ATTR(true, false, true);
+    HP_CONV2_ATTR(false, false, false); HP_CONV2_ATTR(false, true, false); HP_CONV2_ATTR(true, false, false);
+#undef HP_CONV2_ATTR
     t->conv_serial_drain = getenv("HP_CONV_PIPE") != nullptr && getenv("HP_CONV_PIPE")[0] == '0';   // A/B: round-2 first version
     return 0;
 }
@@ -504,40 +510,36 @@ int tc_conv2_refresh(Net &net, cudaStream_t s)
     return 0;
 }
 
-int tc_conv2_stage(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t s)
+template <bool TRAIN, bool U16>
+static int launch_conv2(Net &net, const void *x, DepthNormArgs nm, int64_t n, act_t *p2, float *p1, uint8_t *idx1, uint8_t *idx2, cudaStream_t s)
 {
     TcState *t = net.tc;
     const int grid = (int)(n < t->num_sms ? n : t->num_sms);
+    const uint4 *a2 = reinterpret_cast<const uint4 *>(t->a2_img);
+    const int acc = t->conv_tanh_accurate ? 1 : 0;
     if (t->conv_serial_drain)
-        tc_conv2_kernel<false, false, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
-                                                                                  net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
+        tc_conv2_kernel<TRAIN, U16, false><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, nm, t->b1_img, a2, net.params, p2, (int)n, p1, idx1, idx2, acc);
     else
-        tc_conv2_kernel<false, false, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
-                                                                                 net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
+        tc_conv2_kernel<TRAIN, U16, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, nm, t->b1_img, a2, net.params, p2, (int)n, p1, idx1, idx2, acc);
     LAUNCH_CHECK(net);
     return 0;
+}
+
+int tc_conv2_stage(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t s)
+{
+    return launch_conv2<false, false>(net, x, DepthNormArgs{0.f, 0.f, 1.f}, n, p2, nullptr, nullptr, nullptr, s);
 }
 
 // 16-bit depth crops in, include/handtrack.h:700 applied in the loader (no fp32 crop buffer in HBM)
 int tc_conv2_stage_u16(Net &net, const uint16_t *depth, int64_t n, float depth_scale, float dmin, float dmax, act_t *p2, cudaStream_t s)
 {
-    TcState *t = net.tc;
-    const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv2_kernel<false, true, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(depth, DepthNormArgs{depth_scale, dmin, dmax - dmin}, t->b1_img,
-                                                                      reinterpret_cast<const uint4 *>(t->a2_img), net.params, p2, (int)n, nullptr, nullptr, nullptr, t->conv_tanh_accurate ? 1 : 0);
-    LAUNCH_CHECK(net);
-    return 0;
+    return launch_conv2<false, true>(net, depth, DepthNormArgs{depth_scale, dmin, dmax - dmin}, n, p2, nullptr, nullptr, nullptr, s);
 }
 
 // training forward: also writes p1 (fp32 CHW), idx1, idx2 into the FP32 workspace layouts the backward kernels read
 int tc_conv2_stage_train(Net &net, const float *x, int64_t n, act_t *p2, cudaStream_t s)
 {
-    TcState *t = net.tc;
-    const int grid = (int)(n < t->num_sms ? n : t->num_sms);
-    tc_conv2_kernel<true, false, true><<<grid, cv2::THREADS, cv2::SMEM, s>>>(x, DepthNormArgs{0.f, 0.f, 1.f}, t->b1_img, reinterpret_cast<const uint4 *>(t->a2_img),
-                                                                      net.params, p2, (int)n, net.ws.p1, net.ws.idx1, net.ws.idx2, t->conv_tanh_accurate ? 1 : 0);
-    LAUNCH_CHECK(net);
-    return 0;
+    return launch_conv2<true, false>(net, x, DepthNormArgs{0.f, 0.f, 1.f}, n, p2, net.ws.p1, net.ws.idx1, net.ws.idx2, s);
 }
 
 }  // namespace hp
