@@ -116,7 +116,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float *__restrict__ bias = ea.bias;
     void *__restrict__ out = ea.out;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t *staging = smem + STAGES * STAGE_BYTES;  // [4 epilogue warps][2][STG_BYTES]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(staging + 8 * STG_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;

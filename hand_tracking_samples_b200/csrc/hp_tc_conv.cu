@@ -86,7 +86,7 @@ tc_conv_kernel(const float *__restrict__ x, const uint8_t *__restrict__ b1_img, 
     using namespace cv;
     const bool acc_tanh = tanh_accurate != 0;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     float *bias1 = reinterpret_cast<float *>(smem + OFF_BIAS);
     float *bias2 = bias1 + 16;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);

@@ -30,7 +30,8 @@
 //   warps 4-11  epilogue 1 (two warpgroups, one per pooled-column parity): TMEM -> running max over the 16 window
 //               positions -> +bias, tanh -> p1 planes (smem); training: also p1 and the conv1-stage winners to global
 //   warps 12-15 conv2 weights -> TMEM once; then epilogue 2: TMEM -> pair add -> 2x2 max -> +bias, tanh -> global features
-//   warps 16-19 loader: crop -> two fp16 image copies in smem (double-buffered)
+//   warp 3      crop producer: cp.async.bulk (TMA) HBM -> 4-deep staging ring, mbarrier complete_tx
+//   warps 16-19 converter: staged crop (fp32, or 16-bit depth + handtrack.h:700) -> two fp16 image copies in smem
 #include "hp_ptx.cuh"
 #include "hp_tc.cuh"
 
@@ -55,7 +56,10 @@ constexpr int P1_BUF = 2 * P1_PLANE;
 constexpr int OFF_B1 = 0;                      // 32 KB, 1024-aligned (128B swizzle)
 constexpr int OFF_IMG = 32768;                 // 2 x IMG_BUF
 constexpr int OFF_P1 = OFF_IMG + 2 * IMG_BUF;  // 2 x P1_BUF
-constexpr int OFF_BIAS = OFF_P1 + 2 * P1_BUF;  // 16 + 64 floats
+constexpr int NSTAGE = 4;                      // crops in flight from HBM (TMA bulk copies into a staging ring)
+constexpr int STAGE_BYTES = 16384;             // one fp32 crop (a 16-bit crop uses the first 8 KB)
+constexpr int OFF_STAGE = OFF_P1 + 2 * P1_BUF; // NSTAGE x STAGE_BYTES
+constexpr int OFF_BIAS = OFF_STAGE + NSTAGE * STAGE_BYTES;  // 16 + 64 floats
 constexpr int OFF_BAR = OFF_BIAS + 512;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
 // TMEM columns
@@ -105,7 +109,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     using namespace cv2;
     const bool acc_tanh = tanh_accurate != 0;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     float *bias1 = reinterpret_cast<float *>(smem + OFF_BIAS);
     float *bias2 = bias1 + 16;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
@@ -119,7 +123,9 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     uint64_t *acc2_full = bars + 15;
     uint64_t *acc2_empty = bars + 16;
     uint64_t *w2_full = bars + 17;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 18);
+    uint64_t *stage_full = bars + 18;   // [NSTAGE]
+    uint64_t *stage_empty = bars + 22;  // [NSTAGE]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 26);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int my_crops = (n > (int)blockIdx.x) ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -138,6 +144,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         ptx::mbar_init(acc2_full, 1);
         ptx::mbar_init(acc2_empty, 4);
         ptx::mbar_init(w2_full, 4);
+        for (int b = 0; b < NSTAGE; b++) {
+            ptx::mbar_init(&stage_full[b], 1);
+            ptx::mbar_init(&stage_empty[b], 4);
+        }
         ptx::fence_barrier_init();
     }
     // zero the p1 planes once (pad pixels x = 15 and rows 240..255 are read by the tap shifts) and the image buffers
@@ -220,6 +230,21 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                 ptx::umma_commit(&p1_empty[pb]);
             }
             __syncwarp();
+        }
+    } else {
+        // ===================== crop producer: TMA bulk copies HBM -> staging ring, NSTAGE crops ahead =====================
+        // (the LDG -> convert -> STS loader of round 1 could only look one crop ahead: the DRAM latency of every crop
+        //  was exposed once the MMA side got faster)
+        if (lane == 0) {
+            constexpr uint32_t BYTES = U16 ? N_IN * 2 : N_IN * 4;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(x_in);
+            for (int it = 0; it < my_crops; it++) {
+                const int sg = it % NSTAGE;
+                ptx::mbar_wait(&stage_empty[sg], ((it / NSTAGE) & 1) ^ 1);
+                const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                ptx::mbar_expect_tx(&stage_full[sg], BYTES);
+                ptx::bulk_load_1d(smem + OFF_STAGE + sg * STAGE_BYTES, src + crop * BYTES, BYTES, &stage_full[sg]);
+            }
         }
     }
     } else if (warp < 12) {
@@ -427,44 +452,37 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             }
         }
     } else {
-        // ===================== loader: crop -> two fp16 image copies =====================
+        // ===================== converter: staged crop -> two fp16 image copies =====================
         if (PIPE) reg_dec<REG_LOAD>();
         const int t = threadIdx.x - 16 * 32;  // 0..127
         for (int it = 0; it < my_crops; it++) {
-            const int ib = it & 1;
-            const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-            uint32_t lo[4][2], mi[4][2], hi[4][2];   // pixels 8j..8j+3, 8j+4..8j+7, 8j+8..8j+11 of chunk j = t + 128 k, packed fp16x2
-            if (U16) {
-                const uint2 *src = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(x_in) + crop * N_IN);
+            const int ib = it & 1, sg = it % NSTAGE;
+            const uint8_t *st = smem + OFF_STAGE + sg * STAGE_BYTES;
+            ptx::mbar_wait(&stage_full[sg], (it / NSTAGE) & 1);
+            uint2 pk[8];   // pixels 4f .. 4f+3 of group f = t + 128 k, packed fp16x2
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int j = t + 128 * k;
-                    const uint2 a = __ldg(src + 2 * j), b = __ldg(src + 2 * j + 1);
-                    const uint2 c = (j < 511) ? __ldg(src + 2 * j + 2) : make_uint2(0, 0);
-                    auto cvt = [&](uint32_t w) { return pack_act(normalize_depth(w & 0xffffu, nm), normalize_depth(w >> 16, nm)); };
-                    lo[k][0] = cvt(a.x); lo[k][1] = cvt(a.y);
-                    mi[k][0] = cvt(b.x); mi[k][1] = cvt(b.y);
-                    if (j < 511) { hi[k][0] = cvt(c.x); hi[k][1] = cvt(c.y); } else { hi[k][0] = hi[k][1] = 0; }
-                }
-            } else {
-                const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(x_in) + crop * N_IN);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int j = t + 128 * k;  // 8-pixel chunk index
-                    const float4 a = __ldg(src + 2 * j), b = __ldg(src + 2 * j + 1);
-                    const float4 c = (j < 511) ? __ldg(src + 2 * j + 2) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    lo[k][0] = pack_act(a.x, a.y); lo[k][1] = pack_act(a.z, a.w);
-                    mi[k][0] = pack_act(b.x, b.y); mi[k][1] = pack_act(b.z, b.w);
-                    hi[k][0] = pack_act(c.x, c.y); hi[k][1] = pack_act(c.z, c.w);
+            for (int k = 0; k < 8; k++) {
+                const int f = t + 128 * k;
+                if (U16) {
+                    const uint2 a = *reinterpret_cast<const uint2 *>(st + f * 8);
+                    pk[k].x = pack_act(normalize_depth(a.x & 0xffffu, nm), normalize_depth(a.x >> 16, nm));
+                    pk[k].y = pack_act(normalize_depth(a.y & 0xffffu, nm), normalize_depth(a.y >> 16, nm));
+                } else {
+                    const float4 a = *reinterpret_cast<const float4 *>(st + f * 16);
+                    pk[k].x = pack_act(a.x, a.y);
+                    pk[k].y = pack_act(a.z, a.w);
                 }
             }
+            // every staged value of this warp is in registers (the conversions consumed the loads): free the stage
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&stage_empty[sg]);
             ptx::mbar_wait(&img_empty[ib], ((it >> 1) & 1) ^ 1);
             uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int j = t + 128 * k;
-                *reinterpret_cast<uint4 *>(img + j * 16) = make_uint4(lo[k][0], lo[k][1], mi[k][0], mi[k][1]);             // pixels 8j .. 8j+7
-                *reinterpret_cast<uint4 *>(img + IMG_COPY + j * 16) = make_uint4(mi[k][0], mi[k][1], hi[k][0], hi[k][1]);  // pixels 8j+4 .. 8j+11
+            for (int k = 0; k < 8; k++) {
+                const int f = t + 128 * k;
+                *reinterpret_cast<uint2 *>(img + f * 8) = pk[k];                          // copy 0: pixel p at byte 2 p
+                if (f > 0) *reinterpret_cast<uint2 *>(img + IMG_COPY + f * 8 - 8) = pk[k];   // copy 1: shifted by 4 pixels
             }
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&img_full[ib]);
