@@ -60,6 +60,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// Same, telling the hardware it may keep the thread suspended for up to `ns` nanoseconds per attempt (it is woken when
+// the phase completes): far fewer trips round the retry loop, i.e. fewer issue slots taken from the warps that share the
+// scheduler with the waiter.  In the fused conv kernel nearly half of all issued instructions were such retries.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
 
 // ---- TMA ----------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)

@@ -10,7 +10,7 @@
 // epilogue stages 41 KB more for the 2x2 pool -- ~2.6 k of the measured 2.78 k cycles per crop (profiles/r1_v4_summary.md).
 // conv1 is unchanged here (pooled-window GEMM, see hp_tc_conv.cu); conv2 is TRANSPOSED AND TAP-PAIRED:
 //
-//     D[m = 2 co + g][n = pixel 16 y + x]  +=  A_j[m][ci] * P[n + 16 ky + kxh][ci]        j = (ky, kxh), 8 MMAs M128 x N192 x K16
+//     D[m = 2 co + g][n = pixel 16 y + x]  +=  A_j[m][ci] * P[n + 16 ky + kxh][ci]        j = (ky, kxh), 2 x 8 MMAs M128 x N96 x K16
 //
 //   * A = the conv2 weights, resident in TENSOR MEMORY for the whole kernel (tcgen05.mma with the A operand in TMEM): row
 //     2co+g of MMA j holds W[co][ci][ky][kxh + 2g].  The 64 output channels fill all 128 datapath lanes by computing two
@@ -21,12 +21,13 @@
 //   * pixels are accumulator COLUMNS, so the 2x2 max-pool, bias, tanh and (training) the first-strict-maximum winner run in
 //     one thread's registers: no staging buffer, no barrier among the epilogue warps.
 //   * tensor time 8 x 96 = 768 cycles per crop (was 1024), 75 % of the issued MACs useful (was 56 %).
-// TMEM: columns 0-255 two conv1 accumulators, 256-447 the conv2 accumulator, 448-511 the conv2 weights.
+// TMEM: columns 0-255 two conv1 accumulators, 256-447 the conv2 accumulator (two independently handed-over halves of
+// 96 columns: output rows 0-5 and 6-11), 448-511 the conv2 weights.
 //
 // Warp roles (640 threads, 1 CTA/SM, crops strided over the grid):
 //   warp 0      conv1 weight image (cp.async.bulk), TMEM allocation
 //   warp 1      conv1 MMA issuer (12 MMAs M128 N128 K16 per crop)
-//   warp 2      conv2 MMA issuer (8 MMAs M128 N192 K16 per crop, A from TMEM)
+//   warp 2      conv2 MMA issuer (2 x 8 MMAs M128 N96 K16 per crop, A from TMEM)
 //   warps 4-11  epilogue 1 (two warpgroups, one per pooled-column parity): TMEM -> running max over the 16 window
 //               positions -> +bias, tanh -> p1 planes (smem); training: also p1 and the conv1-stage winners to global
 //   warps 12-15 conv2 weights -> TMEM once; then epilogue 2: TMEM -> pair add -> 2x2 max -> +bias, tanh -> global features
@@ -44,6 +45,8 @@ namespace hp {
         (net).launches++;                \
         HP_CUDA_TRY(cudaGetLastError()); \
     } while (0)
+
+#define WAIT(bar, parity) ptx::mbar_wait_hint(bar, parity, 4000u)
 
 namespace cv2 {
 constexpr int THREADS = 640;
@@ -64,9 +67,9 @@ constexpr int OFF_BAR = OFF_BIAS + 512;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
 // TMEM columns
 constexpr int ACC1 = 0;     // two 128-column conv1 accumulators (window-position halves)
-constexpr int ACC2 = 256;   // conv2 accumulator: 192 columns (pixels), lanes (co, tap half)
+constexpr int ACC2 = 256;   // conv2 accumulator: two halves of 96 columns (output rows 0-5 / 6-11), lanes (co, tap half)
 constexpr int W2 = 448;     // conv2 weights: 8 MMAs x 8 columns (16 fp16 K values each)
-constexpr int N2 = 192;     // conv2 MMA N: output pixels 16 y + x <= 187, + 2 for the tap-pair shift
+constexpr int N2 = 96;      // conv2 MMA N per half: pixels 16 y + x of 6 output rows (<= 91), + 2 for the tap-pair shift
 }  // namespace cv2
 
 // depth normalisation of include/handtrack.h:700, bit-exact with normalize_depth_kernel (hp_post.cu)
@@ -120,12 +123,12 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     uint64_t *acc1_empty = bars + 9;  // [2]
     uint64_t *p1_full = bars + 11;    // [2]
     uint64_t *p1_empty = bars + 13;   // [2]
-    uint64_t *acc2_full = bars + 15;
-    uint64_t *acc2_empty = bars + 16;
-    uint64_t *w2_full = bars + 17;
-    uint64_t *stage_full = bars + 18;   // [NSTAGE]
-    uint64_t *stage_empty = bars + 22;  // [NSTAGE]
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 26);
+    uint64_t *acc2_full = bars + 15;    // [2]: one per half of the conv2 accumulator
+    uint64_t *acc2_empty = bars + 17;   // [2]
+    uint64_t *w2_full = bars + 19;
+    uint64_t *stage_full = bars + 20;   // [NSTAGE]
+    uint64_t *stage_empty = bars + 24;  // [NSTAGE]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 28);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int my_crops = (n > (int)blockIdx.x) ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -141,8 +144,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             ptx::mbar_init(&p1_full[b], 8);
             ptx::mbar_init(&p1_empty[b], 1);
         }
-        ptx::mbar_init(acc2_full, 1);
-        ptx::mbar_init(acc2_empty, 4);
+        for (int b = 0; b < 2; b++) {
+            ptx::mbar_init(&acc2_full[b], 1);
+            ptx::mbar_init(&acc2_empty[b], 4);
+        }
         ptx::mbar_init(w2_full, 4);
         for (int b = 0; b < NSTAGE; b++) {
             ptx::mbar_init(&stage_full[b], 1);
@@ -174,19 +179,19 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     } else if (warp == 1) {
         // ===================== conv1 MMA issuer (as in hp_tc_conv.cu) =====================
         constexpr uint32_t idesc1 = ptx::make_idesc_f16(128, 128);
-        ptx::mbar_wait(wgt_full, 0);
+        WAIT(wgt_full, 0);
         const uint32_t sB1 = ptx::smem_u32(smem + OFF_B1);
         const uint64_t bd0 = ptx::make_desc_sw128(sB1);
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1;
-            ptx::mbar_wait(&img_full[ib], (it >> 1) & 1);
+            WAIT(&img_full[ib], (it >> 1) & 1);
             ptx::tc_fence_after();
             const uint64_t ad0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_IMG + ib * IMG_BUF), 128, 512);
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 const int e = g >> 1, half = g & 1;        // e: pooled-column parity (which image copy)
                 const uint32_t u = (uint32_t)(it * 2 + e);  // use count of accumulator `half`
-                ptx::mbar_wait(&acc1_empty[half], (u & 1) ^ 1);
+                WAIT(&acc1_empty[half], (u & 1) ^ 1);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                     const uint32_t d = tmem_base + ACC1 + half * 128;
@@ -210,26 +215,32 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     } else if (warp == 2) {
         // ===================== conv2 MMA issuer: 8 tap pairs, A (weights) from TMEM =====================
         constexpr uint32_t idesc2 = ptx::make_idesc_f16(128, N2);
-        ptx::mbar_wait(w2_full, 0);
+        WAIT(w2_full, 0);
         ptx::tc_fence_after();
         for (int it = 0; it < my_crops; it++) {
             const int pb = it & 1;
-            ptx::mbar_wait(&p1_full[pb], (it >> 1) & 1);
-            ptx::mbar_wait(acc2_empty, (it & 1) ^ 1);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF), P1_PLANE, 128);
-                const uint32_t d = tmem_base + ACC2, a0 = tmem_base + W2;
+            WAIT(&p1_full[pb], (it >> 1) & 1);
+            // The accumulator is split in two halves (output rows 0-5 and 6-11), each with its own full/empty handshake:
+            // the epilogue drains one half while the MMAs of the other run.  (A single 192-column accumulator made
+            // "8 MMAs -> drain -> next 8 MMAs" a serial loop of ~2.4 k cycles per crop, the pace of the whole kernel.)
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int shift = (j >> 1) * P1_PITCH + (j & 1);   // pixel rows: 16 ky + kxh
-                    if (j == 0) ptx::umma_f16_ts_c<false>(d, a0, bd0, idesc2);
-                    else ptx::umma_f16_ts_c<true>(d, a0 + 8 * j, bd0 + shift, idesc2);
+            for (int h = 0; h < 2; h++) {
+                WAIT(&acc2_empty[h], (it & 1) ^ 1);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF), P1_PLANE, 128) + h * N2;
+                    const uint32_t d = tmem_base + ACC2 + h * N2, a0 = tmem_base + W2;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int shift = (j >> 1) * P1_PITCH + (j & 1);   // pixel rows: 16 ky + kxh
+                        if (j == 0) ptx::umma_f16_ts_c<false>(d, a0, bd0, idesc2);
+                        else ptx::umma_f16_ts_c<true>(d, a0 + 8 * j, bd0 + shift, idesc2);
+                    }
+                    ptx::umma_commit(&acc2_full[h]);
+                    if (h == 1) ptx::umma_commit(&p1_empty[pb]);
                 }
-                ptx::umma_commit(acc2_full);
-                ptx::umma_commit(&p1_empty[pb]);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ===================== crop producer: TMA bulk copies HBM -> staging ring, NSTAGE crops ahead =====================
@@ -240,7 +251,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             const uint8_t *src = reinterpret_cast<const uint8_t *>(x_in);
             for (int it = 0; it < my_crops; it++) {
                 const int sg = it % NSTAGE;
-                ptx::mbar_wait(&stage_empty[sg], ((it / NSTAGE) & 1) ^ 1);
+                WAIT(&stage_empty[sg], ((it / NSTAGE) & 1) ^ 1);
                 const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 ptx::mbar_expect_tx(&stage_full[sg], BYTES);
                 ptx::bulk_load_1d(smem + OFF_STAGE + sg * STAGE_BYTES, src + crop * BYTES, BYTES, &stage_full[sg]);
@@ -258,7 +269,6 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         for (int it = 0; it < my_crops; it++) {
             const int pb = it & 1;
             uint8_t *planes = smem + OFF_P1 + pb * P1_BUF;
-            ptx::mbar_wait(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
             float mx[16];
             int am[16];
             // one 32-column chunk = 2 window positions x 16 channels: running (first strict) maximum per channel
@@ -284,7 +294,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                 // chunks k = 0..7 (half = k / 4, c = k % 4): load k+1 is issued before chunk k is reduced, and a slot is handed
                 // back to the MMA issuer as soon as its last load has landed (before that chunk's arithmetic)
                 uint32_t ra[32], rb[32];
-                ptx::mbar_wait(&acc1_full[my_e * 2 + 0], it & 1);
+                WAIT(&acc1_full[my_e * 2 + 0], it & 1);
                 ptx::tc_fence_after();
                 ptx::tmem_ld32(ta0, ra);
                 ptx::tmem_ld_wait();
@@ -295,7 +305,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&acc1_empty[0]);
-                        ptx::mbar_wait(&acc1_full[my_e * 2 + 1], it & 1);
+                        WAIT(&acc1_full[my_e * 2 + 1], it & 1);
                         ptx::tc_fence_after();
                     }
                     if (k + 1 < 8) {
@@ -313,7 +323,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             } else {
 #pragma unroll 1
                 for (int half = 0; half < 2; half++) {
-                    ptx::mbar_wait(&acc1_full[my_e * 2 + half], it & 1);
+                    WAIT(&acc1_full[my_e * 2 + half], it & 1);
                     ptx::tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < 4; c++) {   // 32 columns = 2 window positions x 16 channels
@@ -327,6 +337,9 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                     if (lane == 0) ptx::mbar_arrive(&acc1_empty[half]);
                 }
             }
+            // only the STORES need the p1 buffer to be free (conv2 of two crops ago done): waiting here, not before the
+            // drain, keeps the conv1 accumulator slots turning over while conv2 is behind
+            WAIT(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
             if (py < 15 && px < 15) {
                 uint32_t pk[8];
 #pragma unroll
@@ -376,78 +389,76 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         const float b2 = bias2[co];
         for (int it = 0; it < my_crops; it++) {
             const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-            ptx::mbar_wait(acc2_full, it & 1);
-            ptx::tc_fence_after();
-            // This lane finalises pooled rows py = 3 g + s (s = 0..2): output rows y = 2 py + d, columns 16 y + x.
-            //   window A = D[.][32 s + 16 d + 0..15]       (rows y of the even lanes)
-            //   window B = D[.][96 + 32 s + 16 d + 0..15]  (rows y of the odd lanes)
-            // even lane (kx 0,1 half of pixel n):  own = A[x],     sends B[x]     (the odd lane's pixels, its kx 0,1 half)
-            // odd  lane (kx 2,3 half of pixel n-2): own = B[x + 2], sends A[x + 2] (the even lane's pixels, their kx 2,3 half)
-            float best[3][6];
-            int arg[3][6];
-            // one step = one output row y = 2 (3 g + s) + d of this lane's half of the rows: pair add, then the 2x2 pool
-            auto reduce_row = [&](const uint32_t (&A)[16], const uint32_t (&B)[16], int s, int d) {
+            // Accumulator half h holds output rows y = 6 h + r (r = 0..5) as columns 16 r + x.  Lane 2co (g = 0) carries the
+            // kx {0,1} half of pixel (y, x) in column 16 r + x, lane 2co+1 (g = 1) the kx {2,3} half in column 16 r + x + 2.
+            // The even lane finalises x = 0..5 (pooled columns 0-2), the odd lane x = 6..11 (pooled columns 3-5); per row
+            // each lane needs six values of its partner: one shfl.xor(1) each way.
+            //   even: own = W[i],     sends W[6 + i] (its half of the odd lane's pixels)
+            //   odd:  own = W[8 + i], sends W[2 + i] (its half of the even lane's pixels)
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                WAIT(&acc2_full[h], it & 1);
+                ptx::tc_fence_after();
+                float best[3][3];
+                int arg[3][3];
+                auto reduce_row = [&](const uint32_t (&W)[16], int r) {
+                    const int s = r >> 1, d = r & 1;
 #pragma unroll
-                for (int xx = 0; xx < 12; xx++) {
-                    const float own = __uint_as_float(g ? B[xx + 2] : A[xx]);
-                    const float send = __uint_as_float(g ? A[xx + 2] : B[xx]);
-                    const float v = own + __shfl_xor_sync(0xffffffffu, send, 1);
-                    const int pxx = xx >> 1, pos = d * 2 + (xx & 1);   // scan order (0,0),(1,0),(0,1),(1,1), cnn.h:157-161
-                    if (pos == 0) {
-                        best[s][pxx] = v;
-                        arg[s][pxx] = 0;
-                    } else if (TRAIN) {
-                        if (v > best[s][pxx]) { best[s][pxx] = v; arg[s][pxx] = pos; }
-                    } else {
-                        best[s][pxx] = fmaxf(best[s][pxx], v);
+                    for (int i = 0; i < 6; i++) {
+                        const float own = __uint_as_float(g ? W[8 + i] : W[i]);
+                        const float send = __uint_as_float(g ? W[2 + i] : W[6 + i]);
+                        const float v = own + __shfl_xor_sync(0xffffffffu, send, 1);
+                        const int pxl = i >> 1, pos = d * 2 + (i & 1);   // scan order (0,0),(1,0),(0,1),(1,1), cnn.h:157-161
+                        if (pos == 0) {
+                            best[s][pxl] = v;
+                            arg[s][pxl] = 0;
+                        } else if (TRAIN) {
+                            if (v > best[s][pxl]) { best[s][pxl] = v; arg[s][pxl] = pos; }
+                        } else {
+                            best[s][pxl] = fmaxf(best[s][pxl], v);
+                        }
+                    }
+                };
+                auto release_half = [&]() {   // last read of this half done: hand it back to the MMA issuer
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&acc2_empty[h]);
+                };
+                const uint32_t t2 = lane_base + ACC2 + h * N2;
+                if (PIPE) {
+                    uint32_t W0[16], W1[16];
+                    ptx::tmem_ld16(t2, W0);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        if (r + 1 < 6) {
+                            if (r & 1) ptx::tmem_ld16(t2 + 16 * (r + 1), W0);
+                            else ptx::tmem_ld16(t2 + 16 * (r + 1), W1);
+                        }
+                        if (r & 1) reduce_row(W1, r);
+                        else reduce_row(W0, r);
+                        if (r + 1 < 6) ptx::tmem_ld_wait();
+                        if (r == 4) release_half();   // the load of the last row (r = 5) has landed
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        uint32_t W[16];
+                        ptx::tmem_ld16(t2 + 16 * r, W);
+                        ptx::tmem_ld_wait();
+                        if (r == 5) release_half();
+                        reduce_row(W, r);
                     }
                 }
-            };
-            auto release_acc2 = [&]() {   // last read of this crop's accumulator done: hand it back to the MMA issuer
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(acc2_empty);
-            };
-            const uint32_t t2 = lane_base + ACC2;
-            if (PIPE) {
-                uint32_t A0[16], B0[16], A1[16], B1[16];
-                ptx::tmem_ld16(t2, A0);
-                ptx::tmem_ld16(t2 + 96, B0);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int k = 0; k < 6; k++) {   // k = 2 s + d
-                    if (k + 1 < 6) {
-                        const uint32_t col = 32 * ((k + 1) >> 1) + 16 * ((k + 1) & 1);
-                        if (k & 1) { ptx::tmem_ld16(t2 + col, A0); ptx::tmem_ld16(t2 + 96 + col, B0); }
-                        else { ptx::tmem_ld16(t2 + col, A1); ptx::tmem_ld16(t2 + 96 + col, B1); }
-                    }
-                    if (k & 1) reduce_row(A1, B1, k >> 1, k & 1);
-                    else reduce_row(A0, B0, k >> 1, k & 1);
-                    if (k + 1 < 6) ptx::tmem_ld_wait();
-                    if (k == 4) release_acc2();   // the loads of the last row (k = 5) have landed
-                }
-            } else {
+                // + bias, tanh (max and the monotone tanh commute in the forward pass), features in HWC order (pp * 64 + co)
 #pragma unroll
                 for (int s = 0; s < 3; s++) {
 #pragma unroll
-                    for (int d = 0; d < 2; d++) {
-                        uint32_t A[16], B[16];
-                        ptx::tmem_ld16(t2 + 32 * s + 16 * d, A);
-                        ptx::tmem_ld16(t2 + 96 + 32 * s + 16 * d, B);
-                        ptx::tmem_ld_wait();
-                        if (s == 2 && d == 1) release_acc2();
-                        reduce_row(A, B, s, d);
+                    for (int pxl = 0; pxl < 3; pxl++) {
+                        const int pp = (3 * h + s) * 6 + 3 * g + pxl;
+                        p2_out[crop * P2_N + pp * 64 + co] = __float2half_rn(tanh_conv(best[s][pxl] + b2, acc_tanh));
+                        if (TRAIN) idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg[s][pxl];
                     }
-                }
-            }
-            // + bias, tanh (max and the monotone tanh commute in the forward pass), features in HWC order (pp * 64 + co)
-#pragma unroll
-            for (int s = 0; s < 3; s++) {
-#pragma unroll
-                for (int pxx = 0; pxx < 6; pxx++) {
-                    const int pp = (3 * g + s) * 6 + pxx;
-                    p2_out[crop * P2_N + pp * 64 + co] = __float2half_rn(tanh_conv(best[s][pxx] + b2, acc_tanh));
-                    if (TRAIN) idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg[s][pxx];
                 }
             }
         }
@@ -458,7 +469,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1, sg = it % NSTAGE;
             const uint8_t *st = smem + OFF_STAGE + sg * STAGE_BYTES;
-            ptx::mbar_wait(&stage_full[sg], (it / NSTAGE) & 1);
+            WAIT(&stage_full[sg], (it / NSTAGE) & 1);
             uint2 pk[8];   // pixels 4f .. 4f+3 of group f = t + 128 k, packed fp16x2
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -476,7 +487,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             // every staged value of this warp is in registers (the conversions consumed the loads): free the stage
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&stage_empty[sg]);
-            ptx::mbar_wait(&img_empty[ib], ((it >> 1) & 1) ^ 1);
+            WAIT(&img_empty[ib], ((it >> 1) & 1) ^ 1);
             uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
