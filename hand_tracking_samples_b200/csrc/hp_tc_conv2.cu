@@ -24,15 +24,16 @@
 // TMEM: columns 0-255 two conv1 accumulators, 256-447 the conv2 accumulator (two independently handed-over halves of
 // 96 columns: output rows 0-5 and 6-11), 448-511 the conv2 weights.
 //
-// Warp roles (640 threads, 1 CTA/SM, crops strided over the grid):
+// Warp roles (768 threads, 1 CTA/SM, crops strided over the grid):
 //   warp 0      conv1 weight image (cp.async.bulk), TMEM allocation
 //   warp 1      conv1 MMA issuer (12 MMAs M128 N128 K16 per crop)
 //   warp 2      conv2 MMA issuer (2 x 8 MMAs M128 N96 K16 per crop, A from TMEM)
 //   warps 4-11  epilogue 1 (two warpgroups, one per pooled-column parity): TMEM -> running max over the 16 window
 //               positions -> +bias, tanh -> p1 planes (smem); training: also p1 and the conv1-stage winners to global
-//   warps 12-15 conv2 weights -> TMEM once; then epilogue 2: TMEM -> pair add -> 2x2 max -> +bias, tanh -> global features
+//   warps 12-19 epilogue 2 (two warpgroups, one per accumulator half; the first also puts the conv2 weights into TMEM
+//               once): TMEM -> pair add -> 2x2 max -> +bias, tanh -> global features
 //   warp 3      crop producer: cp.async.bulk (TMA) HBM -> 4-deep staging ring, mbarrier complete_tx
-//   warps 16-19 converter: staged crop (fp32, or 16-bit depth + handtrack.h:700) -> two fp16 image copies in smem
+//   warps 20-23 converter: staged crop (fp32, or 16-bit depth + handtrack.h:700) -> two fp16 image copies in smem
 #include "hp_ptx.cuh"
 #include "hp_tc.cuh"
 
@@ -49,7 +50,7 @@ namespace hp {
 #define WAIT(bar, parity) ptx::mbar_wait_hint(bar, parity, 4000u)
 
 namespace cv2 {
-constexpr int THREADS = 640;
+constexpr int THREADS = 768;
 constexpr int IMG_COPY = 9216;                 // one fp16 image copy (8 KB) + slack for the pad rows' reads
 constexpr int IMG_BUF = 2 * IMG_COPY;          // aligned copy + copy shifted by 4 pixels
 constexpr int P1_PITCH = 16;                   // pixels per row of the pooled conv1 stage in smem (15 used + 1 zero)
@@ -91,14 +92,14 @@ __device__ __forceinline__ float normalize_depth(uint32_t v, const DepthNormArgs
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 namespace cv2 {
-constexpr int REG_CTRL = 40, REG_EPI1 = 136, REG_EPI2 = 104, REG_LOAD = 64, REG_LAUNCH = 96;
-static_assert(REG_CTRL + 2 * REG_EPI1 + REG_EPI2 + REG_LOAD <= 5 * REG_LAUNCH, "setmaxnreg split exceeds the CTA's launch allocation: .inc would never be granted");
+constexpr int REG_CTRL = 32, REG_EPI1 = 128, REG_EPI2 = 80, REG_LOAD = 32, REG_LAUNCH = 80;
+static_assert(REG_CTRL + 2 * REG_EPI1 + 2 * REG_EPI2 + REG_LOAD <= 6 * REG_LAUNCH, "setmaxnreg split exceeds the CTA's launch allocation: .inc would never be granted");
 }  // namespace cv2
 
 // PIPE: the accumulator drains are software-pipelined (the next tcgen05.ld is in flight while the previous chunk is
-// reduced) and the CTA's registers are re-divided between the warpgroups with setmaxnreg (96 per thread at launch ->
-// 40 issue/control | 136 + 136 epilogue 1 | 104 epilogue 2 | 64 loader), so that the two register buffers of the
-// pipelined drain do not spill.  The new sizes must not add up to more than the launch allocation (5 x 96): the pool a
+// reduced) and the CTA's registers are re-divided between the warpgroups with setmaxnreg (80 per thread at launch ->
+// 32 issue/control | 128 + 128 epilogue 1 | 80 + 80 epilogue 2 | 32 converter), so that the two register buffers of the
+// pipelined drain do not spill.  The new sizes must not add up to more than the launch allocation (6 x 80): the pool a
 // setmaxnreg.inc draws from holds only what the CTA's own warpgroups have released -- an over-subscribed split makes
 // the last .inc wait forever (this hung the first version of this kernel).  Why: conv1 has two accumulator slots per crop tile pair and its
 // MMA issuer stalls until the epilogue has read a slot back; with load -> wait -> reduce in series each 128-column
@@ -366,14 +367,18 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
         }
-    } else if (warp < 16) {
+    } else if (warp < 20) {
         // ===================== conv2 weights -> TMEM (once), then epilogue 2 =====================
-        if (PIPE) reg_inc<REG_EPI2>();
-        const int ew = warp - 12;               // == warp % 4: the TMEM lane quarter this warp may access
+        // two warpgroups, one per accumulator half: a single warpgroup doing both halves ran at IPC ~0.25 (one warp per
+        // scheduler cannot hide the shuffle / TMEM-load latencies) and was busy 100 % of the crop period
+        if (PIPE && REG_EPI2 > REG_LAUNCH) reg_inc<REG_EPI2>();
+        if (PIPE && REG_EPI2 < REG_LAUNCH) reg_dec<REG_EPI2>();
+        const int ew = warp & 3;                // == warp % 4: the TMEM lane quarter this warp may access
+        const int my_h = (warp - 12) >> 2;      // accumulator half this warpgroup drains
         const int m = ew * 32 + lane;           // accumulator lane = 2 co + g
         const int co = m >> 1, g = m & 1;
         const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
-        {
+        if (my_h == 0) {
             const uint4 *src = a2_img + m * 16;   // 128 fp16 = 64 words: K = (MMA j, ci)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -395,8 +400,8 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             // each lane needs six values of its partner: one shfl.xor(1) each way.
             //   even: own = W[i],     sends W[6 + i] (its half of the odd lane's pixels)
             //   odd:  own = W[8 + i], sends W[2 + i] (its half of the even lane's pixels)
-#pragma unroll 1
-            for (int h = 0; h < 2; h++) {
+            {
+                const int h = my_h;
                 WAIT(&acc2_full[h], it & 1);
                 ptx::tc_fence_after();
                 float best[3][3];
@@ -465,7 +470,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
     } else {
         // ===================== converter: staged crop -> two fp16 image copies =====================
         if (PIPE) reg_dec<REG_LOAD>();
-        const int t = threadIdx.x - 16 * 32;  // 0..127
+        const int t = threadIdx.x - 20 * 32;  // 0..127
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1, sg = it % NSTAGE;
             const uint8_t *st = smem + OFF_STAGE + sg * STAGE_BYTES;
