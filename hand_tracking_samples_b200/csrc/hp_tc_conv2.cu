@@ -26,8 +26,8 @@
 //
 // Warp roles (768 threads, 1 CTA/SM, crops strided over the grid):
 //   warp 0      conv1 weight image (cp.async.bulk), TMEM allocation
-//   warp 1      MMA issuer: per crop 12 conv1 MMAs (M128 N128 K16, SS) and 2 x 8 conv2 MMAs (M128 N96 K16, A from TMEM)
-//               in one static interleaved order (conv2 one crop behind conv1)
+//   warp 1      conv1 MMA issuer (12 MMAs M128 N128 K16 per crop)
+//   warp 2      conv2 MMA issuer (2 x 8 MMAs M128 N96 K16 per crop, A from TMEM)
 //   warps 4-11  epilogue 1 (two warpgroups, one per pooled-column parity): TMEM -> running max over the 16 window
 //               positions -> +bias, tanh -> p1 planes (smem); training: also p1 and the conv1-stage winners to global
 //   warps 12-19 epilogue 2 (two warpgroups, one per accumulator half; the first also puts the conv2 weights into TMEM
@@ -92,13 +92,13 @@ __device__ __forceinline__ float normalize_depth(uint32_t v, const DepthNormArgs
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 namespace cv2 {
-constexpr int REG_CTRL = 48, REG_EPI1 = 120, REG_EPI2 = 80, REG_LOAD = 32, REG_LAUNCH = 80;
+constexpr int REG_CTRL = 32, REG_EPI1 = 128, REG_EPI2 = 80, REG_LOAD = 32, REG_LAUNCH = 80;
 static_assert(REG_CTRL + 2 * REG_EPI1 + 2 * REG_EPI2 + REG_LOAD <= 6 * REG_LAUNCH, "setmaxnreg split exceeds the CTA's launch allocation: .inc would never be granted");
 }  // namespace cv2
 
 // PIPE: the accumulator drains are software-pipelined (the next tcgen05.ld is in flight while the previous chunk is
 // reduced) and the CTA's registers are re-divided between the warpgroups with setmaxnreg (80 per thread at launch ->
-// 48 issue/control | 120 + 120 epilogue 1 | 80 + 80 epilogue 2 | 32 converter), so that the two register buffers of the
+// 32 issue/control | 128 + 128 epilogue 1 | 80 + 80 epilogue 2 | 32 converter), so that the two register buffers of the
 // pipelined drain do not spill.  The new sizes must not add up to more than the launch allocation (6 x 80): the pool a
 // setmaxnreg.inc draws from holds only what the CTA's own warpgroups have released -- an over-subscribed split makes
 // the last .inc wait forever (this hung the first version of this kernel).  Why: conv1 has two accumulator slots per crop tile pair and its
@@ -178,30 +178,25 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             ptx::bulk_load_1d(smem + OFF_B1, b1_img, 32768, wgt_full);
         }
     } else if (warp == 1) {
-        // ===================== the MMA issuer: conv1 and conv2 in ONE statically interleaved order =====================
-        // Two independent issuer warps fed the (in-order) tensor pipe in whatever order their waits resolved: conv2's
-        // 16 MMAs arrived as one 768-cycle burst in front of the conv1 groups the next crop was waiting for, and with only
-        // four accumulator buffers in TMEM (2 conv1 slots, 2 conv2 halves) the pipe idled ~30 % of the time (ncu:
-        // tensor pipe 70 % active, every other role waiting on it).  The order below keeps a drain of each buffer (~450
-        // cycles from commit to hand-back) underneath MMAs that use the OTHER buffers; conv2 runs one crop behind conv1:
-        //     conv1(it) g0 g1 | conv2(it-1) half 0 | conv1(it) g2 g3 | conv2(it-1) half 1
+        // ===================== conv1 MMA issuer (as in hp_tc_conv.cu) =====================
         constexpr uint32_t idesc1 = ptx::make_idesc_f16(128, 128);
-        constexpr uint32_t idesc2 = ptx::make_idesc_f16(128, N2);
         WAIT(wgt_full, 0);
-        WAIT(w2_full, 0);
-        ptx::tc_fence_after();
-        const uint64_t bd1 = ptx::make_desc_sw128(ptx::smem_u32(smem + OFF_B1));
-        auto conv1_pair = [&](int it, int e) {   // groups (e, half 0) and (e, half 1) of crop `it`
+        const uint32_t sB1 = ptx::smem_u32(smem + OFF_B1);
+        const uint64_t bd0 = ptx::make_desc_sw128(sB1);
+        for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1;
+            WAIT(&img_full[ib], (it >> 1) & 1);
+            ptx::tc_fence_after();
             const uint64_t ad0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_IMG + ib * IMG_BUF), 128, 512);
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t u = (uint32_t)(it * 2 + e);   // use count of accumulator slot `half`
+            for (int g = 0; g < 4; g++) {
+                const int e = g >> 1, half = g & 1;        // e: pooled-column parity (which image copy)
+                const uint32_t u = (uint32_t)(it * 2 + e);  // use count of accumulator `half`
                 WAIT(&acc1_empty[half], (u & 1) ^ 1);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                     const uint32_t d = tmem_base + ACC1 + half * 128;
-                    const uint64_t ad = ad0 + ((e * IMG_COPY) >> 4), bd = bd1 + ((half * 16384) >> 4);
+                    const uint64_t ad = ad0 + ((e * IMG_COPY) >> 4), bd = bd0 + ((half * 16384) >> 4);
                     // K step ks covers patch rows 2ks, 2ks+1; the all-zero K step of each window-position half is skipped
                     if (half == 0) {
                         ptx::umma_f16_c<false>(d, ad, bd, idesc1);
@@ -212,46 +207,42 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                         ptx::umma_f16_c<true>(d, ad + (512 >> 4), bd + 4, idesc1);
                         ptx::umma_f16_c<true>(d, ad + (768 >> 4), bd + 6, idesc1);
                     }
-                    ptx::umma_commit(&acc1_full[e * 2 + half]);
-                    if (e == 1 && half == 1) ptx::umma_commit(&img_empty[ib]);
+                    ptx::umma_commit(&acc1_full[g]);
+                    if (g == 3) ptx::umma_commit(&img_empty[ib]);
                 }
                 __syncwarp();
             }
-        };
-        auto conv2_half = [&](int it, int h) {   // output rows 6h .. 6h+5 of crop `it`: 8 tap pairs, A (weights) from TMEM
-            const int pb = it & 1;
-            WAIT(&acc2_empty[h], (it & 1) ^ 1);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF), P1_PLANE, 128) + h * N2;
-                const uint32_t d = tmem_base + ACC2 + h * N2, a0 = tmem_base + W2;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int shift = (j >> 1) * P1_PITCH + (j & 1);   // pixel rows: 16 ky + kxh
-                    if (j == 0) ptx::umma_f16_ts_c<false>(d, a0, bd0, idesc2);
-                    else ptx::umma_f16_ts_c<true>(d, a0 + 8 * j, bd0 + shift, idesc2);
-                }
-                ptx::umma_commit(&acc2_full[h]);
-                if (h == 1) ptx::umma_commit(&p1_empty[pb]);
-            }
-            __syncwarp();
-        };
-        for (int it = 0; it <= my_crops; it++) {
-            if (it < my_crops) {
-                WAIT(&img_full[it & 1], (it >> 1) & 1);
-                ptx::tc_fence_after();
-                conv1_pair(it, 0);
-            }
-            if (it >= 1) {
-                WAIT(&p1_full[(it - 1) & 1], ((it - 1) >> 1) & 1);
-                ptx::tc_fence_after();
-                conv2_half(it - 1, 0);
-            }
-            if (it < my_crops) conv1_pair(it, 1);
-            if (it >= 1) conv2_half(it - 1, 1);
         }
     } else if (warp == 2) {
-        // idle (the conv2 MMAs are issued by warp 1 in the interleaved order above)
+        // ===================== conv2 MMA issuer: 8 tap pairs, A (weights) from TMEM =====================
+        constexpr uint32_t idesc2 = ptx::make_idesc_f16(128, N2);
+        WAIT(w2_full, 0);
+        ptx::tc_fence_after();
+        for (int it = 0; it < my_crops; it++) {
+            const int pb = it & 1;
+            WAIT(&p1_full[pb], (it >> 1) & 1);
+            // The accumulator is split in two halves (output rows 0-5 and 6-11), each with its own full/empty handshake:
+            // the epilogue drains one half while the MMAs of the other run.  (A single 192-column accumulator made
+            // "8 MMAs -> drain -> next 8 MMAs" a serial loop of ~2.4 k cycles per crop, the pace of the whole kernel.)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                WAIT(&acc2_empty[h], (it & 1) ^ 1);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF), P1_PLANE, 128) + h * N2;
+                    const uint32_t d = tmem_base + ACC2 + h * N2, a0 = tmem_base + W2;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int shift = (j >> 1) * P1_PITCH + (j & 1);   // pixel rows: 16 ky + kxh
+                        if (j == 0) ptx::umma_f16_ts_c<false>(d, a0, bd0, idesc2);
+                        else ptx::umma_f16_ts_c<true>(d, a0 + 8 * j, bd0 + shift, idesc2);
+                    }
+                    ptx::umma_commit(&acc2_full[h]);
+                    if (h == 1) ptx::umma_commit(&p1_empty[pb]);
+                }
+                __syncwarp();
+            }
+        }
     } else {
         // ===================== crop producer: TMA bulk copies HBM -> staging ring, NSTAGE crops ahead =====================
         // (the LDG -> convert -> STS loader of round 1 could only look one crop ahead: the DRAM latency of every crop
