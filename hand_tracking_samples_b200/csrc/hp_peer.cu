@@ -27,6 +27,7 @@
 // hp_save_cnnb call on the host returns HP_ERR_PEER.
 #include "hp_common.cuh"
 #include "hp_peer.cuh"
+#include "hp_ptx.cuh"
 
 namespace hp {
 
@@ -135,6 +136,121 @@ __global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_kernel(PeerPtrs P, i
     peer_barrier<WORLD>(P, rank, epoch + 2);
 }
 
+// ---- the same exchange with the NVLink traffic moved by the TMA engine -----------------------------------------------
+// peer_sgd_kernel keeps (G-1) x 16 bytes per thread in flight: 16 CTAs x 1024 threads reach ~220 GB/s of remote loads at
+// two GPUs (tools/dbg/p2p_bw.cu) -- a 16.5 MB reduce-scatter read takes ~75 us, longer than the backward kernels it is
+// meant to hide behind.  Here one thread per CTA issues cp.async.bulk copies of CHUNK bytes from every peer's gradient
+// store into a shared-memory ring (mbarrier complete_tx), STAGES chunks ahead, so each of the 16 CTAs keeps
+// STAGES x (G-1) x CHUNK bytes (~170 KB) in flight without occupying registers; the other warps add the chunks in rank
+// order (same order, same bits as peer_sgd_kernel), apply w <- fma(-alpha, sum, w), store the owner's copy and stage
+// the new weights in a double-buffered shared tile that the same thread bulk-stores into every peer's weight store.
+constexpr int PT_CONS = PEER_THREADS - 32;   // consumer threads (warps 0..30); warp 31 lane 0 drives the TMA loads
+__device__ __forceinline__ void pt_wait(uint64_t *bar, uint32_t parity, uint32_t *err)
+{
+    const unsigned long long t0 = globaltimer_ns();
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > 20000000000ull) {   // a bulk copy that never completes: fail loudly instead of hanging the GPU
+            atomicExch(err, 0xdeadu);
+            asm volatile("trap;");
+        }
+    }
+}
+template <int WORLD, int CHUNK_F4, int STAGES>
+__global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_tma_kernel(PeerPtrs P, int rank, int off, int count4, float alpha, uint32_t epoch)
+{
+    constexpr int CHUNK_B = CHUNK_F4 * 16;
+    extern __shared__ uint8_t pt_raw[];
+    uint8_t *sm = pt_raw + ((128u - (ptx::smem_u32(pt_raw) & 127u)) & 127u);
+    uint8_t *stage0 = sm;                                        // [STAGES][WORLD-1][CHUNK_B]
+    uint8_t *out0 = sm + (size_t)STAGES * (WORLD - 1) * CHUNK_B;  // [2][CHUNK_B]
+    __shared__ uint64_t full[STAGES], empty[STAGES];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (!peer_barrier<WORLD>(P, rank, epoch + 1)) return;   // incomplete sums: leave the weights alone (also a CTA-wide sync)
+    ptx::fence_proxy_async_all();                           // the bulk (async-proxy) reads below come after the barrier's acquire
+    const int lo = (int)((int64_t)count4 * rank / WORLD), hi = (int)((int64_t)count4 * (rank + 1) / WORLD);
+    const int nchunks = (hi - lo + CHUNK_F4 - 1) / CHUNK_F4;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 31) {
+        if ((threadIdx.x & 31) == 0) {
+            int k = 0;
+            for (int c = blockIdx.x; c < nchunks; c += gridDim.x, k++) {
+                const int sg = k % STAGES;
+                pt_wait(&empty[sg], ((k / STAGES) & 1) ^ 1, P.error);
+                const int f0 = lo + c * CHUNK_F4, nf = (hi - f0 < CHUNK_F4) ? hi - f0 : CHUNK_F4;
+                ptx::mbar_expect_tx(&full[sg], (uint32_t)(nf * 16 * (WORLD - 1)));
+#pragma unroll
+                for (int p = 0; p < WORLD; p++) {
+                    if (p == rank) continue;
+                    const int slot = p < rank ? p : p - 1;
+                    ptx::bulk_load_1d(stage0 + ((size_t)sg * (WORLD - 1) + slot) * CHUNK_B, reinterpret_cast<const float4 *>(P.grads[p] + off) + f0,
+                                      (uint32_t)(nf * 16), &full[sg]);
+                }
+            }
+        }
+    } else {
+        const int t = threadIdx.x;   // 0 .. PT_CONS-1
+        int k = 0;
+        for (int c = blockIdx.x; c < nchunks; c += gridDim.x, k++) {
+            const int sg = k % STAGES, ob = k & 1;
+            const int f0 = lo + c * CHUNK_F4, nf = (hi - f0 < CHUNK_F4) ? hi - f0 : CHUNK_F4;
+            // the bulk stores that read out buffer `ob` two chunks ago must have finished reading it
+            if (t == 0) ptx::bulk_wait_read<1>();
+            ptx::named_bar_sync(1, PT_CONS);
+            pt_wait(&full[sg], (k / STAGES) & 1, P.error);
+            const float4 *st = reinterpret_cast<const float4 *>(stage0 + (size_t)sg * (WORLD - 1) * CHUNK_B);
+            float4 *ot = reinterpret_cast<float4 *>(out0 + (size_t)ob * CHUNK_B);
+            for (int i = t; i < nf; i += PT_CONS) {
+                const float4 mine = reinterpret_cast<const float4 *>(P.grads[rank] + off)[f0 + i];
+                float4 s = rank == 0 ? mine : st[i];   // rank order 0..G-1 on every owner: deterministic
+#pragma unroll
+                for (int p = 1; p < WORLD; p++) {
+                    const float4 v = (p == rank) ? mine : st[(p < rank ? p : p - 1) * CHUNK_F4 + i];
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+                float4 w = reinterpret_cast<const float4 *>(P.params[rank] + off)[f0 + i];
+                w.x = fmaf(-alpha, s.x, w.x); w.y = fmaf(-alpha, s.y, w.y);
+                w.z = fmaf(-alpha, s.z, w.z); w.w = fmaf(-alpha, s.w, w.w);
+                reinterpret_cast<float4 *>(P.params[rank] + off)[f0 + i] = w;
+                ot[i] = w;
+            }
+            ptx::fence_proxy_async();          // this thread's out-buffer writes -> visible to the bulk stores
+            ptx::named_bar_sync(1, PT_CONS);   // every consumer has read the stage and written its part of the out buffer
+            if (t == 0) {
+                ptx::mbar_arrive(&empty[sg]);
+#pragma unroll
+                for (int p = 0; p < WORLD; p++)
+                    if (p != rank) ptx::bulk_store_1d(reinterpret_cast<float4 *>(P.params[p] + off) + f0, ot, (uint32_t)(nf * 16));
+                ptx::bulk_commit();
+            }
+        }
+        if (t == 0) {
+            ptx::bulk_wait<0>();      // every peer store of this CTA has been performed
+            __threadfence_system();
+        }
+    }
+    peer_barrier<WORLD>(P, rank, epoch + 2);
+}
+
+template <int WORLD, int CHUNK_F4, int STAGES>
+static int launch_peer_tma(PeerState *ps, int blocks, int off, int count4, float alpha, uint32_t epoch, cudaStream_t s)
+{
+    constexpr int SMEM = (STAGES * (WORLD - 1) + 2) * CHUNK_F4 * 16 + 128;
+    static_assert(SMEM <= 227 * 1024, "peer exchange tile too large");
+    static bool attr = false;
+    if (!attr) {
+        HP_CUDA_TRY(cudaFuncSetAttribute(peer_sgd_tma_kernel<WORLD, CHUNK_F4, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr = true;
+    }
+    peer_sgd_tma_kernel<WORLD, CHUNK_F4, STAGES><<<blocks, PEER_THREADS, SMEM, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch);
+    return 0;
+}
+
 // The conv bucket (16,864 floats) finishes last and its exchange is exposed at the end of the step, so it is done in
 // ONE barrier instead of two: every rank pushes its gradient sums into slot [rank] of every peer's inbox, the CTAs meet
 // once, and every rank then adds the G slots of its own inbox in rank order and updates its own weights -- all ranks
@@ -194,6 +310,24 @@ int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
     if (blocks > ps->max_blocks) blocks = ps->max_blocks;
     if (blocks < 1) blocks = 1;
     ps->epoch += 2;
+    static const bool use_tma = !(getenv("HP_PEER_TMA") && getenv("HP_PEER_TMA")[0] == '0');   // HP_PEER_TMA=0: the LDG/STG kernel (A/B runs)
+    if (use_tma) {
+        int rc = 2;
+        switch (ps->world) {   // bytes in flight per CTA = STAGES x (G-1) x chunk: ~130-170 KB
+        case 2: rc = launch_peer_tma<2, 2048, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 3: rc = launch_peer_tma<3, 1024, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 4: rc = launch_peer_tma<4, 1024, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 5: rc = launch_peer_tma<5, 512, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 6: rc = launch_peer_tma<6, 512, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 7: rc = launch_peer_tma<7, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 8: rc = launch_peer_tma<8, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
+        default: set_error("peer path supports 2..8 ranks, got %d", ps->world); return 2;
+        }
+        if (rc) return rc;
+        LAUNCH_CHECK(net);
+        net.tc_dirty = true;
+        return 0;
+    }
     switch (ps->world) {
 #define HP_CASE(W, U) case W: peer_sgd_kernel<W, U><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
     HP_CASE(2, 4) HP_CASE(3, 2) HP_CASE(4, 2) HP_CASE(5, 1) HP_CASE(6, 1) HP_CASE(7, 1) HP_CASE(8, 1)
