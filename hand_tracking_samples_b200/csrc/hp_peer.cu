@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_kernel(PeerPtrs P, i
 // STAGES x (G-1) x CHUNK bytes (~170 KB) in flight without occupying registers; the other warps add the chunks in rank
 // order (same order, same bits as peer_sgd_kernel), apply w <- fma(-alpha, sum, w), store the owner's copy and stage
 // the new weights in a double-buffered shared tile that the same thread bulk-stores into every peer's weight store.
-constexpr int PT_CONS = PEER_THREADS - 32;   // consumer threads (warps 0..30); warp 31 lane 0 drives the TMA loads
+constexpr int PT_CONS = PEER_THREADS - 32;   // consumer threads (warps 0..30); warp 31 lane 0 drives the TMA engine
+constexpr int PT_CWARPS = PT_CONS / 32;
 __device__ __forceinline__ void pt_wait(uint64_t *bar, uint32_t parity, uint32_t *err)
 {
     const unsigned long long t0 = globaltimer_ns();
@@ -155,19 +156,30 @@ __device__ __forceinline__ void pt_wait(uint64_t *bar, uint32_t parity, uint32_t
         }
     }
 }
+// Stage layout: [WORLD gradient chunks in rank order][this rank's weight chunk]; everything the consumers touch comes
+// out of shared memory (the first version read the local gradient and weight chunks with LDG inside the consumer loop:
+// a DRAM round trip per chunk, slower than the LDG kernel it was meant to replace).  All hand-overs are mbarriers, so the
+// 31 consumer warps run independently of one another:
+//   full[s]      TMA -> consumers   (complete_tx)          empty[s]     consumer warps -> TMA thread (count 31)
+//   out_full[b]  consumer warps -> TMA thread (count 31)    out_free[b]  TMA thread -> consumers (the bulk stores have read it)
 template <int WORLD, int CHUNK_F4, int STAGES>
 __global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_tma_kernel(PeerPtrs P, int rank, int off, int count4, float alpha, uint32_t epoch)
 {
     constexpr int CHUNK_B = CHUNK_F4 * 16;
+    constexpr int SLOTS = WORLD + 1;
     extern __shared__ uint8_t pt_raw[];
     uint8_t *sm = pt_raw + ((128u - (ptx::smem_u32(pt_raw) & 127u)) & 127u);
-    uint8_t *stage0 = sm;                                        // [STAGES][WORLD-1][CHUNK_B]
-    uint8_t *out0 = sm + (size_t)STAGES * (WORLD - 1) * CHUNK_B;  // [2][CHUNK_B]
-    __shared__ uint64_t full[STAGES], empty[STAGES];
+    uint8_t *stage0 = sm;                                     // [STAGES][SLOTS][CHUNK_B]
+    uint8_t *out0 = sm + (size_t)STAGES * SLOTS * CHUNK_B;    // [2][CHUNK_B]
+    __shared__ uint64_t full[STAGES], empty[STAGES], out_full[2], out_free[2];
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], 1);
+            ptx::mbar_init(&empty[s], PT_CWARPS);
+        }
+        for (int b = 0; b < 2; b++) {
+            ptx::mbar_init(&out_full[b], PT_CWARPS);
+            ptx::mbar_init(&out_free[b], 1);
         }
         ptx::fence_barrier_init();
     }
@@ -175,63 +187,74 @@ __global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_tma_kernel(PeerPtrs 
     ptx::fence_proxy_async_all();                           // the bulk (async-proxy) reads below come after the barrier's acquire
     const int lo = (int)((int64_t)count4 * rank / WORLD), hi = (int)((int64_t)count4 * (rank + 1) / WORLD);
     const int nchunks = (hi - lo + CHUNK_F4 - 1) / CHUNK_F4;
-    const int warp = threadIdx.x >> 5;
+    const int my_chunks = (nchunks > (int)blockIdx.x) ? (nchunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto chunk_range = [&](int k, int &f0, int &nf) {
+        f0 = lo + ((int)blockIdx.x + k * (int)gridDim.x) * CHUNK_F4;
+        nf = (hi - f0 < CHUNK_F4) ? hi - f0 : CHUNK_F4;
+    };
     if (warp == 31) {
-        if ((threadIdx.x & 31) == 0) {
-            int k = 0;
-            for (int c = blockIdx.x; c < nchunks; c += gridDim.x, k++) {
+        if (lane == 0) {
+            auto load = [&](int k) {
                 const int sg = k % STAGES;
+                int f0, nf;
+                chunk_range(k, f0, nf);
                 pt_wait(&empty[sg], ((k / STAGES) & 1) ^ 1, P.error);
-                const int f0 = lo + c * CHUNK_F4, nf = (hi - f0 < CHUNK_F4) ? hi - f0 : CHUNK_F4;
-                ptx::mbar_expect_tx(&full[sg], (uint32_t)(nf * 16 * (WORLD - 1)));
+                ptx::mbar_expect_tx(&full[sg], (uint32_t)(nf * 16 * SLOTS));
+                uint8_t *st = stage0 + (size_t)sg * SLOTS * CHUNK_B;
 #pragma unroll
-                for (int p = 0; p < WORLD; p++) {
-                    if (p == rank) continue;
-                    const int slot = p < rank ? p : p - 1;
-                    ptx::bulk_load_1d(stage0 + ((size_t)sg * (WORLD - 1) + slot) * CHUNK_B, reinterpret_cast<const float4 *>(P.grads[p] + off) + f0,
-                                      (uint32_t)(nf * 16), &full[sg]);
+                for (int p = 0; p < WORLD; p++)
+                    ptx::bulk_load_1d(st + (size_t)p * CHUNK_B, reinterpret_cast<const float4 *>(P.grads[p] + off) + f0, (uint32_t)(nf * 16), &full[sg]);
+                ptx::bulk_load_1d(st + (size_t)WORLD * CHUNK_B, reinterpret_cast<const float4 *>(P.params[rank] + off) + f0, (uint32_t)(nf * 16), &full[sg]);
+            };
+            for (int k = 0; k < STAGES - 1 && k < my_chunks; k++) load(k);
+            for (int k = 0; k < my_chunks; k++) {
+                if (k + STAGES - 1 < my_chunks) load(k + STAGES - 1);
+                const int ob = k & 1;
+                int f0, nf;
+                chunk_range(k, f0, nf);
+                pt_wait(&out_full[ob], (k >> 1) & 1, P.error);   // every consumer warp has written (and proxy-fenced) its part
+                const uint8_t *ot = out0 + (size_t)ob * CHUNK_B;
+#pragma unroll
+                for (int p = 0; p < WORLD; p++)   // the owner's own store goes through the same engine
+                    ptx::bulk_store_1d(reinterpret_cast<float4 *>(P.params[p] + off) + f0, ot, (uint32_t)(nf * 16));
+                ptx::bulk_commit();
+                if (k >= 1) {   // the stores of chunk k-1 have read their out buffer: hand it back
+                    ptx::bulk_wait_read<1>();
+                    ptx::mbar_arrive(&out_free[(k - 1) & 1]);
                 }
             }
+            ptx::bulk_wait<0>();      // every store of this CTA has been performed
+            __threadfence_system();
         }
     } else {
         const int t = threadIdx.x;   // 0 .. PT_CONS-1
-        int k = 0;
-        for (int c = blockIdx.x; c < nchunks; c += gridDim.x, k++) {
+        for (int k = 0; k < my_chunks; k++) {
             const int sg = k % STAGES, ob = k & 1;
-            const int f0 = lo + c * CHUNK_F4, nf = (hi - f0 < CHUNK_F4) ? hi - f0 : CHUNK_F4;
-            // the bulk stores that read out buffer `ob` two chunks ago must have finished reading it
-            if (t == 0) ptx::bulk_wait_read<1>();
-            ptx::named_bar_sync(1, PT_CONS);
+            int f0, nf;
+            chunk_range(k, f0, nf);
             pt_wait(&full[sg], (k / STAGES) & 1, P.error);
-            const float4 *st = reinterpret_cast<const float4 *>(stage0 + (size_t)sg * (WORLD - 1) * CHUNK_B);
+            if (k >= 2) pt_wait(&out_free[ob], ((k >> 1) - 1) & 1, P.error);   // chunk k-2's stores no longer read this buffer
+            const float4 *st = reinterpret_cast<const float4 *>(stage0 + (size_t)sg * SLOTS * CHUNK_B);
             float4 *ot = reinterpret_cast<float4 *>(out0 + (size_t)ob * CHUNK_B);
             for (int i = t; i < nf; i += PT_CONS) {
-                const float4 mine = reinterpret_cast<const float4 *>(P.grads[rank] + off)[f0 + i];
-                float4 s = rank == 0 ? mine : st[i];   // rank order 0..G-1 on every owner: deterministic
+                float4 s = st[i];   // rank order 0..G-1 on every owner: deterministic, same bits as peer_sgd_kernel
 #pragma unroll
                 for (int p = 1; p < WORLD; p++) {
-                    const float4 v = (p == rank) ? mine : st[(p < rank ? p : p - 1) * CHUNK_F4 + i];
+                    const float4 v = st[p * CHUNK_F4 + i];
                     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
                 }
-                float4 w = reinterpret_cast<const float4 *>(P.params[rank] + off)[f0 + i];
+                float4 w = st[WORLD * CHUNK_F4 + i];
                 w.x = fmaf(-alpha, s.x, w.x); w.y = fmaf(-alpha, s.y, w.y);
                 w.z = fmaf(-alpha, s.z, w.z); w.w = fmaf(-alpha, s.w, w.w);
-                reinterpret_cast<float4 *>(P.params[rank] + off)[f0 + i] = w;
                 ot[i] = w;
             }
-            ptx::fence_proxy_async();          // this thread's out-buffer writes -> visible to the bulk stores
-            ptx::named_bar_sync(1, PT_CONS);   // every consumer has read the stage and written its part of the out buffer
-            if (t == 0) {
+            ptx::fence_proxy_async();   // this thread's out-buffer writes -> visible to the bulk stores
+            __syncwarp();
+            if (lane == 0) {
                 ptx::mbar_arrive(&empty[sg]);
-#pragma unroll
-                for (int p = 0; p < WORLD; p++)
-                    if (p != rank) ptx::bulk_store_1d(reinterpret_cast<float4 *>(P.params[p] + off) + f0, ot, (uint32_t)(nf * 16));
-                ptx::bulk_commit();
+                ptx::mbar_arrive(&out_full[ob]);
             }
-        }
-        if (t == 0) {
-            ptx::bulk_wait<0>();      // every peer store of this CTA has been performed
-            __threadfence_system();
         }
     }
     peer_barrier<WORLD>(P, rank, epoch + 2);
@@ -240,7 +263,7 @@ __global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_tma_kernel(PeerPtrs 
 template <int WORLD, int CHUNK_F4, int STAGES>
 static int launch_peer_tma(PeerState *ps, int blocks, int off, int count4, float alpha, uint32_t epoch, cudaStream_t s)
 {
-    constexpr int SMEM = (STAGES * (WORLD - 1) + 2) * CHUNK_F4 * 16 + 128;
+    constexpr int SMEM = (STAGES * (WORLD + 1) + 2) * CHUNK_F4 * 16 + 128;
     static_assert(SMEM <= 227 * 1024, "peer exchange tile too large");
     static bool attr = false;
     if (!attr) {
@@ -313,14 +336,14 @@ int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
     static const bool use_tma = !(getenv("HP_PEER_TMA") && getenv("HP_PEER_TMA")[0] == '0');   // HP_PEER_TMA=0: the LDG/STG kernel (A/B runs)
     if (use_tma) {
         int rc = 2;
-        switch (ps->world) {   // bytes in flight per CTA = STAGES x (G-1) x chunk: ~130-170 KB
-        case 2: rc = launch_peer_tma<2, 2048, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 3: rc = launch_peer_tma<3, 1024, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 4: rc = launch_peer_tma<4, 1024, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 5: rc = launch_peer_tma<5, 512, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 6: rc = launch_peer_tma<6, 512, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 7: rc = launch_peer_tma<7, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 8: rc = launch_peer_tma<8, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
+        switch (ps->world) {   // stage = (G + 1) chunks; STAGES x stage + 2 out buffers <= ~190 KB
+        case 2: rc = launch_peer_tma<2, 1024, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 3: rc = launch_peer_tma<3, 1024, 2>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 4: rc = launch_peer_tma<4, 512, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 5: rc = launch_peer_tma<5, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 6: rc = launch_peer_tma<6, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 7: rc = launch_peer_tma<7, 512, 2>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 8: rc = launch_peer_tma<8, 512, 2>(ps, blocks, off, count4, alpha, epoch, s); break;
         default: set_error("peer path supports 2..8 ranks, got %d", ps->world); return 2;
         }
         if (rc) return rc;
