@@ -462,6 +462,7 @@ int hp_destroy(hp_net *net)
     Net &n = net->n;
     cudaSetDevice(n.device);
     cudaDeviceSynchronize();
+    if (n.step_graph.exec) cudaGraphExecDestroy(n.step_graph.exec);
     if (n.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n.nccl_comm);
     if (n.peer) peer_shutdown(n);   // normally done by hp_dp_shutdown after a host-side barrier
     tc_destroy(n);
@@ -866,6 +867,14 @@ int hp_apply_grads_device(hp_net *net, float alpha, void *stream)
     return sgd_apply(net->n, alpha, (cudaStream_t)stream);
 }
 
+// One step, eagerly: forward + backward on the caller's stream, the update tail pipelined on the side streams.
+static int train_step_eager(Net &N, const float *x_dev, const float *t_dev, int64_t n, float alpha, float *mse_dev, int precision, cudaStream_t s)
+{
+    HP_CUDA_TRY(cudaEventRecord(N.ev_start, s));
+    if (int rc = grad_device(N, x_dev, t_dev, n, mse_dev, precision, s)) return rc;
+    return finish_step(N, alpha, precision, s);
+}
+
 int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, int64_t n, float alpha, float *mse_dev, int precision,
                           void *stream)
 {
@@ -876,9 +885,51 @@ int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, i
     HP_CUDA_TRY(cudaSetDevice(N.device));
     if (int rc = check_peer(N)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    HP_CUDA_TRY(cudaEventRecord(N.ev_start, s));
-    if (int rc = grad_device(N, x_dev, t_dev, n, mse_dev, precision, s)) return rc;
-    return finish_step(N, alpha, precision, s);
+    Net::StepGraph &G = N.step_graph;
+    static const bool no_graph = getenv("HP_NO_GRAPH") != nullptr;
+    // graph replay: single GPU, one workspace chunk, nothing that needs host-visible events, shadows in step with the weights.
+    // The legacy NULL stream cannot be captured.
+    const bool eligible = !no_graph && !G.disabled && N.world == 1 && !N.profiling && !N.step_timing && n <= FP32_CHUNK && s != nullptr &&
+                          !(precision == HP_PRECISION_TENSOR && N.tc_dirty);
+    const bool same = G.x == x_dev && G.t == t_dev && G.mse == mse_dev && G.n == n && G.alpha == alpha && G.precision == precision && G.stream == s;
+    if (!eligible || !same) {
+        if (!same) {
+            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+            G.x = x_dev; G.t = t_dev; G.mse = mse_dev; G.n = n; G.alpha = alpha; G.precision = precision; G.stream = s;
+            G.seen = 0;
+        }
+        if (eligible) G.seen = 1;
+        return train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s);
+    }
+    if (!G.exec) {
+        if (G.seen < 1) { G.seen = 1; return train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s); }
+        // second call with the same arguments: every buffer exists by now (the eager step allocated them), so capture
+        const int64_t l0 = N.launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            G.disabled = true;
+            return train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s);
+        }
+        const int rc = train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        G.launches_per_step = N.launches - l0;
+        N.launches = l0;
+        if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            G.exec = nullptr;
+            G.disabled = true;   // something in the step is not capturable here: stay eager
+            N.tc_dirty = true;   // host-side flags advanced during the aborted capture; the shadows were not actually refreshed
+            return train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s);
+        }
+        cudaGraphDestroy(graph);
+    }
+    HP_CUDA_TRY(cudaGraphLaunch(G.exec, s));
+    N.launches += G.launches_per_step;
+    N.last_n = std::min<int64_t>(n, FP32_CHUNK);
+    N.tc_dirty = (precision != HP_PRECISION_TENSOR);
+    return HP_OK;
 }
 
 int hp_train_batch(hp_net *net, const float *x, const float *t, int64_t n, float alpha, float *mse_out, int precision)

@@ -145,6 +145,19 @@ struct Net {
     __nv_bfloat16 *grads_bf = nullptr;    // wire buffer, .cnnb order
     bool step_timing = false;
     int64_t launches = 0;
+    // One optimiser step as a CUDA graph (single GPU): the ~30 launches + ~15 event hops of a batch-256 step cost more on the
+    // host than the kernels run on the device.  Keyed on the call's arguments; captured the second time a key repeats.
+    struct StepGraph {
+        const void *x = nullptr, *t = nullptr, *mse = nullptr;
+        int64_t n = 0;
+        float alpha = 0.f;
+        int precision = -1;
+        cudaStream_t stream = nullptr;
+        int seen = 0;                 // consecutive calls with this key
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches_per_step = 0;
+        bool disabled = false;        // HP_NO_GRAPH=1, or a capture failed once
+    } step_graph;
     int64_t last_n = 0;
     // per-stage timing (hp_profile): a pool of events, (stage, begin, end) triples
     bool profiling = false;
