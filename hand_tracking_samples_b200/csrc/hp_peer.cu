@@ -333,7 +333,11 @@ int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
     if (blocks > ps->max_blocks) blocks = ps->max_blocks;
     if (blocks < 1) blocks = 1;
     ps->epoch += 2;
-    static const bool use_tma = !(getenv("HP_PEER_TMA") && getenv("HP_PEER_TMA")[0] == '0');   // HP_PEER_TMA=0: the LDG/STG kernel (A/B runs)
+    // HP_PEER_TMA=1 selects the TMA variant.  Measured at 2 GPUs (profiles/r2_dp_exchange.md) the two are equal (278-288 us
+    // per step) and flat in the number of exchange CTAs beyond 16: the step is then bounded by the structure around the
+    // exchange (exposed conv bucket + shadow refresh, SM reservation), not by the bytes in flight; the LDG kernel, which
+    // round 1 validated on 8 GPUs, stays the default.
+    static const bool use_tma = getenv("HP_PEER_TMA") && getenv("HP_PEER_TMA")[0] == '1';
     if (use_tma) {
         int rc = 2;
         switch (ps->world) {   // stage = (G + 1) chunks; STAGES x stage + 2 out buffers <= ~190 KB
