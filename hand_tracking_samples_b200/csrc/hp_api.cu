@@ -634,11 +634,17 @@ static int eval_host_pipeline(Net &N, const void *x, int elem, const DepthNorm *
         HP_CUDA_TRY(cudaEventRecord(N.ev_in[b], h2d));
         HP_CUDA_TRY(cudaStreamWaitEvent(s, N.ev_in[b], 0));
         const float *xin = N.dev_in[b];
-        if (norm && precision == HP_PRECISION_TENSOR && !N.tc->conv_v1) {
-            // tensor path: the 16-bit depth goes straight into the conv kernel, which normalises in its loader
+        bool decoded_in_epilogue = false;
+        if (precision == HP_PRECISION_TENSOR && !N.tc->conv_v1 && (norm || dec)) {
+            // tensor path: 16-bit depth goes straight into the conv kernel, which normalises in its loader, and the decode
+            // runs in the fc2 epilogue (when y is not wanted it never exists in HBM)
             if (N.tc_dirty)
                 if (int rc = tc_refresh_weights(N, s)) return rc;
-            if (int rc = tc_forward_u16(N, (const uint16_t *)N.dev_in[b], norm->scale, norm->dmin, norm->dmax, m, N.dev_out[b], s)) return rc;
+            if (int rc = tc_forward_decode(N, norm ? nullptr : N.dev_in[b], norm ? (const uint16_t *)N.dev_in[b] : nullptr, norm ? norm->scale : 0.f,
+                                           norm ? norm->dmin : 0.f, norm ? norm->dmax : 1.f, m, (y || !dec) ? N.dev_out[b] : nullptr,
+                                           dec ? N.dev_dec[b] : nullptr, s))
+                return rc;
+            decoded_in_epilogue = dec != nullptr;
         } else {
             if (norm) {
                 if (int rc = post_normalize_depth(N, (const uint16_t *)N.dev_in[b], m, norm->scale, norm->dmin, norm->dmax, N.dev_norm[b], s)) return rc;
@@ -646,7 +652,7 @@ static int eval_host_pipeline(Net &N, const void *x, int elem, const DepthNorm *
             }
             if (int rc = eval_device(N, xin, m, N.dev_out[b], precision, s, n)) return rc;
         }
-        if (dec)
+        if (dec && !decoded_in_epilogue)
             if (int rc = post_decode(N, N.dev_out[b], m, N.dev_dec[b], s)) return rc;
         HP_CUDA_TRY(cudaEventRecord(N.ev_comp[b], s));
         HP_CUDA_TRY(cudaStreamWaitEvent(d2h, N.ev_comp[b], 0));
@@ -697,7 +703,7 @@ int hp_eval_depth_batch(hp_net *net, const uint16_t *depth, int64_t n, float dep
 int hp_eval_depth_batch_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax, float *y_dev,
                                float *decoded_dev, int precision, void *stream)
 {
-    if (!net || n < 0 || (n && (!depth_dev || !y_dev)) || !(dmax > dmin)) { set_error("bad argument"); return HP_ERR_INVALID; }
+    if (!net || n < 0 || (n && (!depth_dev || (!y_dev && !decoded_dev))) || !(dmax > dmin)) { set_error("bad argument"); return HP_ERR_INVALID; }
     if (int rc = check_precision(precision)) return rc;
     if (n == 0) return HP_OK;
     Net &N = net->n;
@@ -706,18 +712,18 @@ int hp_eval_depth_batch_device(hp_net *net, const uint16_t *depth_dev, int64_t n
     if (precision == HP_PRECISION_TENSOR && !N.tc->conv_v1) {
         if (N.tc_dirty)
             if (int rc = tc_refresh_weights(N, s)) return rc;
-        if (int rc = tc_forward_u16(N, depth_dev, depth_scale, dmin, dmax, n, y_dev, s)) return rc;
-    } else {
-        // FP32 path: normalise chunk by chunk into the staging buffer (bit-identical values), then Eval
-        for (int64_t b = 0; b < n; b += STAGE_CHUNK) {
-            const int64_t m = std::min<int64_t>(STAGE_CHUNK, n - b);
-            if (int rc = ensure_staging(N, m, false, false)) return rc;
-            if (int rc = post_normalize_depth(N, depth_dev + b * N_IN, m, depth_scale, dmin, dmax, N.dev_norm[0], s)) return rc;
-            if (int rc = eval_device(N, N.dev_norm[0], m, y_dev + b * N_OUT, precision, s, n)) return rc;
-        }
+        return tc_forward_decode(N, nullptr, depth_dev, depth_scale, dmin, dmax, n, y_dev, decoded_dev, s);
     }
-    if (decoded_dev)
-        if (int rc = post_decode(N, y_dev, n, decoded_dev, s)) return rc;
+    // FP32 path (and the round-1 conv kernel): normalise chunk by chunk into the staging buffer (bit-identical values), then Eval
+    for (int64_t b = 0; b < n; b += STAGE_CHUNK) {
+        const int64_t m = std::min<int64_t>(STAGE_CHUNK, n - b);
+        if (int rc = ensure_staging(N, m, false, false)) return rc;
+        float *yb = y_dev ? y_dev + b * N_OUT : N.dev_out[0];
+        if (int rc = post_normalize_depth(N, depth_dev + b * N_IN, m, depth_scale, dmin, dmax, N.dev_norm[0], s)) return rc;
+        if (int rc = eval_device(N, N.dev_norm[0], m, yb, precision, s, n)) return rc;
+        if (decoded_dev)
+            if (int rc = post_decode(N, yb, m, decoded_dev + b * 48, s)) return rc;
+    }
     return HP_OK;
 }
 
@@ -739,7 +745,7 @@ int hp_eval_frames_device(hp_net *net, const uint16_t *frames_dev, int32_t width
                           const int32_t *frame_of_crop_dev, const float *dst_cams_dev, int64_t n, uint16_t background, float depth_scale,
                           float dmin, float dmax, float *y_dev, float *decoded_dev, int precision, void *stream)
 {
-    if (!net || n < 0 || width <= 0 || height <= 0 || !src_intrinsics || (n && (!frames_dev || !dst_cams_dev || !y_dev)) || !(dmax > dmin)) {
+    if (!net || n < 0 || width <= 0 || height <= 0 || !src_intrinsics || (n && (!frames_dev || !dst_cams_dev || (!y_dev && !decoded_dev))) || !(dmax > dmin)) {
         set_error("bad argument");
         return HP_ERR_INVALID;
     }
@@ -758,8 +764,8 @@ int hp_eval_frames_device(hp_net *net, const uint16_t *frames_dev, int32_t width
         if (int rc = post_sample_d(N, fr, width, height, src_intrinsics, frame_of_crop_dev ? frame_of_crop_dev + b : nullptr,
                                    dst_cams_dev + b * HP_RESAMPLE_CAM_FLOATS, m, background, crops, s))
             return rc;
-        if (int rc = hp_eval_depth_batch_device(net, crops, m, depth_scale, dmin, dmax, y_dev + b * N_OUT, decoded_dev ? decoded_dev + b * 48 : nullptr,
-                                                precision, stream))
+        if (int rc = hp_eval_depth_batch_device(net, crops, m, depth_scale, dmin, dmax, y_dev ? y_dev + b * N_OUT : nullptr,
+                                                decoded_dev ? decoded_dev + b * 48 : nullptr, precision, stream))
             return rc;
     }
     return HP_OK;

@@ -105,6 +105,8 @@ int post_render_labels(Net &net, const float *points, const float *vals, int64_t
 // ---- tensor-core path launchers (hp_tc.cu) -----------------------------------
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s);
 int tc_forward_u16(Net &net, const uint16_t *depth, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, cudaStream_t s);
+int tc_forward_decode(Net &net, const float *x, const uint16_t *x16, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, float *dec_out,
+                      cudaStream_t s);
 int tc_refresh_weights(Net &net, cudaStream_t s);
 int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s);   // 0: fc2 shadows, 1: fc1 shadows, 2: conv images
 int tc_init(Net &net);

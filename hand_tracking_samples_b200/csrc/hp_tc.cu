@@ -44,7 +44,7 @@ constexpr int STG_BYTES = 4096;                 // per-warp output staging tile:
 constexpr int GEMM_THREADS = 256;
 constexpr int gemm_smem(int bn) { return stages_for(bn) * (A_BYTES + bn * BK * 2) + 8 * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
 
-enum { TC_EPI_TANH_ACT = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3, TC_EPI_STORE_BF16 = 4 };
+enum { TC_EPI_TANH_ACT = 0, TC_EPI_SOFTMAX_F32 = 1, TC_EPI_STORE_F32 = 2, TC_EPI_DTANH = 3, TC_EPI_STORE_BF16 = 4, TC_EPI_SOFTMAX_DECODE = 5 };
 enum { TC_FLAG_ACCUMULATE = 1, TC_FLAG_ROWS_HWC_TO_CHW = 2 };
 
 struct EpiArgs {
@@ -55,6 +55,8 @@ struct EpiArgs {
     int flags;                 // STORE_F32: TC_FLAG_ACCUMULATE (out += acc), TC_FLAG_ROWS_HWC_TO_CHW (row k' -> (k'&63)*36 + (k'>>6))
     int ksplit;                // STORE_F32 only, 0/1 = off: K is cut into ksplit ranges of whole 64-blocks, every (range, tile) pair is a
                                // work item and range r stores its partial product at out + r*M*N (long-K, small-output weight gradients)
+    float *decoded;            // SOFTMAX_DECODE: [M][48] decoded peaks (CNNOutputAnalysis, include/handtrack.h:218-241); `out` (y) may be null
+    float *scratch;            // SOFTMAX_DECODE: [gridDim.x][128][256] floats, the CTA's current y tile (stays in L2)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -109,7 +111,7 @@ template <int EPI, int BN, bool OPS_F16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs ea, int M, int N, int K)
 {
-    static_assert(EPI != TC_EPI_SOFTMAX_F32 || BN == 256, "the fused chunked softmax needs whole 256-wide spans in one tile");
+    static_assert((EPI != TC_EPI_SOFTMAX_F32 && EPI != TC_EPI_SOFTMAX_DECODE) || BN == 256, "the fused chunked softmax needs whole 256-wide spans in one tile");
     constexpr int STAGES = stages_for(BN);
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -284,7 +286,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     flush(c & 1, v, gtile + c * 128, (size_t)N * 2);
                 }
-            } else if (EPI == TC_EPI_SOFTMAX_F32) {
+            } else if (EPI == TC_EPI_SOFTMAX_F32 || EPI == TC_EPI_SOFTMAX_DECODE) {
                 uint8_t *gtile = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 4;
                 const bool big = (n_blk * BN) < N_BIG_SPANS * BIG_SPAN;  // one 256-wide span vs sixteen 16-wide spans
                 constexpr float LOG2E = 1.4426950408889634f;
@@ -305,6 +307,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     inv = 1.0f / sum;
                 }
+                // SOFTMAX_DECODE: the numeric core of CNNOutputAnalysis (include/handtrack.h:218-241) on this thread's own row
+                // while it is still on chip.  The row's 256 softmax values go to a per-CTA scratch tile (re-written every
+                // tile, so it lives in L2) only because the 3x3 / 5x5 neighbourhoods around a data-dependent peak need
+                // indexed access; the running argmax works on the registers: per 32-column chunk its maximum (NaN-ignoring,
+                // like `>` in ImageFindMax, misc_image.h:300-304), and the FIRST chunk whose maximum is strictly greater
+                // wins, so the first raster-order maximum lies in that chunk and is found by one 32-value scan afterwards.
+                const int drow = m_blk * BM + ew * 32 + lane;
+                float *srow = (EPI == TC_EPI_SOFTMAX_DECODE) ? ea.scratch + ((size_t)blockIdx.x * BM + ew * 32 + lane) * 256 : nullptr;
+                float best = -1.0f;
+                int bchunk = 0;
+                bool nan00 = false;
+                unsigned long long p1d = 0;   // Peaks1D arg-max of the sixteen 16-wide spans, 4 bits each
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; c++) {   // 32 columns = 128 B of fp32 per row
                     uint32_t r[32];
@@ -327,14 +341,85 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         i0 = 1.0f / s0;
                         i1 = 1.0f / s1;
                     }
+                    float yv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) yv[j] = v[j] * ((j < 16) ? i0 : i1);
                     uint4 o[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const float sc = (q < 4) ? i0 : i1;
-                        o[q] = make_uint4(__float_as_uint(v[q * 4] * sc), __float_as_uint(v[q * 4 + 1] * sc), __float_as_uint(v[q * 4 + 2] * sc),
-                                          __float_as_uint(v[q * 4 + 3] * sc));
+                    for (int q = 0; q < 8; q++)
+                        o[q] = make_uint4(__float_as_uint(yv[q * 4]), __float_as_uint(yv[q * 4 + 1]), __float_as_uint(yv[q * 4 + 2]), __float_as_uint(yv[q * 4 + 3]));
+                    if (EPI == TC_EPI_SOFTMAX_DECODE) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) reinterpret_cast<float4 *>(srow + c * 32)[q] = make_float4(yv[q * 4], yv[q * 4 + 1], yv[q * 4 + 2], yv[q * 4 + 3]);
+                        if (big) {
+                            float mc = fmaxf(yv[0], yv[1]);
+#pragma unroll
+                            for (int j = 2; j < 32; j++) mc = fmaxf(mc, yv[j]);
+                            if (mc > best) { best = mc; bchunk = c; }
+                            if (c == 0) nan00 = yv[0] != yv[0];
+                        } else {
+#pragma unroll
+                            for (int sp = 0; sp < 2; sp++) {   // Peaks1D, misc_image.h:389-399: if (r[p] < r[x]) p = x
+                                float pv = yv[16 * sp];
+                                int pi = 0;
+#pragma unroll
+                                for (int xx = 1; xx < 16; xx++)
+                                    if (pv < yv[16 * sp + xx]) { pv = yv[16 * sp + xx]; pi = xx; }
+                                p1d |= (unsigned long long)pi << (4 * (2 * c + sp));
+                            }
+                        }
+                        if (out) flush(c & 1, o, gtile + c * 128, (size_t)N * 4);
+                    } else {
+                        flush(c & 1, o, gtile + c * 128, (size_t)N * 4);
                     }
-                    flush(c & 1, o, gtile + c * 128, (size_t)N * 4);
+                }
+                if (EPI == TC_EPI_SOFTMAX_DECODE && drow < M) {
+                    float *dec = ea.decoded + (size_t)drow * 48;
+                    if (big) {
+                        // ImageFindMax: the first element of the winning chunk that equals the maximum; pixel (0,0) NaN keeps (0,0)
+                        int bi = 0;
+                        if (!nan00) {
+                            const float *ch = srow + bchunk * 32;
+                            bi = bchunk * 32 + 31;
+#pragma unroll 1
+                            for (int j = 30; j >= 0; j--)
+                                if (ch[j] == best) bi = bchunk * 32 + j;
+                        }
+                        const float *mp = srow;
+                        const int bx = bi & 15, by = bi >> 4;
+                        float wsum = 0.0f, vx = 0.0f, vy = 0.0f;
+                        for (int sy_ = max(0, by - 1); sy_ < min(16, by + 2); sy_++)
+                            for (int sx = max(0, bx - 1); sx < min(16, bx + 2); sx++) {   // PeakSubPixel, misc_image.h:316-322
+                                const float w = mp[sy_ * 16 + sx];
+                                vx = __fadd_rn(vx, __fmul_rn((float)sx, w));
+                                vy = __fadd_rn(vy, __fmul_rn((float)sy_, w));
+                                wsum = __fadd_rn(wsum, w);
+                            }
+                        const float px = (wsum == 0) ? (float)bx : __fdiv_rn(vx, wsum);
+                        const float py = (wsum == 0) ? (float)by : __fdiv_rn(vy, wsum);
+                        // PeakVolume, misc_image.h:330 (float -> int as the pinned x86 build converts it, see hp_post.cu)
+                        const float fx = __fadd_rn(px, 0.5f), fy = __fadd_rn(py, 0.5f);
+                        const bool x_ok = fx >= -2147483648.0f && fx < 2147483648.0f, y_ok = fy >= -2147483648.0f && fy < 2147483648.0f;
+                        const int rx = x_ok ? (int)fx : 0, ry = y_ok ? (int)fy : 0;
+                        float vol = 0.0f;
+                        if (x_ok && y_ok)
+                            for (int sy_ = max(0, ry - 1); sy_ < min(16, ry + 2); sy_++)
+                                for (int sx = max(0, rx - 1); sx < min(16, rx + 2); sx++) vol = __fadd_rn(vol, mp[sy_ * 16 + sx]);
+                        *reinterpret_cast<float4 *>(dec + 4 * n_blk) = make_float4(px, py, vol, mp[bi]);
+                    } else {
+#pragma unroll 1
+                        for (int sp = 0; sp < 16; sp++) {
+                            const float *r1 = srow + 16 * sp;
+                            const int pi = (int)((p1d >> (4 * sp)) & 15);
+                            float vv = 0.0f, wsum = 0.0f;
+                            for (int i = max(0, pi - 1); i < min(16, pi + 2); i++) {
+                                const float w = r1[i];
+                                vv = __fadd_rn(vv, __fmul_rn((float)i, w));
+                                wsum = __fadd_rn(wsum, w);
+                            }
+                            dec[32 + sp] = __fdiv_rn((wsum == 0) ? (float)pi : __fdiv_rn(vv, wsum), 15.0f);
+                        }
+                    }
                 }
             }
             if (EPI == TC_EPI_STORE_F32) {
@@ -712,6 +797,7 @@ int tc_init(Net &net)
     HP_GEMM_ATTR(TC_EPI_TANH_ACT, 256, true);
     HP_GEMM_ATTR(TC_EPI_TANH_ACT, 64, true);
     HP_GEMM_ATTR(TC_EPI_SOFTMAX_F32, 256, true);
+    HP_GEMM_ATTR(TC_EPI_SOFTMAX_DECODE, 256, true);
     HP_GEMM_ATTR(TC_EPI_STORE_F32, 64, true);      // fc2 logits at small batch
     HP_GEMM_ATTR(TC_EPI_STORE_F32, 256, false);    // weight gradients
     HP_GEMM_ATTR(TC_EPI_STORE_F32, 128, false);
@@ -743,6 +829,7 @@ void tc_destroy(Net &net)
     if (t->b1_img) cudaFree(t->b1_img);
     if (t->b2_img) cudaFree(t->b2_img);
     if (t->a2_img) cudaFree(t->a2_img);
+    if (t->dec_scratch) cudaFree(t->dec_scratch);
     if (t->p2) cudaFree(t->p2);
     if (t->h1) cudaFree(t->h1);
     delete t;
@@ -798,9 +885,12 @@ static int tc_ensure(Net &net, int64_t n)
 }
 
 // x16 != nullptr: the crops arrive as 16-bit depth and include/handtrack.h:700 runs inside the conv kernel's loader
-static int tc_forward_impl(Net &net, const float *x, const uint16_t *x16, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, cudaStream_t s)
+// dec_out != nullptr: the decode runs in the fc2 epilogue (y_out may then be null: the 9.2 KB per crop never reach HBM)
+static int tc_forward_impl(Net &net, const float *x, const uint16_t *x16, float depth_scale, float dmin, float dmax, int64_t n, float *y_out,
+                           float *dec_out, cudaStream_t s)
 {
     TcState *t = net.tc;
+    if (dec_out && !t->dec_scratch) HP_CUDA_TRY(cudaMalloc((void **)&t->dec_scratch, (size_t)t->total_sms * BM * 256 * sizeof(float)));
     for (int64_t b = 0; b < n; b += TC_CHUNK) {
         const int64_t m = (n - b < TC_CHUNK) ? n - b : TC_CHUNK;
         if (int rc = tc_ensure(net, m)) return rc;
@@ -823,8 +913,14 @@ static int tc_forward_impl(Net &net, const float *x, const uint16_t *x16, float 
             StageTimer st(net, 2, s);
             const int tiles = m_tiles * (FC2_OUT / 256);
             const int grid = tiles < t->num_sms ? tiles : t->num_sms;
-            EpiArgs ea{net.params + OFF_F2B, y_out + b * N_OUT, nullptr, nullptr, 0};
-            tc_gemm_kernel<TC_EPI_SOFTMAX_F32, 256, true><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
+            EpiArgs ea{net.params + OFF_F2B, y_out ? y_out + b * N_OUT : nullptr, nullptr, nullptr, 0};
+            if (dec_out) {
+                ea.decoded = dec_out + b * 48;
+                ea.scratch = t->dec_scratch;
+                tc_gemm_kernel<TC_EPI_SOFTMAX_DECODE, 256, true><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
+            } else {
+                tc_gemm_kernel<TC_EPI_SOFTMAX_F32, 256, true><<<grid, GEMM_THREADS, gemm_smem(256), s>>>(t->tm_h1, t->tm_w2t, ea, (int)m, FC2_OUT, FC2_IN);
+            }
             LAUNCH_CHECK(net);
         }
     }
@@ -833,12 +929,19 @@ static int tc_forward_impl(Net &net, const float *x, const uint16_t *x16, float 
 
 int tc_forward(Net &net, const float *x, int64_t n, float *y_out, cudaStream_t s)
 {
-    return tc_forward_impl(net, x, nullptr, 0.f, 0.f, 1.f, n, y_out, s);
+    return tc_forward_impl(net, x, nullptr, 0.f, 0.f, 1.f, n, y_out, nullptr, s);
 }
 
 int tc_forward_u16(Net &net, const uint16_t *depth, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, cudaStream_t s)
 {
-    return tc_forward_impl(net, nullptr, depth, depth_scale, dmin, dmax, n, y_out, s);
+    return tc_forward_impl(net, nullptr, depth, depth_scale, dmin, dmax, n, y_out, nullptr, s);
+}
+
+// Eval + CNNOutputAnalysis decode in one pass (decode inside the fc2 epilogue); x16 or x, y_out optional
+int tc_forward_decode(Net &net, const float *x, const uint16_t *x16, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, float *dec_out,
+                      cudaStream_t s)
+{
+    return tc_forward_impl(net, x, x16, depth_scale, dmin, dmax, n, y_out, dec_out, s);
 }
 
 template <int EPI, int BN, bool OPS_F16>

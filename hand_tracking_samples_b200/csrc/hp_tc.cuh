@@ -65,6 +65,7 @@ struct TcState {
     bool conv_tanh_accurate = false;   // HP_CONV_TANH=accurate: two-MUFU tanh in the conv epilogues too (A/B runs)
     bool conv_serial_drain = false;    // HP_CONV_PIPE=0: v2 conv kernel without the pipelined accumulator drains (A/B runs)
     bool conv_v1 = false;          // HP_CONV_V1=1: run the round-1 conv kernel (hp_tc_conv.cu) instead of hp_tc_conv2.cu
+    float *dec_scratch = nullptr;  // [SMs][128][256]: the y tile a fc2 CTA decodes in its epilogue (SOFTMAX_DECODE), L2-resident
     uint8_t *b2_img = nullptr;     // 32 KB: conv2 taps, [16 taps][2 k-chunks][64 co][8 ci] fp16 (no-swizzle core matrices)
     __nv_bfloat16 *w1b = nullptr;  // [2304 (k' HWC)][2048] = fc1.W as stored (B operand of the fc1 dX GEMM)
     __nv_bfloat16 *w2b = nullptr;  // [2048][2304] = fc2.W as stored

@@ -152,9 +152,11 @@ HP_API int hp_eval_decode_batch(hp_net *net, const float *x, int64_t n, float *y
  * on the device, bit-exactly.  The reference uses drange = {0.1, 0.7} and depth_scale = 0.001. */
 HP_API int hp_eval_depth_batch(hp_net *net, const uint16_t *depth, int64_t n, float depth_scale, float dmin, float dmax, float *y,
                                float *decoded, int precision);
-/* Same chain with DEVICE buffers on the caller's stream: depth_dev[n][4096] uint16 -> y_dev[n][2304] (required) and,
- * if decoded_dev != NULL, decoded_dev[n][48].  On the tensor path the normalisation runs inside the convolution
- * kernel's loader: no fp32 crop buffer exists in HBM (8 KB read per crop instead of 8 + 16 + 16). */
+/* Same chain with DEVICE buffers on the caller's stream: depth_dev[n][4096] uint16 -> y_dev[n][2304] and/or
+ * decoded_dev[n][48] (each optional, not both NULL).  On the tensor path the normalisation runs inside the convolution
+ * kernel's loader (no fp32 crop buffer exists in HBM: 8 KB read per crop instead of 8 + 16 + 16) and the decode runs inside
+ * the fc2 + softmax kernel's epilogue; with y_dev == NULL the 9,216 bytes of y per crop are never written either.  The
+ * decoded values equal hp_decode_batch of the same y bit for bit. */
 HP_API int hp_eval_depth_batch_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax,
                                       float *y_dev, float *decoded_dev, int precision, void *stream);
 HP_API int hp_normalize_depth_device(hp_net *net, const uint16_t *depth_dev, int64_t n, float depth_scale, float dmin, float dmax,
@@ -175,7 +177,7 @@ HP_API int hp_resample_depth_device(hp_net *net, const uint16_t *frames_dev, int
                                     uint16_t *crops_dev, void *stream);
 /* The tracker's chain from the full frame on (include/handtrack.h:698-702) without leaving the device: resample
  * (SampleD) -> normalise (handtrack.h:700, inside the convolution kernel's loader on the tensor path) -> Eval ->
- * optional decode.  y_dev[n][2304] required, decoded_dev[n][48] optional. */
+ * optional decode.  y_dev[n][2304] and decoded_dev[n][48] are each optional (not both NULL). */
 HP_API int hp_eval_frames_device(hp_net *net, const uint16_t *frames_dev, int32_t width, int32_t height, const float src_intrinsics[4],
                                  const int32_t *frame_of_crop_dev, const float *dst_cams_dev, int64_t n, uint16_t background,
                                  float depth_scale, float dmin, float dmax, float *y_dev, float *decoded_dev, int precision, void *stream);

@@ -532,6 +532,30 @@ def test_depth_upload_path(net, orc, p0):
             assert np.array_equal(decd.cpu().numpy(), orc.decode(yd.cpu().numpy()))
 
 
+def test_decode_fused_into_fc2_epilogue_is_bit_exact(net, orc, p0):
+    # tensor path: CNNOutputAnalysis' numeric core runs in the fc2 + softmax kernel's epilogue (hp_tc.cu, SOFTMAX_DECODE);
+    # it must equal the stand-alone decode of the same y bit for bit, with and without y being written
+    import torch
+    x = np.concatenate([synth.depthlike_crops(200, 141), synth.uniform_crops(100, 142),
+                        np.stack([np.full(4096, 1e3, np.float32), np.zeros(4096, np.float32)])])   # incl. a NaN row and a flat one
+    for params in (p0, peaky(p0)):
+        net.set_params(params)
+        y, dec = net.eval_decode_batch(x, precision=hp.PRECISION_TENSOR)
+        assert np.array_equal(y, net.eval_batch(x, precision=hp.PRECISION_TENSOR), equal_nan=True)
+        want = orc.decode(y)
+        assert np.array_equal(dec, want, equal_nan=True)
+        dec_only = net.eval_decode_batch(x, precision=hp.PRECISION_TENSOR, want_y=False)
+        assert np.array_equal(dec_only, want, equal_nan=True)
+    # device entry point, 16-bit depth in, decoded only (no y anywhere in HBM)
+    d = np.random.default_rng(7).integers(0, 900, (257, 4096)).astype(np.uint16)
+    dd = torch.from_numpy(d.view(np.int16)).cuda()
+    decd = torch.empty((257, 48), device="cuda")
+    net.eval_depth_batch_device(dd.data_ptr(), 257, None, decd.data_ptr(), precision=hp.PRECISION_TENSOR, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    y16, _ = net.eval_depth_batch(d, precision=hp.PRECISION_TENSOR, want_decoded=False)
+    assert np.array_equal(decd.cpu().numpy(), orc.decode(y16), equal_nan=True)
+
+
 def test_label_rendering_is_bit_exact_and_trains(net, orc, p0):
     g = golden("labels_render.npz")
     want = g["t_u8"].astype(np.float32) / np.float32(255.0)
