@@ -374,27 +374,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if (EPI == TC_EPI_SOFTMAX_DECODE && drow < M) {
+                    // Every read below is this thread's own row of the scratch tile (L2 hits); the loads of a step are issued
+                    // together (fully unrolled, predicated) so that the tail costs three L2 round trips, not one per value.
                     float *dec = ea.decoded + (size_t)drow * 48;
                     if (big) {
                         // ImageFindMax: the first element of the winning chunk that equals the maximum; pixel (0,0) NaN keeps (0,0)
-                        int bi = 0;
-                        if (!nan00) {
-                            const float *ch = srow + bchunk * 32;
-                            bi = bchunk * 32 + 31;
-#pragma unroll 1
-                            for (int j = 30; j >= 0; j--)
-                                if (ch[j] == best) bi = bchunk * 32 + j;
+                        float cv[32];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float4 f = reinterpret_cast<const float4 *>(srow + bchunk * 32)[q];
+                            cv[4 * q] = f.x; cv[4 * q + 1] = f.y; cv[4 * q + 2] = f.z; cv[4 * q + 3] = f.w;
                         }
-                        const float *mp = srow;
+                        int bi = bchunk * 32 + 31;
+#pragma unroll
+                        for (int j = 30; j >= 0; j--)
+                            if (cv[j] == best) bi = bchunk * 32 + j;
+                        if (nan00) bi = 0;
                         const int bx = bi & 15, by = bi >> 4;
+                        float w9[9];
+#pragma unroll
+                        for (int k = 0; k < 9; k++) {
+                            const int sy_ = by - 1 + k / 3, sx = bx - 1 + k % 3;
+                            w9[k] = (sy_ >= 0 && sy_ < 16 && sx >= 0 && sx < 16) ? srow[sy_ * 16 + sx] : 0.0f;
+                        }
+                        const float peak = srow[bi];
                         float wsum = 0.0f, vx = 0.0f, vy = 0.0f;
-                        for (int sy_ = max(0, by - 1); sy_ < min(16, by + 2); sy_++)
-                            for (int sx = max(0, bx - 1); sx < min(16, bx + 2); sx++) {   // PeakSubPixel, misc_image.h:316-322
-                                const float w = mp[sy_ * 16 + sx];
-                                vx = __fadd_rn(vx, __fmul_rn((float)sx, w));
-                                vy = __fadd_rn(vy, __fmul_rn((float)sy_, w));
-                                wsum = __fadd_rn(wsum, w);
+#pragma unroll
+                        for (int k = 0; k < 9; k++) {   // PeakSubPixel, misc_image.h:316-322: rows ascending, columns ascending, clipped
+                            const int sy_ = by - 1 + k / 3, sx = bx - 1 + k % 3;
+                            if (sy_ >= 0 && sy_ < 16 && sx >= 0 && sx < 16) {
+                                vx = __fadd_rn(vx, __fmul_rn((float)sx, w9[k]));
+                                vy = __fadd_rn(vy, __fmul_rn((float)sy_, w9[k]));
+                                wsum = __fadd_rn(wsum, w9[k]);
                             }
+                        }
                         const float px = (wsum == 0) ? (float)bx : __fdiv_rn(vx, wsum);
                         const float py = (wsum == 0) ? (float)by : __fdiv_rn(vy, wsum);
                         // PeakVolume, misc_image.h:330 (float -> int as the pinned x86 build converts it, see hp_post.cu)
@@ -402,20 +415,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const bool x_ok = fx >= -2147483648.0f && fx < 2147483648.0f, y_ok = fy >= -2147483648.0f && fy < 2147483648.0f;
                         const int rx = x_ok ? (int)fx : 0, ry = y_ok ? (int)fy : 0;
                         float vol = 0.0f;
-                        if (x_ok && y_ok)
-                            for (int sy_ = max(0, ry - 1); sy_ < min(16, ry + 2); sy_++)
-                                for (int sx = max(0, rx - 1); sx < min(16, rx + 2); sx++) vol = __fadd_rn(vol, mp[sy_ * 16 + sx]);
-                        *reinterpret_cast<float4 *>(dec + 4 * n_blk) = make_float4(px, py, vol, mp[bi]);
+                        if (x_ok && y_ok) {
+                            float v9[9];
+#pragma unroll
+                            for (int k = 0; k < 9; k++) {
+                                const int sy_ = ry - 1 + k / 3, sx = rx - 1 + k % 3;
+                                v9[k] = (sy_ >= 0 && sy_ < 16 && sx >= 0 && sx < 16) ? srow[sy_ * 16 + sx] : 0.0f;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 9; k++) {
+                                const int sy_ = ry - 1 + k / 3, sx = rx - 1 + k % 3;
+                                if (sy_ >= 0 && sy_ < 16 && sx >= 0 && sx < 16) vol = __fadd_rn(vol, v9[k]);
+                            }
+                        }
+                        *reinterpret_cast<float4 *>(dec + 4 * n_blk) = make_float4(px, py, vol, peak);
                     } else {
-#pragma unroll 1
+                        float r3[16][3];
+#pragma unroll
                         for (int sp = 0; sp < 16; sp++) {
-                            const float *r1 = srow + 16 * sp;
+                            const int pi = (int)((p1d >> (4 * sp)) & 15);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                const int i = pi - 1 + k;
+                                r3[sp][k] = (i >= 0 && i < 16) ? srow[16 * sp + i] : 0.0f;
+                            }
+                        }
+#pragma unroll
+                        for (int sp = 0; sp < 16; sp++) {
                             const int pi = (int)((p1d >> (4 * sp)) & 15);
                             float vv = 0.0f, wsum = 0.0f;
-                            for (int i = max(0, pi - 1); i < min(16, pi + 2); i++) {
-                                const float w = r1[i];
-                                vv = __fadd_rn(vv, __fmul_rn((float)i, w));
-                                wsum = __fadd_rn(wsum, w);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                const int i = pi - 1 + k;
+                                if (i >= 0 && i < 16) {
+                                    vv = __fadd_rn(vv, __fmul_rn((float)i, r3[sp][k]));
+                                    wsum = __fadd_rn(wsum, r3[sp][k]);
+                                }
                             }
                             dec[32 + sp] = __fdiv_rn((wsum == 0) ? (float)pi : __fdiv_rn(vv, wsum), 15.0f);
                         }
