@@ -295,7 +295,6 @@ static int eval_device(Net &net, const float *x, int64_t n, float *y, int precis
         if (net.tc_dirty) {
             if (int rc = tc_refresh_weights(net, s)) return rc;
         }
-        net.tc_call_n = call_n;   // small-call tiling is chosen per call, not per pipeline chunk
         return tc_forward(net, x, n, y, s);
     }
     net.fp32_small_call = call_n <= 64;   // one FC summation order per call, not per chunk (hp_fp32.cu, fc_small)
@@ -641,7 +640,6 @@ static int eval_host_pipeline(Net &N, const void *x, int elem, const DepthNorm *
             // runs in the fc2 epilogue (when y is not wanted it never exists in HBM)
             if (N.tc_dirty)
                 if (int rc = tc_refresh_weights(N, s)) return rc;
-            N.tc_call_n = n;
             if (int rc = tc_forward_decode(N, norm ? nullptr : N.dev_in[b], norm ? (const uint16_t *)N.dev_in[b] : nullptr, norm ? norm->scale : 0.f,
                                            norm ? norm->dmin : 0.f, norm ? norm->dmax : 1.f, m, (y || !dec) ? N.dev_out[b] : nullptr,
                                            dec ? N.dev_dec[b] : nullptr, s))

@@ -126,7 +126,6 @@ struct Net {
     Workspace ws;
     TcState *tc = nullptr;
     bool tc_dirty = true;                 // bf16 shadows stale w.r.t. params
-    int64_t tc_call_n = 0;                // tensor path: crops of the whole API call the next tc_forward chunk belongs to (0 = the chunk itself)
     bool fp32_small_call = true;          // FP32 path: the current call holds <= 64 crops in total (split-K FC kernels allowed)
     // pinned staging for HOST entry points
     float *pin_in[2] = {nullptr, nullptr};

@@ -801,30 +801,6 @@ __global__ void __launch_bounds__(256) loss_from_y(const float *__restrict__ y, 
     }
 }
 
-// LSoftMaxChunked::forward (cnn.h:497-511) from fp32 logits for the small-batch inference path, in exactly the
-// arithmetic and summation order of the fused fc2 epilogue (ex2.approx of logit * log2 e; 256-spans summed four columns
-// at a time in column order, 16-spans sequentially; multiply by the reciprocal), so that a crop's result does not depend
-// on which of the two paths its call took.  One thread per (crop, span).
-__global__ void __launch_bounds__(128) softmax_spans_tc(const float *__restrict__ logits, float *__restrict__ y, int n)
-{
-    constexpr float LOG2E = 1.4426950408889634f;
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= n * 24) return;
-    const int row = i / 24, sp = i - row * 24;
-    const int off = sp < 8 ? sp * 256 : 2048 + (sp - 8) * 16, len = sp < 8 ? 256 : 16;
-    const float *l = logits + (size_t)row * N_OUT + off;
-    float *o = y + (size_t)row * N_OUT + off;
-    float sum = 0.f;
-    if (len == 256) {
-        for (int j = 0; j < 256; j += 4)
-            sum += ex2_fast(l[j] * LOG2E) + ex2_fast(l[j + 1] * LOG2E) + ex2_fast(l[j + 2] * LOG2E) + ex2_fast(l[j + 3] * LOG2E);
-    } else {
-        for (int j = 0; j < 16; j++) sum += ex2_fast(l[j] * LOG2E);
-    }
-    const float inv = 1.0f / sum;
-    for (int j = 0; j < len; j++) o[j] = ex2_fast(l[j] * LOG2E) * inv;
-}
-
 void tc_set_reserved_sms(Net &net, int reserve)
 {
     TcState *t = net.tc;
@@ -945,41 +921,10 @@ static int tc_ensure(Net &net, int64_t n)
 
 // x16 != nullptr: the crops arrive as 16-bit depth and include/handtrack.h:700 runs inside the conv kernel's loader
 // dec_out != nullptr: the decode runs in the fc2 epilogue (y_out may then be null: the 9.2 KB per crop never reach HBM)
-template <int EPI, int BN, bool OPS_F16>
-static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB, const EpiArgs &ea, int M, int N, int K, cudaStream_t s);
-
-// Calls of at most this many crops stream the FC weights through 64-wide tiles (4x the CTAs of the 256-wide tiling, which
-// would leave 9 of 148 SMs pulling 9.4 MB each) and take the softmax from fp32 logits in a separate kernel.  Decided per
-// CALL (tc_call_n), never per workspace chunk.
-constexpr int64_t TC_SMALL_CALL = 512;
-
 static int tc_forward_impl(Net &net, const float *x, const uint16_t *x16, float depth_scale, float dmin, float dmax, int64_t n, float *y_out,
                            float *dec_out, cudaStream_t s)
 {
     TcState *t = net.tc;
-    const int64_t call_n = net.tc_call_n > 0 ? net.tc_call_n : n;
-    net.tc_call_n = 0;
-    if (call_n <= TC_SMALL_CALL && !dec_out && y_out) {
-        if (int rc = tc_ensure(net, n)) return rc;
-        if (int rc = ensure_workspace(net, n)) return rc;   // fp32 logits live in the shared workspace
-        {
-            StageTimer st(net, 0, s);
-            if (x16) {
-                if (int rc = tc_conv2_stage_u16(net, x16, n, depth_scale, dmin, dmax, t->p2, s)) return rc;
-            } else if (int rc = tc_conv_stage(net, x, n, t->p2, s)) return rc;
-        }
-        {
-            StageTimer st(net, 1, s);
-            if (int rc = launch_gemm<TC_EPI_TANH_ACT, 64, true>(net, t->tm_p2, t->tm_w1t64, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, (int)n, FC1_OUT,
-                                                                FC1_IN, s)) return rc;
-        }
-        StageTimer st(net, 2, s);
-        if (int rc = launch_gemm<TC_EPI_STORE_F32, 64, true>(net, t->tm_h1, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, net.ws.logits, nullptr, nullptr, 0}, (int)n,
-                                                             FC2_OUT, FC2_IN, s)) return rc;
-        softmax_spans_tc<<<(unsigned)((n * 24 + 127) / 128), 128, 0, s>>>(net.ws.logits, y_out, (int)n);
-        LAUNCH_CHECK(net);
-        return 0;
-    }
     if (dec_out && !t->dec_scratch) HP_CUDA_TRY(cudaMalloc((void **)&t->dec_scratch, (size_t)t->total_sms * BM * 256 * sizeof(float)));
     for (int64_t b = 0; b < n; b += TC_CHUNK) {
         const int64_t m = (n - b < TC_CHUNK) ? n - b : TC_CHUNK;
