@@ -893,9 +893,12 @@ int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, i
     cudaStream_t s = (cudaStream_t)stream;
     Net::StepGraph &G = N.step_graph;
     static const bool no_graph = getenv("HP_NO_GRAPH") != nullptr;
-    // graph replay: single GPU, one workspace chunk, nothing that needs host-visible events, shadows in step with the weights.
+    // graph replay: one workspace chunk, nothing that needs host-visible events, shadows in step with the weights.
     // The legacy NULL stream cannot be captured.
-    const bool eligible = !no_graph && !G.disabled && N.world == 1 && !N.profiling && !N.step_timing && n <= FP32_CHUNK && s != nullptr &&
+    // Data parallel: only the peer-memory exchange (its kernels keep their barrier epochs in device memory, so a replayed
+    // launch is a new exchange); NCCL steps stay eager.
+    const bool dp_ok = N.world == 1 || (N.peer && N.peer->ready);
+    const bool eligible = !no_graph && !G.disabled && dp_ok && !N.profiling && !N.step_timing && n <= FP32_CHUNK && s != nullptr &&
                           !(precision == HP_PRECISION_TENSOR && N.tc_dirty);
     const bool same = G.x == x_dev && G.t == t_dev && G.mse == mse_dev && G.n == n && G.alpha == alpha && G.precision == precision && G.stream == s;
     if (!eligible || !same) {

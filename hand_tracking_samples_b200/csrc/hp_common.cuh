@@ -147,7 +147,7 @@ struct Net {
     __nv_bfloat16 *grads_bf = nullptr;    // wire buffer, .cnnb order
     bool step_timing = false;
     int64_t launches = 0;
-    // One optimiser step as a CUDA graph (single GPU): the ~30 launches + ~15 event hops of a batch-256 step cost more on the
+    // One optimiser step as a CUDA graph (single GPU, or data parallel over the peer-memory exchange): the ~30 launches + ~15 event hops of a batch-256 step cost more on the
     // host than the kernels run on the device.  Keyed on the call's arguments; captured the second time a key repeats.
     struct StepGraph {
         const void *x = nullptr, *t = nullptr, *mse = nullptr;

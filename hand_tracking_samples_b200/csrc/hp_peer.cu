@@ -90,6 +90,20 @@ __device__ __forceinline__ bool peer_barrier(const PeerPtrs &P, int rank, uint32
     return __syncthreads_or(bad) == 0;
 }
 
+// This CTA's barrier epoch so far (identical for CTA b of every rank: all ranks make the same sequence of launches with the
+// same grids).  The caller advances it with peer_epoch_advance once the launch's barriers are behind it.
+__device__ __forceinline__ uint32_t peer_epoch_load(const PeerPtrs &P)
+{
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) s_epoch = P.counters[blockIdx.x];
+    __syncthreads();
+    return s_epoch;
+}
+__device__ __forceinline__ void peer_epoch_advance(const PeerPtrs &P, uint32_t epoch, uint32_t by)
+{
+    if (threadIdx.x == 0) P.counters[blockIdx.x] = epoch + by;
+}
+
 __device__ __forceinline__ float4 ld_peer(const float4 *p)
 {
     // peer gradient sums change every step and are read exactly once: bypass L1, do not allocate
@@ -104,8 +118,10 @@ __device__ __forceinline__ float4 ld_peer(const float4 *p)
 // the exchange ends -- measured on 8xB200 with 48 x 512-thread CTAs: the fc2 dX GEMM took 52 us instead of 17 and the
 // step 362 us instead of ~280.
 template <int WORLD, int U>
-__global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_kernel(PeerPtrs P, int rank, int off, int count4, float alpha, uint32_t epoch)
+__global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_kernel(PeerPtrs P, int rank, int off, int count4, float alpha)
 {
+    const uint32_t epoch = peer_epoch_load(P);
+    peer_epoch_advance(P, epoch, 2);
     if (!peer_barrier<WORLD>(P, rank, epoch + 1)) return;   // incomplete sums: leave the weights alone
     const int lo = (int)((int64_t)count4 * rank / WORLD), hi = (int)((int64_t)count4 * (rank + 1) / WORLD);
     const int stride = gridDim.x * PEER_THREADS;
@@ -163,8 +179,10 @@ __device__ __forceinline__ void pt_wait(uint64_t *bar, uint32_t parity, uint32_t
 //   full[s]      TMA -> consumers   (complete_tx)          empty[s]     consumer warps -> TMA thread (count 31)
 //   out_full[b]  consumer warps -> TMA thread (count 31)    out_free[b]  TMA thread -> consumers (the bulk stores have read it)
 template <int WORLD, int CHUNK_F4, int STAGES>
-__global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_tma_kernel(PeerPtrs P, int rank, int off, int count4, float alpha, uint32_t epoch)
+__global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_tma_kernel(PeerPtrs P, int rank, int off, int count4, float alpha)
 {
+    const uint32_t epoch = peer_epoch_load(P);
+    peer_epoch_advance(P, epoch, 2);
     constexpr int CHUNK_B = CHUNK_F4 * 16;
     constexpr int SLOTS = WORLD + 1;
     extern __shared__ uint8_t pt_raw[];
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(PEER_THREADS, 1) peer_sgd_tma_kernel(PeerPtrs 
 }
 
 template <int WORLD, int CHUNK_F4, int STAGES>
-static int launch_peer_tma(PeerState *ps, int blocks, int off, int count4, float alpha, uint32_t epoch, cudaStream_t s)
+static int launch_peer_tma(PeerState *ps, int blocks, int off, int count4, float alpha, cudaStream_t s)
 {
     constexpr int SMEM = (STAGES * (WORLD + 1) + 2) * CHUNK_F4 * 16 + 128;
     static_assert(SMEM <= 227 * 1024, "peer exchange tile too large");
@@ -270,7 +288,7 @@ static int launch_peer_tma(PeerState *ps, int blocks, int off, int count4, float
         HP_CUDA_TRY(cudaFuncSetAttribute(peer_sgd_tma_kernel<WORLD, CHUNK_F4, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr = true;
     }
-    peer_sgd_tma_kernel<WORLD, CHUNK_F4, STAGES><<<blocks, PEER_THREADS, SMEM, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch);
+    peer_sgd_tma_kernel<WORLD, CHUNK_F4, STAGES><<<blocks, PEER_THREADS, SMEM, s>>>(ps->ptrs, ps->rank, off, count4, alpha);
     return 0;
 }
 
@@ -281,8 +299,13 @@ static int launch_peer_tma(PeerState *ps, int blocks, int off, int count4, float
 // can only overwrite the buffer read here after it has passed the NEXT step's barrier, which this rank joins after this
 // kernel has finished (stream order), so no closing barrier is needed.
 template <int WORLD>
-__global__ void __launch_bounds__(PEER_THREADS, 1) peer_small_kernel(PeerPtrs P, int rank, int off, int count4, float alpha, uint32_t epoch, int parity)
+__global__ void __launch_bounds__(PEER_THREADS, 1) peer_small_kernel(PeerPtrs P, int rank, int off, int count4, float alpha)
 {
+    const uint32_t epoch = peer_epoch_load(P);
+    const int parity = (int)(P.counters[PEER_MAX_BLOCKS + blockIdx.x] & 1u);   // launches of this kernel so far: inbox double buffer
+    __syncthreads();
+    if (threadIdx.x == 0) P.counters[PEER_MAX_BLOCKS + blockIdx.x] += 1u;
+    peer_epoch_advance(P, epoch, 1);
     const int per = (count4 + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = (lo + per < count4) ? lo + per : count4;
     const size_t slot = (size_t)PEER_SMALL_FLOATS / 4;   // float4 per (parity, rank) slot
@@ -312,14 +335,11 @@ int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
     PeerState *ps = net.peer;
     if (!ps) { set_error("peer path not initialised"); return 2; }
     const int count4 = count / 4;
-    const uint32_t epoch = ps->epoch;
     if (count <= PEER_SMALL_FLOATS) {
         int blocks = (count4 + PEER_THREADS - 1) / PEER_THREADS;
         if (blocks > ps->max_blocks) blocks = ps->max_blocks;
-        const int parity = (int)(ps->small_steps++ & 1);
-        ps->epoch += 1;
         switch (ps->world) {
-#define HP_CASE(W) case W: peer_small_kernel<W><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch, parity); break;
+#define HP_CASE(W) case W: peer_small_kernel<W><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha); break;
         HP_CASE(2) HP_CASE(3) HP_CASE(4) HP_CASE(5) HP_CASE(6) HP_CASE(7) HP_CASE(8)
 #undef HP_CASE
         default: set_error("peer path supports 2..8 ranks, got %d", ps->world); return 2;
@@ -332,7 +352,6 @@ int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
     int blocks = (count4 / ps->world + PEER_THREADS - 1) / PEER_THREADS;
     if (blocks > ps->max_blocks) blocks = ps->max_blocks;
     if (blocks < 1) blocks = 1;
-    ps->epoch += 2;
     // HP_PEER_TMA=1 selects the TMA variant.  Measured at 2 GPUs (profiles/r2_dp_exchange.md) the two are equal (278-288 us
     // per step) and flat in the number of exchange CTAs beyond 16: the step is then bounded by the structure around the
     // exchange (exposed conv bucket + shadow refresh, SM reservation), not by the bytes in flight; the LDG kernel, which
@@ -341,13 +360,13 @@ int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
     if (use_tma) {
         int rc = 2;
         switch (ps->world) {   // stage = (G + 1) chunks; STAGES x stage + 2 out buffers <= ~190 KB
-        case 2: rc = launch_peer_tma<2, 1024, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 3: rc = launch_peer_tma<3, 1024, 2>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 4: rc = launch_peer_tma<4, 512, 4>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 5: rc = launch_peer_tma<5, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 6: rc = launch_peer_tma<6, 512, 3>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 7: rc = launch_peer_tma<7, 512, 2>(ps, blocks, off, count4, alpha, epoch, s); break;
-        case 8: rc = launch_peer_tma<8, 512, 2>(ps, blocks, off, count4, alpha, epoch, s); break;
+        case 2: rc = launch_peer_tma<2, 1024, 3>(ps, blocks, off, count4, alpha, s); break;
+        case 3: rc = launch_peer_tma<3, 1024, 2>(ps, blocks, off, count4, alpha, s); break;
+        case 4: rc = launch_peer_tma<4, 512, 4>(ps, blocks, off, count4, alpha, s); break;
+        case 5: rc = launch_peer_tma<5, 512, 3>(ps, blocks, off, count4, alpha, s); break;
+        case 6: rc = launch_peer_tma<6, 512, 3>(ps, blocks, off, count4, alpha, s); break;
+        case 7: rc = launch_peer_tma<7, 512, 2>(ps, blocks, off, count4, alpha, s); break;
+        case 8: rc = launch_peer_tma<8, 512, 2>(ps, blocks, off, count4, alpha, s); break;
         default: set_error("peer path supports 2..8 ranks, got %d", ps->world); return 2;
         }
         if (rc) return rc;
@@ -356,7 +375,7 @@ int peer_sgd_bucket(Net &net, float alpha, int off, int count, cudaStream_t s)
         return 0;
     }
     switch (ps->world) {
-#define HP_CASE(W, U) case W: peer_sgd_kernel<W, U><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha, epoch); break;
+#define HP_CASE(W, U) case W: peer_sgd_kernel<W, U><<<blocks, PEER_THREADS, 0, s>>>(ps->ptrs, ps->rank, off, count4, alpha); break;
     HP_CASE(2, 4) HP_CASE(3, 2) HP_CASE(4, 2) HP_CASE(5, 1) HP_CASE(6, 1) HP_CASE(7, 1) HP_CASE(8, 1)
 #undef HP_CASE
     default: set_error("peer path supports 2..8 ranks, got %d", ps->world); return 2;
@@ -417,6 +436,7 @@ int peer_init(Net &net, const void *handles, int rank, int world, int reserved_s
         ps->ptrs.inbox[p] = (float *)m[3];
     }
     ps->ptrs.error = ps->my_flags + PEER_MAX_BLOCKS * PEER_MAX_WORLD;
+    ps->ptrs.counters = ps->my_flags + PEER_MAX_BLOCKS * PEER_MAX_WORLD + 32;   // zeroed with the flags at export
     {
         uint32_t *dptr = nullptr;
         HP_CUDA_TRY(cudaHostGetDevicePointer((void **)&dptr, ps->host_err, 0));
@@ -432,8 +452,6 @@ int peer_init(Net &net, const void *handles, int rank, int world, int reserved_s
         int b = atoi(e);
         if (b >= 1 && b <= PEER_MAX_BLOCKS) ps->max_blocks = b;
     }
-    ps->epoch = 0;
-    ps->small_steps = 0;
     ps->ready = true;
     return 0;
 }

@@ -11,13 +11,16 @@ constexpr int PEER_MAX_BLOCKS = 128;
 constexpr int PEER_THREADS = 1024;
 constexpr int PEER_SMALL_FLOATS = 16896;                                // buckets up to this size (the conv bucket: 16,864) go through the inbox
 constexpr int PEER_INBOX_FLOATS = 2 * PEER_MAX_WORLD * PEER_SMALL_FLOATS;   // [parity][source rank][PEER_SMALL_FLOATS]
-constexpr int PEER_FLAG_WORDS = PEER_MAX_BLOCKS * PEER_MAX_WORLD + 32;   // barrier flags + error word
+constexpr int PEER_FLAG_WORDS = PEER_MAX_BLOCKS * PEER_MAX_WORLD + 32 + 2 * PEER_MAX_BLOCKS;   // barrier flags + error word + per-CTA counters
 
 struct PeerPtrs {                        // passed to the kernel by value
     float *params[PEER_MAX_WORLD];       // every rank's FP32 master weights (.cnnb order); [rank] is local
     float *grads[PEER_MAX_WORLD];        // every rank's gradient sums
     uint32_t *flags[PEER_MAX_WORLD];     // every rank's flag array [PEER_MAX_BLOCKS][PEER_MAX_WORLD]
     float *inbox[PEER_MAX_WORLD];        // every rank's small-bucket inbox
+    uint32_t *counters;                  // local, per CTA: [b] barrier epoch reached so far, [PEER_MAX_BLOCKS + b] small-bucket launches so far.
+                                         // Kept on the device (not passed as launch arguments) so that a captured CUDA graph of the
+                                         // training step replays correctly: every launch advances its own CTAs' counters.
     uint32_t *error;                     // local error word (barrier timeout): sticky, every later exchange kernel of this rank is a no-op
     volatile uint32_t *error_host;       // the same word in mapped pinned host memory, so that the host sees it without a device sync
     unsigned long long timeout_ns;       // barrier spin limit (HP_PEER_TIMEOUT_S, default 30 s)
@@ -33,8 +36,7 @@ struct PeerState {
     int n_mapped = 0;
     int rank = 0, world = 1;
     int max_blocks = PEER_MAX_BLOCKS;
-    uint32_t small_steps = 0;            // launches of the small-bucket kernel so far (inbox parity)
-    uint32_t epoch = 0;                  // identical on all ranks: every rank makes the same sequence of launches
+
     bool ready = false;
 };
 
