@@ -49,6 +49,17 @@ namespace hp {
 
 #define WAIT(bar, parity) ptx::mbar_wait_hint(bar, parity, 4000u)
 
+// HP_CONV_TRACE=1 at build time: clock64 stamps of CTA 0's warp roles for its first 24 crops (tools/dbg/conv2_trace.py)
+#ifdef HP_CONV_TRACE
+__device__ long long g_conv2_trace[8 * 24 * 16];
+#define TRACE2(role, it, ev)                                                                                                  \
+    do {                                                                                                                      \
+        if (blockIdx.x == 0 && lane == 0 && (it) < 24) g_conv2_trace[((role) * 24 + (it)) * 16 + (ev)] = clock64();          \
+    } while (0)
+#else
+#define TRACE2(role, it, ev) do {} while (0)
+#endif
+
 namespace cv2 {
 constexpr int THREADS = 768;
 constexpr int IMG_COPY = 9216;                 // one fp16 image copy (8 KB) + slack for the pad rows' reads
@@ -185,8 +196,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         const uint64_t bd0 = ptx::make_desc_sw128(sB1);
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1;
+            TRACE2(0, it, 0);
             WAIT(&img_full[ib], (it >> 1) & 1);
             ptx::tc_fence_after();
+            TRACE2(0, it, 1);
             const uint64_t ad0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_IMG + ib * IMG_BUF), 128, 512);
 #pragma unroll
             for (int g = 0; g < 4; g++) {
@@ -194,6 +207,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                 const uint32_t u = (uint32_t)(it * 2 + e);  // use count of accumulator `half`
                 WAIT(&acc1_empty[half], (u & 1) ^ 1);
                 ptx::tc_fence_after();
+                TRACE2(0, it, 2 + 2 * g);
                 if (ptx::elect_one()) {
                     const uint32_t d = tmem_base + ACC1 + half * 128;
                     const uint64_t ad = ad0 + ((e * IMG_COPY) >> 4), bd = bd0 + ((half * 16384) >> 4);
@@ -211,6 +225,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                     if (g == 3) ptx::umma_commit(&img_empty[ib]);
                 }
                 __syncwarp();
+                TRACE2(0, it, 3 + 2 * g);
             }
         }
     } else if (warp == 2) {
@@ -220,7 +235,9 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         ptx::tc_fence_after();
         for (int it = 0; it < my_crops; it++) {
             const int pb = it & 1;
+            TRACE2(1, it, 0);
             WAIT(&p1_full[pb], (it >> 1) & 1);
+            TRACE2(1, it, 1);
             // The accumulator is split in two halves (output rows 0-5 and 6-11), each with its own full/empty handshake:
             // the epilogue drains one half while the MMAs of the other run.  (A single 192-column accumulator made
             // "8 MMAs -> drain -> next 8 MMAs" a serial loop of ~2.4 k cycles per crop, the pace of the whole kernel.)
@@ -228,6 +245,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             for (int h = 0; h < 2; h++) {
                 WAIT(&acc2_empty[h], (it & 1) ^ 1);
                 ptx::tc_fence_after();
+                TRACE2(1, it, 2 + 2 * h);
                 if (ptx::elect_one()) {
                     const uint64_t bd0 = ptx::make_desc_nosw(ptx::smem_u32(smem + OFF_P1 + pb * P1_BUF), P1_PLANE, 128) + h * N2;
                     const uint32_t d = tmem_base + ACC2 + h * N2, a0 = tmem_base + W2;
@@ -241,6 +259,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                     if (h == 1) ptx::umma_commit(&p1_empty[pb]);
                 }
                 __syncwarp();
+                TRACE2(1, it, 3 + 2 * h);
             }
         }
     } else {
@@ -295,8 +314,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                 // chunks k = 0..7 (half = k / 4, c = k % 4): load k+1 is issued before chunk k is reduced, and a slot is handed
                 // back to the MMA issuer as soon as its last load has landed (before that chunk's arithmetic)
                 uint32_t ra[32], rb[32];
+                if (ew == 0) TRACE2(2 + my_e, it, 0);
                 WAIT(&acc1_full[my_e * 2 + 0], it & 1);
                 ptx::tc_fence_after();
+                if (ew == 0) TRACE2(2 + my_e, it, 1);
                 ptx::tmem_ld32(ta0, ra);
                 ptx::tmem_ld_wait();
 #pragma unroll
@@ -306,8 +327,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&acc1_empty[0]);
+                        if (ew == 0) TRACE2(2 + my_e, it, 2);
                         WAIT(&acc1_full[my_e * 2 + 1], it & 1);
                         ptx::tc_fence_after();
+                        if (ew == 0) TRACE2(2 + my_e, it, 3);
                     }
                     if (k + 1 < 8) {
                         const uint32_t ta = ta0 + ((k + 1) >> 2) * 128 + ((k + 1) & 3) * 32;
@@ -321,6 +344,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc1_empty[1]);
+                if (ew == 0) TRACE2(2 + my_e, it, 4);
             } else {
 #pragma unroll 1
                 for (int half = 0; half < 2; half++) {
@@ -341,6 +365,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             // only the STORES need the p1 buffer to be free (conv2 of two crops ago done): waiting here, not before the
             // drain, keeps the conv1 accumulator slots turning over while conv2 is behind
             WAIT(&p1_empty[pb], ((it >> 1) & 1) ^ 1);
+            if (ew == 0) TRACE2(2 + my_e, it, 5);
             if (py < 15 && px < 15) {
                 uint32_t pk[8];
 #pragma unroll
@@ -366,6 +391,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             ptx::fence_proxy_async();   // generic-proxy stores -> visible to the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p1_full[pb]);
+            if (ew == 0) TRACE2(2 + my_e, it, 6);
         }
     } else if (warp < 20) {
         // ===================== conv2 weights -> TMEM (once), then epilogue 2 =====================
@@ -402,8 +428,10 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             //   odd:  own = W[8 + i], sends W[2 + i] (its half of the even lane's pixels)
             {
                 const int h = my_h;
+                if (ew == 0) TRACE2(4 + my_h, it, 0);
                 WAIT(&acc2_full[h], it & 1);
                 ptx::tc_fence_after();
+                if (ew == 0) TRACE2(4 + my_h, it, 1);
                 float best[3][3];
                 int arg[3][3];
                 auto reduce_row = [&](const uint32_t (&W)[16], int r) {
@@ -428,6 +456,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&acc2_empty[h]);
+                    if (ew == 0) TRACE2(4 + my_h, it, 2);
                 };
                 const uint32_t t2 = lane_base + ACC2 + h * N2;
                 if (PIPE) {
@@ -465,6 +494,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                         if (TRAIN) idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg[s][pxl];
                     }
                 }
+                if (ew == 0) TRACE2(4 + my_h, it, 3);
             }
         }
     } else {
@@ -474,7 +504,9 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
         for (int it = 0; it < my_crops; it++) {
             const int ib = it & 1, sg = it % NSTAGE;
             const uint8_t *st = smem + OFF_STAGE + sg * STAGE_BYTES;
+            if (t < 32) TRACE2(6, it, 0);
             WAIT(&stage_full[sg], (it / NSTAGE) & 1);
+            if (t < 32) TRACE2(6, it, 1);
             uint2 pk[8];   // pixels 4f .. 4f+3 of group f = t + 128 k, packed fp16x2
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -493,6 +525,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&stage_empty[sg]);
             WAIT(&img_empty[ib], ((it >> 1) & 1) ^ 1);
+            if (t < 32) TRACE2(6, it, 2);
             uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -502,6 +535,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             }
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&img_full[ib]);
+            if (t < 32) TRACE2(6, it, 3);
         }
     }
     ptx::tc_fence_before();
@@ -523,6 +557,13 @@ __global__ void __launch_bounds__(256) build_conv2_tmem_image(const float *__res
     const int ky = j >> 1, kx = (j & 1) + 2 * g;
     a2[i] = __float2half_rn(params[OFF_C2W + co * C2_KDIM + ci * 16 + ky * 4 + kx]);
 }
+
+#ifdef HP_CONV_TRACE
+extern "C" __attribute__((visibility("default"))) int hp_debug_conv2_trace(long long *out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_conv2_trace, sizeof(long long) * n);
+}
+#endif
 
 int tc_conv2_init(Net &net)
 {
