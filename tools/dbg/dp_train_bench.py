@@ -10,6 +10,7 @@ dp.init_data_parallel(net, mode=os.environ.get('HP_DP_MODE', 'peer'))
 if os.environ.get('HP_BF16_WIRE'): net.dp_set_bf16_gradients(True)
 TB = 256
 tx = torch.rand((TB, 4096), device="cuda"); tt = torch.from_numpy(synth.heatmap_labels(TB, 1)).cuda(); mse = torch.empty(TB, device="cuda")
+torch.cuda.set_stream(torch.cuda.Stream(device=local))   # the legacy NULL stream cannot be captured into the step graph
 st = torch.cuda.current_stream().cuda_stream
 for prec, name in ((hp.PRECISION_TENSOR, "tensor"),):
     for _ in range(10):

@@ -3,7 +3,7 @@
 fraction of every point.
 
   python tools/sweep.py > profiles/r2_sweep_1gpu.json
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/sweep.py > profiles/r2_sweep_Ngpu.json
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/sweep.py --out profiles/r2_sweep_Ngpu.json
 
 Per point: time of one Eval pass over the global batch = max over ranks of the CUDA-event time between barriers
 (mean of `reps` back-to-back passes after 3 warm-up passes; the input slice of a rank is reused across passes, so points
@@ -78,8 +78,9 @@ def main():
                          "frac_of_fp32_ffma_nominal": tf / (world * 74.0) if name == "fp32" else None,
                          "weight_stream_floor_us": 18.9e6 / (pk["hbm_gbs"] * 1e9) * 1e6 if name == "tensor" else 37.8e6 / (pk["hbm_gbs"] * 1e9) * 1e6})
     if rank == 0:
+        out = open(sys.argv[sys.argv.index("--out") + 1], "w") if "--out" in sys.argv else sys.stdout   # NCCL prints its version on stdout
         print(json.dumps({"gpu": torch.cuda.get_device_name(0), "n_gpus": world, "burst_bf16_tflops_per_gpu": pk["bf16_tflops"], "hbm_gbs": pk["hbm_gbs"],
-                          "note": "global batch sharded evenly, no collective; time = max over ranks", "rows": rows}, indent=1))
+                          "note": "global batch sharded evenly, no collective; time = max over ranks", "rows": rows}, indent=1), file=out)
     if world > 1:
         dist.destroy_process_group()
 
