@@ -422,7 +422,7 @@ def train_arm(args, net, hp, dp, dist, dev, rank, world, local, stream, gen, tim
     tx = torch.rand((TB, 4096), device=dev, generator=gen)
     tt = torch.from_numpy(synth.heatmap_labels(TB, 4321 + rank)).to(dev)
     mse = torch.empty(TB, device=dev)
-    kt = max(min(K, 200), 20)
+    kt = 100   # optimiser steps per timed run (a 256-sample step is ~0.2 ms: shorter runs time the ranks' start skew)
 
     def step_fn(n_, xs, ts, ms_, nb, prec, scale):
         return lambda: n_.train_batch_device(xs.data_ptr(), ts.data_ptr(), nb, 0.001 / scale, ms_.data_ptr(), precision=prec, stream=stream)
@@ -513,7 +513,7 @@ def train_arm(args, net, hp, dp, dist, dev, rank, world, local, stream, gen, tim
     except Exception as e:
         sc["nccl_b%d" % TB] = {"error": str(e)[:120]}
     # correctness of the exchange, visible to the driver: every rank ends bit-identical, and the step equals the single-GPU
-    # step on the concatenated batch (FP32 path <= 2e-5, tensor path <= 1e-2 of the update)
+    # step on the concatenated batch (FP32 path <= 5e-5, tensor path <= 1e-2 of the update)
     try:
         sc["dp_check"] = dp_check(hp, dp, dist, dev, local, rank, world, stream, mode)
     except Exception as e:
@@ -531,13 +531,13 @@ def dp_check(hp, dp, dist, dev, local, rank, world, stream, mode, n_per=32):
     ts = [synth.heatmap_labels(n_per, 800 + r) for r in range(world)]
     xd, td = torch.from_numpy(xs[rank]).to(dev), torch.from_numpy(ts[rank]).to(dev)
     xall, tall = np.concatenate(xs), np.concatenate(ts)
-    res = {"samples_per_rank": n_per, "steps": 2}
+    res = {"samples_per_rank": n_per, "steps": 4, "note": "steps 3 and 4 replay the captured step graph"}
     ok_all = True
-    for name, prec, tol in (("fp32", hp.PRECISION_FP32, 2e-5), ("tensor", hp.PRECISION_TENSOR, 1e-2)):
+    for name, prec, tol in (("fp32", hp.PRECISION_FP32, 5e-5), ("tensor", hp.PRECISION_TENSOR, 1e-2)):
         net_d = hp.PoseInitializerCNN("", device=local)
         p0 = net_d.get_params()
         dp.init_data_parallel(net_d, mode=mode)
-        for _ in range(2):
+        for _ in range(4):
             net_d.train_batch_device(xd.data_ptr(), td.data_ptr(), n_per, 0.001, None, precision=prec, stream=stream)
         torch.cuda.synchronize()
         p_dp = net_d.get_params()
@@ -547,7 +547,7 @@ def dp_check(hp, dp, dist, dev, local, rank, world, stream, mode, n_per=32):
         same = torch.tensor([1.0 if torch.equal(mine, ref0) else 0.0], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         ref = hp.PoseInitializerCNN("", device=local)
-        for _ in range(2):
+        for _ in range(4):
             ref.train_batch(xall, tall, 0.001, precision=prec)
         p1 = ref.get_params()
         rel = float(np.abs((p_dp - p0) - (p1 - p0)).max() / np.abs(p1 - p0).max())

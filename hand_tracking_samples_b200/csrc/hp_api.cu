@@ -985,6 +985,16 @@ int hp_device_ptrs(hp_net *net, float **params_dev, float **grads_dev)
     return HP_OK;
 }
 
+// a captured training step bakes in the exchange mode, the grid sizes and the wire format: any change to those drops it
+static void drop_step_graph(Net &N)
+{
+    Net::StepGraph &G = N.step_graph;
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    G.seen = 0;
+    G.x = nullptr;
+    G.disabled = false;
+}
+
 int hp_dp_unique_id(void *id128)
 {
     if (!id128) { set_error("id128 is NULL"); return HP_ERR_INVALID; }
@@ -1002,6 +1012,7 @@ int hp_dp_init(hp_net *net, const void *id128, int rank, int world)
     Id128 id;
     memcpy(id.b, id128, 128);
     HP_NCCL_TRY(g_nccl.CommInitRank(&N.nccl_comm, world, id, rank));
+    drop_step_graph(N);
     N.rank = rank;
     N.world = world;
     // The persistent tensor-core kernels take one CTA with ~200 KB of shared memory on every SM, which leaves NCCL's
@@ -1022,6 +1033,7 @@ int hp_dp_set_bf16_gradients(hp_net *net, int enable)
     HP_CUDA_TRY(cudaSetDevice(N.device));
     if (enable && !N.grads_bf) HP_CUDA_TRY(cudaMalloc((void **)&N.grads_bf, (size_t)N_PARAMS * sizeof(__nv_bfloat16)));
     N.dp_bf16 = enable != 0;
+    drop_step_graph(N);
     return HP_OK;
 }
 
@@ -1043,6 +1055,7 @@ int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world)
     int reserve = 16;
     if (const char *e = getenv("HP_DP_RESERVE_SMS")) reserve = atoi(e);
     if (int rc = peer_init(N, all_handles, rank, world, reserve)) return rc;
+    drop_step_graph(N);
     N.rank = rank;
     N.world = world;
     if (N.tc) tc_set_reserved_sms(N, reserve);
@@ -1066,7 +1079,10 @@ HP_API int hp_debug_peer_exchange(hp_net *net, int bucket, float alpha, int max_
     HP_CUDA_TRY(cudaSetDevice(N.device));
     const int off[3] = {OFF_F2W, OFF_F1W, 0};
     const int end[3] = {N_PARAMS, OFF_F2W, OFF_F1W};
-    if (max_blocks > 0) N.peer->max_blocks = max_blocks < PEER_MAX_BLOCKS ? max_blocks : PEER_MAX_BLOCKS;
+    if (max_blocks > 0) {
+        N.peer->max_blocks = max_blocks < PEER_MAX_BLOCKS ? max_blocks : PEER_MAX_BLOCKS;
+        drop_step_graph(N);
+    }
     return peer_sgd_bucket(N, alpha, off[bucket], end[bucket] - off[bucket], (cudaStream_t)stream);
 }
 
@@ -1074,8 +1090,9 @@ int hp_dp_shutdown(hp_net *net)
 {
     if (!net) return HP_OK;
     Net &N = net->n;
+    cudaSetDevice(N.device);
+    drop_step_graph(N);
     if (N.peer) {
-        cudaSetDevice(N.device);
         peer_shutdown(N);
     }
     if (N.nccl_comm) {

@@ -47,6 +47,30 @@ for mode in ("peer", "nccl"):
         assert g.item() <= tol and identical
     if mode == "peer":
         assert net.dp_peer_status() == 0
+        # the same steps on a capturable stream: the second identical call captures the whole step (exchange kernels
+        # included -- their barrier epochs live in device memory) and later calls replay the graph
+        side = torch.cuda.Stream()
+        for prec, tol in ((hp.PRECISION_FP32, 5e-5), (hp.PRECISION_TENSOR, 2e-2)):
+            res = []
+            for stream in (st, side.cuda_stream):
+                net.Init()
+                torch.cuda.synchronize()
+                for _ in range(5):
+                    net.train_batch_device(xd.data_ptr(), td.data_ptr(), hi - lo, 0.001, None, precision=prec, stream=stream)
+                torch.cuda.synchronize()
+                res.append(net.get_params())
+            ref = hp.PoseInitializerCNN("", device=local)
+            for _ in range(5):
+                ref.train_batch(x, t, 0.001, precision=prec)
+            p_1 = ref.get_params()
+            rel = np.abs((res[1] - p0) - (p_1 - p0)).max() / np.abs(p_1 - p0).max()
+            g = torch.tensor([rel], device="cuda"); dist.all_reduce(g, op=dist.ReduceOp.MAX)
+            identical = ranks_identical(res[1])
+            if rank == 0:
+                print("peer, graph replay, precision %d, 5 steps: rel err vs 1 GPU %.3e (tol %g), ranks identical %s, equal to the eager DP steps: %s"
+                      % (prec, g.item(), tol, identical, np.array_equal(res[0], res[1])), flush=True)
+            assert g.item() <= tol and identical and np.array_equal(res[0], res[1])
+        assert net.dp_peer_status() == 0
     else:
         # opt-in bf16 gradient transport (NCCL path, tensor-precision steps only): same step within the tensor-path bound
         net.Init()
