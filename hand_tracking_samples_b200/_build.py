@@ -51,6 +51,20 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_trace():
+    """Debug build for tools/dbg/conv2_trace.py: the same objects with hp_tc_conv2.cu recompiled under -DHP_CONV_TRACE, linked
+    to tools/dbg/_bin/libhandposedd_trace.so (selected with HP_LIB_OVERRIDE).  Never the product library."""
+    build()
+    out_dir = os.path.join(os.path.dirname(HERE), "tools", "dbg", "_bin")
+    os.makedirs(out_dir, exist_ok=True)
+    obj = os.path.join(out_dir, "hp_tc_conv2_trace.o")
+    subprocess.check_call([nvcc()] + NVCC_FLAGS + ["-DHP_CONV_TRACE", "-c", os.path.join(CSRC, "hp_tc_conv2.cu"), "-o", obj])
+    objs = [obj if s == "hp_tc_conv2.cu" else os.path.join(CSRC, s.replace(".cu", ".o")) for s in SOURCES]
+    lib = os.path.join(out_dir, "libhandposedd_trace.so")
+    subprocess.check_call([nvcc()] + ARCH_FLAGS + ["-shared", "-o", lib] + objs + ["-cudart", "static", "-ldl", "-lpthread"])
+    return lib
+
+
 ROOT = os.path.dirname(HERE)
 DROPIN_BIN = os.path.join(ROOT, "tests", "_bin", "dropin_main")
 

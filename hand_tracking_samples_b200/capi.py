@@ -57,7 +57,9 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path) or _build._stale():
+    if os.environ.get("HP_LIB_OVERRIDE"):   # debug builds (tools/dbg): load exactly this file
+        path = os.environ["HP_LIB_OVERRIDE"]
+    elif not os.path.exists(path) or _build._stale():
         if os.path.exists(_build.nvcc()):
             _build.build()
     if not os.path.exists(path):

@@ -56,6 +56,14 @@ __device__ __forceinline__ float tanh_conv(float t, bool accurate)
     return (t > 44.3614f) ? __int_as_float(0x7fc00000) : y;
 }
 
+// tanh.approx alone: for callers that have already ruled the overflow quirk out for a whole group of values
+__device__ __forceinline__ float tanh_fast(float t)
+{
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(t));
+    return y;
+}
+
 struct TcState {
     // 16-bit shadows of the weights (fp16 for the forward operands, bf16 for the backward ones), in the layouts the MMAs consume (rebuilt by tc_refresh_weights)
     act_t *w1t = nullptr;          // [2048][2304] = fc1.W^T, k contiguous, k in HWC flatten order (pp*64+co)

@@ -48,6 +48,12 @@ namespace hp {
     } while (0)
 
 #define WAIT(bar, parity) ptx::mbar_wait_hint(bar, parity, 4000u)
+// for the roles with a crop period of slack (crop producer, converter): back off between polls, so that their retry
+// loops (a third of this role's issued instructions before) stop taking issue slots from the epilogue warps
+#define WAIT_SLACK(bar, parity)                              \
+    do {                                                     \
+        while (!ptx::mbar_try_wait(bar, parity)) __nanosleep(200); \
+    } while (0)
 
 // HP_CONV_TRACE=1 at build time: clock64 stamps of CTA 0's warp roles for its first 24 crops (tools/dbg/conv2_trace.py)
 #ifdef HP_CONV_TRACE
@@ -271,7 +277,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             const uint8_t *src = reinterpret_cast<const uint8_t *>(x_in);
             for (int it = 0; it < my_crops; it++) {
                 const int sg = it % NSTAGE;
-                WAIT(&stage_empty[sg], ((it / NSTAGE) & 1) ^ 1);
+                WAIT_SLACK(&stage_empty[sg], ((it / NSTAGE) & 1) ^ 1);
                 const int64_t crop = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 ptx::mbar_expect_tx(&stage_full[sg], BYTES);
                 ptx::bulk_load_1d(smem + OFF_STAGE + sg * STAGE_BYTES, src + crop * BYTES, BYTES, &stage_full[sg]);
@@ -368,9 +374,21 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             if (ew == 0) TRACE2(2 + my_e, it, 5);
             if (py < 15 && px < 15) {
                 uint32_t pk[8];
+                float tv[16];
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    pk[j] = pack_act(tanh_conv(mx[2 * j] + bias1[2 * j], acc_tanh), tanh_conv(mx[2 * j + 1] + bias1[2 * j + 1], acc_tanh));
+                for (int j = 0; j < 16; j++) tv[j] = mx[j] + bias1[j];
+                // the reference's overflow-to-NaN quirk (cnn.h:31, t > 44.3614) is tested once per pixel, not per value
+                float top = ptx::max3(tv[0], tv[1], tv[2]);
+#pragma unroll
+                for (int j = 3; j < 15; j += 2) top = ptx::max3(top, tv[j], tv[j + 1]);
+                top = fmaxf(top, tv[15]);
+                if (acc_tanh || top > 44.3614f) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) pk[j] = pack_act(tanh_conv(tv[2 * j], acc_tanh), tanh_conv(tv[2 * j + 1], acc_tanh));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) pk[j] = pack_act(tanh_fast(tv[2 * j]), tanh_fast(tv[2 * j + 1]));
+                }
                 const int q = py * P1_PITCH + px;
                 *reinterpret_cast<uint4 *>(planes + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4 *>(planes + P1_PLANE + q * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -485,12 +503,18 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
                     }
                 }
                 // + bias, tanh (max and the monotone tanh commute in the forward pass), features in HWC order (pp * 64 + co)
+                float top2 = best[0][0];
+#pragma unroll
+                for (int s = 0; s < 3; s++) top2 = ptx::max3(top2, best[s][1], best[s][2]);
+                top2 = ptx::max3(top2, best[1][0], best[2][0]);
+                const bool slow_tanh = acc_tanh || top2 + b2 > 44.3614f;   // overflow-to-NaN quirk: once per thread
 #pragma unroll
                 for (int s = 0; s < 3; s++) {
 #pragma unroll
                     for (int pxl = 0; pxl < 3; pxl++) {
                         const int pp = (3 * h + s) * 6 + 3 * g + pxl;
-                        p2_out[crop * P2_N + pp * 64 + co] = __float2half_rn(tanh_conv(best[s][pxl] + b2, acc_tanh));
+                        const float tq = best[s][pxl] + b2;
+                        p2_out[crop * P2_N + pp * 64 + co] = __float2half_rn(slow_tanh ? tanh_conv(tq, acc_tanh) : tanh_fast(tq));
                         if (TRAIN) idx2_out[crop * P2_N + co * 36 + pp] = (uint8_t)arg[s][pxl];
                     }
                 }
@@ -505,7 +529,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             const int ib = it & 1, sg = it % NSTAGE;
             const uint8_t *st = smem + OFF_STAGE + sg * STAGE_BYTES;
             if (t < 32) TRACE2(6, it, 0);
-            WAIT(&stage_full[sg], (it / NSTAGE) & 1);
+            WAIT_SLACK(&stage_full[sg], (it / NSTAGE) & 1);
             if (t < 32) TRACE2(6, it, 1);
             uint2 pk[8];   // pixels 4f .. 4f+3 of group f = t + 128 k, packed fp16x2
 #pragma unroll
@@ -524,7 +548,7 @@ tc_conv2_kernel(const void *__restrict__ x_in, DepthNormArgs nm, const uint8_t *
             // every staged value of this warp is in registers (the conversions consumed the loads): free the stage
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&stage_empty[sg]);
-            WAIT(&img_empty[ib], ((it >> 1) & 1) ^ 1);
+            WAIT_SLACK(&img_empty[ib], ((it >> 1) & 1) ^ 1);
             if (t < 32) TRACE2(6, it, 2);
             uint8_t *img = smem + OFF_IMG + ib * IMG_BUF;
 #pragma unroll
