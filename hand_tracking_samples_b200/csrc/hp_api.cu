@@ -388,6 +388,11 @@ static int create_resources(Net &n)
         HP_CUDA_TRY(cudaStreamCreateWithPriority(&n.comm_stream, cudaStreamNonBlocking, hi));
     }
     HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.d2h_stream, cudaStreamNonBlocking));
+    HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.aux_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 3; b++) {
+        HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_fork[b], cudaEventDisableTiming));
+        HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_join[b], cudaEventDisableTiming));
+    }
     for (int b = 0; b < 2; b++) {
         HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_in[b], cudaEventDisableTiming));
         HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_out[b], cudaEventDisableTiming));
@@ -496,6 +501,11 @@ int hp_destroy(hp_net *net)
     if (n.stream) cudaStreamDestroy(n.stream);
     if (n.comm_stream) cudaStreamDestroy(n.comm_stream);
     if (n.d2h_stream) cudaStreamDestroy(n.d2h_stream);
+    if (n.aux_stream) cudaStreamDestroy(n.aux_stream);
+    for (int b = 0; b < 3; b++) {
+        if (n.ev_fork[b]) cudaEventDestroy(n.ev_fork[b]);
+        if (n.ev_join[b]) cudaEventDestroy(n.ev_join[b]);
+    }
     delete net;
     return HP_OK;
 }

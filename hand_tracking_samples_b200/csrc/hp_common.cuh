@@ -121,6 +121,8 @@ struct Net {
     cudaStream_t stream = nullptr;        // internal stream for the HOST-buffer entry points
     cudaStream_t comm_stream = nullptr;   // gradient all-reduce stream (H2D copy stream of the host-buffer Eval)
     cudaStream_t d2h_stream = nullptr;    // D2H copy stream of the host-buffer Eval; SGD / shadow-refresh stream of the training tail
+    cudaStream_t aux_stream = nullptr;    // small-batch training: the bias-gradient reductions run here, beside the GEMM chain
+    cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
     float *params = nullptr;              // FP32 master weights, .cnnb order
     float *grads = nullptr;               // FP32 gradient sums, .cnnb order
     Workspace ws;

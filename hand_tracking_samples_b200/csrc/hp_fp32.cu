@@ -505,14 +505,23 @@ __global__ void __launch_bounds__(256) col2im_g1(const float *__restrict__ colgr
 }
 
 // LConv::update for conv1 (cnn.h:269-279) restricted to the pool winners: every
-// other conv1 output has exactly zero gradient.  partial[block][co*25+tap],
-// partial[block][400+co] (bias); thread = (co, 16 sub-lanes over pooled pixels).
+// other conv1 output has exactly zero gradient.  partial[block][co*25+tap], partial[block][400+co] (bias).
+// A warp step covers two pooled pixels of one row, four columns apart, for all 16 channels: lane = (pixel, co).  The 5x5
+// patch of a winner starts at (4 py + dy, 4 px + dx) with (dy, dx) the winner's place in its 4x4 window; with the image
+// rows padded to 68 floats the bank of a patch element is  const + 4 dy + dx + 16 pixel  -- the 16 (dy, dx) of a pixel
+// hit 16 different banks, lanes with the same winner read the same word (broadcast), and the two pixels use the two
+// halves of the banks: no conflicts.  (One thread per (co, 16 pooled pixels), as before, ran ~4-way conflicted on 375
+// shared loads per thread and crop, which -- not the FFMAs -- was the kernel's time.)
 __global__ void __launch_bounds__(256) conv1_wgrad(const float *__restrict__ x, const float *__restrict__ g1,
                                                    const uint8_t *__restrict__ idx1, int64_t n, int per_block,
                                                    float *__restrict__ partial)
 {
-    __shared__ __align__(16) float img[N_IN];
-    const int tid = threadIdx.x, co = tid >> 4, sub = tid & 15;
+    constexpr int PITCH = 68;
+    __shared__ __align__(16) float img[IN_H * PITCH];
+    __shared__ __align__(16) float sg[P1_N];       // the crop's gradients; the cross-warp reduction buffer at the end
+    __shared__ __align__(16) uint8_t si[P1_N];
+    static_assert(8 * 16 * 26 <= P1_N, "reduction buffer");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sel = lane >> 4, co = lane & 15;
     float acc[26];
 #pragma unroll
     for (int k = 0; k < 26; k++) acc[k] = 0.f;
@@ -522,47 +531,44 @@ __global__ void __launch_bounds__(256) conv1_wgrad(const float *__restrict__ x, 
         __syncthreads();
         const float4 *src = reinterpret_cast<const float4 *>(x + crop * N_IN);
 #pragma unroll
-        for (int i = 0; i < 4; i++) reinterpret_cast<float4 *>(img)[tid + 256 * i] = src[tid + 256 * i];
+        for (int i = 0; i < 4; i++) {
+            const int q = tid + 256 * i;   // float4 index: row q / 16, columns 4 (q % 16)
+            *reinterpret_cast<float4 *>(img + (q >> 4) * PITCH + (q & 15) * 4) = src[q];
+        }
+        for (int i = tid; i < P1_N / 4; i += 256) reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(g1 + crop * P1_N)[i];
+        if (tid < P1_N / 16) reinterpret_cast<uint4 *>(si)[tid] = reinterpret_cast<const uint4 *>(idx1 + crop * P1_N)[tid];
         __syncthreads();
-        // all 15 (gradient, winner) pairs of this thread are fetched before the first is used: one round of global-load
-        // latency per crop instead of fifteen
-        float gv[15];
-        int iv[15];
+        // 8 slots per pooled row: pixel pairs (q, q+4) for q = 0..3, (q+4, q+8) for q = 4..6, and pixel 11 alone
+        for (int slot = warp; slot < 8 * P1_H; slot += 8) {
+            const int py = slot >> 3, q = slot & 7;
+            const bool ok = !(q == 7 && sel == 1);
+            const int px = (q < 4 ? q : q + 4) + (ok ? 4 * sel : 0);
+            const int pp = py * P1_W + px;
+            const float g = ok ? sg[co * (P1_W * P1_H) + pp] : 0.f;
+            const int id = si[co * (P1_W * P1_H) + pp];
+            const float *ip = img + (4 * py + (id >> 2)) * PITCH + 4 * px + (id & 3);
 #pragma unroll
-        for (int j = 0; j < 15; j++) {
-            const int pp = sub + 16 * j;
-            const bool ok = pp < P1_W * P1_H;
-            gv[j] = ok ? g1[crop * P1_N + co * 225 + pp] : 0.f;
-            iv[j] = ok ? idx1[crop * P1_N + co * 225 + pp] : 0;
-        }
+            for (int ky = 0; ky < 5; ky++)
 #pragma unroll
-        for (int j = 0; j < 15; j++) {
-            const int pp = sub + 16 * j;
-            if (pp < P1_W * P1_H) {
-                const float g = gv[j];
-                const int id = iv[j];
-                const int py = pp / P1_W, px = pp % P1_W;
-                const float *ip = img + (4 * py + (id >> 2)) * IN_W + 4 * px + (id & 3);
-#pragma unroll
-                for (int ky = 0; ky < 5; ky++)
-#pragma unroll
-                    for (int kx = 0; kx < 5; kx++) acc[ky * 5 + kx] = fmaf(ip[ky * IN_W + kx], g, acc[ky * 5 + kx]);
-                acc[25] += g;
-            }
+                for (int kx = 0; kx < 5; kx++) acc[ky * 5 + kx] = fmaf(ip[ky * PITCH + kx], g, acc[ky * 5 + kx]);
+            acc[25] += g;
         }
     }
+    // the two pixel halves of a warp, then the 8 warps (fixed order: deterministic)
 #pragma unroll
-    for (int k = 0; k < 26; k++) {
-        float v = acc[k];
+    for (int k = 0; k < 26; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+    __syncthreads();
+    if (sel == 0) {
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        acc[k] = v;
+        for (int k = 0; k < 26; k++) sg[(warp * 16 + co) * 26 + k] = acc[k];
     }
-    if (sub == 0) {
-        float *dst = partial + (size_t)blockIdx.x * 416;
+    __syncthreads();
+    for (int o = tid; o < 416; o += 256) {
+        const int c = o < 400 ? o / 25 : o - 400, k = o < 400 ? o % 25 : 25;
+        float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < 25; k++) dst[co * 25 + k] = acc[k];
-        dst[400 + co] = acc[25];
+        for (int w = 0; w < 8; w++) v += sg[(w * 16 + c) * 26 + k];
+        partial[(size_t)blockIdx.x * 416 + o] = v;
     }
 }
 

@@ -620,16 +620,26 @@ __global__ void __launch_bounds__(256) conv2_bwd_operands(const float *__restric
                                                           __nv_bfloat16 *__restrict__ E, __nv_bfloat16 *__restrict__ ET, __nv_bfloat16 *__restrict__ colT,
                                                           float *__restrict__ db_partial, int n, int64_t ld)
 {
-    __shared__ __align__(16) float sg[P2_N];
+    // Shared-memory layouts chosen so that every phase reads conflict-free (the first version of this kernel spent its
+    // time in 5- to 9-way conflicted loads): the gradient transposed to [co][37], the dense error as bf16 [pos][66]
+    // (row pitch 33 words: a column walk over pos pairs is a stride-2 walk over the banks).
+    constexpr int GP = 37, EP = 66;
+    __shared__ __align__(16) float sgT[C2_CO * GP];
     __shared__ __align__(16) float sp1[P1_N];
     __shared__ __align__(16) uint8_t si[P2_N];
+    __shared__ __align__(16) __nv_bfloat16 sE[C2_POS * EP];
     __shared__ __align__(16) uint8_t s_off[C2_POS];   // pos -> y*15 + x      (its patch origin in a p1 plane)
     __shared__ __align__(16) uint8_t s_pp[C2_POS];    // pos -> pooled window (y/2)*6 + x/2
     __shared__ __align__(16) uint8_t s_sub[C2_POS];   // pos -> offset inside the window (y&1)*2 + (x&1)
     const int64_t crop = blockIdx.x;
     const int t = threadIdx.x;
     for (int i = t; i < P2_N / 4; i += 256) {
-        reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(g2_hwc + crop * P2_N)[i];
+        const float4 v = reinterpret_cast<const float4 *>(g2_hwc + crop * P2_N)[i];   // HWC: index pp*64 + co
+        const int pp = i >> 4, co0 = (i & 15) * 4;
+        sgT[(co0 + 0) * GP + pp] = v.x;
+        sgT[(co0 + 1) * GP + pp] = v.y;
+        sgT[(co0 + 2) * GP + pp] = v.z;
+        sgT[(co0 + 3) * GP + pp] = v.w;
         if (i < P2_N / 16) reinterpret_cast<uint4 *>(si)[i] = reinterpret_cast<const uint4 *>(idx2 + crop * P2_N)[i];
     }
     for (int i = t; i < P1_N / 4; i += 256) reinterpret_cast<float4 *>(sp1)[i] = reinterpret_cast<const float4 *>(p1 + crop * P1_N)[i];
@@ -640,51 +650,44 @@ __global__ void __launch_bounds__(256) conv2_bwd_operands(const float *__restric
         s_sub[t] = (uint8_t)((y & 1) * 2 + (xx & 1));
     }
     __syncthreads();
-    auto pack8 = [](const float (&v)[8]) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-        __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-        return make_uint4(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b), *reinterpret_cast<uint32_t *>(&c), *reinterpret_cast<uint32_t *>(&d));
-    };
     // conv2 dB partial of this crop (LConv::update, cnn.h:277): sum over the 36 windows
     if (t < C2_CO) {
         float a = 0.f;
 #pragma unroll 4
-        for (int pp = 0; pp < 36; pp++) a += sg[pp * 64 + t];
+        for (int pp = 0; pp < 36; pp++) a += sgT[t * GP + pp];
         db_partial[crop * C2_CO + t] = a;
     }
+    // dense error (LMaxPool::backward, cnn.h:149-164): the window's gradient at its winner, zero elsewhere.  Lanes walk co.
+    for (int i = t; i < C2_POS * C2_CO; i += 256) {
+        const int pos = i >> 6, co = i & 63;
+        const int pp = s_pp[pos];
+        const float v = (si[co * 36 + pp] == s_sub[pos]) ? sgT[co * GP + pp] : 0.f;
+        sE[pos * EP + co] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
     // E: row (crop*144 + pos) = 64 co = 8 x 16 B
     {
         uint4 *dst = reinterpret_cast<uint4 *>(E + crop * (int64_t)(C2_POS * C2_CO));
         for (int i = t; i < C2_POS * 8; i += 256) {
-            const int pos = i >> 3, co0 = (i & 7) * 8;
-            const int pp = s_pp[pos], sub = s_sub[pos];
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) v[e] = (si[(co0 + e) * 36 + pp] == sub) ? sg[pp * 64 + co0 + e] : 0.f;
-            dst[i] = pack8(v);
+            const uint32_t *r = reinterpret_cast<const uint32_t *>(sE + (i >> 3) * EP + (i & 7) * 8);
+            dst[i] = make_uint4(r[0], r[1], r[2], r[3]);
         }
     }
-    // E^T: row co, columns crop*144 + pos: 18 x 16 B per row
-    for (int i = t; i < C2_CO * 18; i += 256) {
-        const int co = i / 18, j = i - co * 18;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int pos = j * 8 + e, pp = s_pp[pos];
-            v[e] = (si[co * 36 + pp] == s_sub[pos]) ? sg[pp * 64 + co] : 0.f;
-        }
-        *reinterpret_cast<uint4 *>(ET + co * ld + crop * C2_POS + j * 8) = pack8(v);
+    // E^T: row co, columns crop*144 + pos; a lane writes one pos pair (4 B), a warp 128 contiguous bytes
+    for (int i = t; i < C2_CO * (C2_POS / 2); i += 256) {
+        const int co = i / (C2_POS / 2), jj = i - co * (C2_POS / 2);
+        __nv_bfloat162 v;
+        v.x = sE[(2 * jj) * EP + co];
+        v.y = sE[(2 * jj + 1) * EP + co];
+        *reinterpret_cast<__nv_bfloat162 *>(ET + co * ld + crop * C2_POS + 2 * jj) = v;
     }
-    // col^T: row k = tap*16 + ci, columns crop*144 + pos: 18 x 16 B per row
-    for (int i = t; i < C2_KDIM * 18; i += 256) {
-        const int k = i / 18, j = i - k * 18;
+    // col^T (im2col of p1): row k = tap*16 + ci, columns crop*144 + pos, again one pos pair per lane
+    for (int i = t; i < C2_KDIM * (C2_POS / 2); i += 256) {
+        const int k = i / (C2_POS / 2), jj = i - k * (C2_POS / 2);
         const int ci = k & 15, ky = k >> 6, kx = (k >> 4) & 3;
         const float *src = sp1 + ci * (P1_W * P1_H) + ky * P1_W + kx;
-        const uint2 o8 = *reinterpret_cast<const uint2 *>(s_off + j * 8);
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = src[((e < 4 ? o8.x : o8.y) >> (8 * (e & 3))) & 0xff];
-        *reinterpret_cast<uint4 *>(colT + k * ld + crop * C2_POS + j * 8) = pack8(v);
+        const uchar2 o = *reinterpret_cast<const uchar2 *>(s_off + 2 * jj);
+        *reinterpret_cast<__nv_bfloat162 *>(colT + k * ld + crop * C2_POS + 2 * jj) = __floats2bfloat162_rn(src[o.x], src[o.y]);
     }
     if (crop == n - 1) {
         const int64_t R = (int64_t)n * C2_POS, R64 = (R + 63) / 64 * 64;
@@ -1047,6 +1050,27 @@ int fp32_conv1_wgrad(Net &net, const float *x, int64_t n, bool accumulate, cudaS
 
 // conv stages backward of the tensor path: conv2 dL/dp1 and dW2 as tcgen05 GEMMs (see conv2_bwd_operands), conv2 dB as a
 // column sum, conv1 dW/dB winners-only on FFMA (its contraction has 25 taps x 1 input channel: no GEMM shape worth the name).
+// Small batches: the bias-gradient reductions (2-4 us each, no consumer before the bucket is handed to the update) leave
+// the GEMM chain for a side stream: fork after their input exists, join before the bucket's event.  Only the scratch-free
+// reductions qualify (colsum_direct, reduce_partials_warp on its own partial buffer).
+static inline bool side_reductions(int64_t n) { return n <= 512; }
+static int side_fork(Net &net, int i, cudaStream_t s)
+{
+    HP_CUDA_TRY(cudaEventRecord(net.ev_fork[i], s));
+    HP_CUDA_TRY(cudaStreamWaitEvent(net.aux_stream, net.ev_fork[i], 0));
+    return 0;
+}
+static int side_done(Net &net, int i)
+{
+    HP_CUDA_TRY(cudaEventRecord(net.ev_join[i], net.aux_stream));
+    return 0;
+}
+static int side_join(Net &net, int i, cudaStream_t s)
+{
+    HP_CUDA_TRY(cudaStreamWaitEvent(s, net.ev_join[i], 0));
+    return 0;
+}
+
 static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s)
 {
     TcState *t = net.tc;
@@ -1056,7 +1080,12 @@ static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const floa
     const int R = (int)(n * C2_POS);
     conv2_bwd_operands<<<(unsigned)n, 256, 0, s>>>(g2_hwc, w.idx2, w.p1, t->e2, t->e2T, t->colT, t->db2_partial, (int)n, ld);
     LAUNCH_CHECK(net);
-    if (int rc = fp32_reduce_warp(net, G + OFF_C2B, t->db2_partial, (int)n, C2_CO, accumulate, s)) return rc;
+    const bool side = side_reductions(n);
+    if (side) {
+        if (int rc = side_fork(net, 2, s)) return rc;
+        if (int rc = fp32_reduce_warp(net, G + OFF_C2B, t->db2_partial, (int)n, C2_CO, accumulate, net.aux_stream)) return rc;
+        if (int rc = side_done(net, 2)) return rc;
+    } else if (int rc = fp32_reduce_warp(net, G + OFF_C2B, t->db2_partial, (int)n, C2_CO, accumulate, s)) return rc;
     // dW2^T partials: split-K over about half the SMs' worth of ranges x 2 M tiles
     const int kb_total = (R + BK - 1) / BK;
     int target = t->num_sms / 2;
@@ -1072,7 +1101,9 @@ static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const floa
     if (int rc = launch_gemm<TC_EPI_STORE_BF16, 256, false>(net, t->tm_e2, t->tm_w2kt, EpiArgs{nullptr, dcol, nullptr, nullptr, 0, 0}, R, C2_KDIM, C2_CO, s)) return rc;
     col2im_g1_vec<<<(unsigned)n, 256, 0, s>>>(dcol, w.p1, w.g1);
     LAUNCH_CHECK(net);
-    return fp32_conv1_wgrad(net, x, n, accumulate, s);
+    if (int rc = fp32_conv1_wgrad(net, x, n, accumulate, s)) return rc;
+    if (side) return side_join(net, 2, s);
+    return 0;
 }
 
 // Forward + backward of one pass (n <= TRAIN_CAP) with every FC contraction on tcgen05:
@@ -1107,7 +1138,12 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
         loss_from_y<<<(unsigned)n, 256, 0, s>>>(w.y, t_dev, w.dlog, t->dlog_bf, mse);
         LAUNCH_CHECK(net);
     }
-    if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
+    const bool side = side_reductions(n);
+    if (side) {
+        if (int rc = side_fork(net, 0, s)) return rc;
+        if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, net.aux_stream)) return rc;
+        if (int rc = side_done(net, 0)) return rc;
+    } else if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
     transpose_bf16_pair<<<dim3(N_OUT / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->h1, t->h1T, FC1_OUT, 1}, TransposeJob{t->dlog_bf, t->dlogT, N_OUT, 0}, M,
                                                                                  n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
@@ -1119,6 +1155,8 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
         if (int rc = launch_gemm<TC_EPI_STORE_F32, 128, false>(net, t->tm_h1T, t->tm_dlogT128, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
     } else
     if (int rc = launch_gemm<TC_EPI_STORE_F32, 256, false>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
+    if (side)
+        if (int rc = side_join(net, 0, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
     // da1 = (dlog * W2^T) .* (1 - h1^2)
     if (narrow) {
@@ -1128,7 +1166,11 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[0], s));
     // ---- fc1
-    if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
+    if (side) {
+        if (int rc = side_fork(net, 1, s)) return rc;
+        if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, net.aux_stream)) return rc;
+        if (int rc = side_done(net, 1)) return rc;
+    } else if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
     transpose_bf16_pair<<<dim3(FC1_IN / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->p2, t->p2T, FC1_IN, 1}, TransposeJob{t->da1_bf, t->da1T, FC1_OUT, 0}, M,
                                                                                   n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
@@ -1139,6 +1181,8 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     } else
     if (int rc = launch_gemm<TC_EPI_STORE_F32, 256, false>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
                                                     FC1_OUT, n_pad, s)) return rc;
+    if (side)
+        if (int rc = side_join(net, 1, s)) return rc;
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
     // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order
     if (narrow) {

@@ -22,6 +22,7 @@ import torch.distributed as dist  # noqa: E402
 from hand_tracking_samples_b200 import cnn as hp, dp  # noqa: E402
 
 FLOP = 26472960
+REPS_UNIT = int(os.environ.get("HP_SWEEP_REPS_UNIT", 1 << 20))   # crops of tensor-path work per timed point and rank
 
 
 def main():
@@ -52,7 +53,9 @@ def main():
                 break
             lo, hi = dp.shard_range(n, rank, world)
             m = hi - lo
-            reps = max(3, min(200, (1 << 22) // max((n // world + 1) * (1 if name == "tensor" else 16), 1)))
+            # ~35 ms of work per point (bench.py's 20 x 65,536-crop steps): longer back-to-back runs are power-capped on this
+            # pool (1-GPU sweep of 63 passes at 65,536 crops: 33.4 M crops/s against 38-39 M in bench.py on the same box)
+            reps = max(3, min(200, REPS_UNIT // max((n // world + 1) * (1 if name == "tensor" else 32), 1)))
 
             def one():
                 if m > 0:
@@ -80,7 +83,7 @@ def main():
     if rank == 0:
         out = open(sys.argv[sys.argv.index("--out") + 1], "w") if "--out" in sys.argv else sys.stdout   # NCCL prints its version on stdout
         print(json.dumps({"gpu": torch.cuda.get_device_name(0), "n_gpus": world, "burst_bf16_tflops_per_gpu": pk["bf16_tflops"], "hbm_gbs": pk["hbm_gbs"],
-                          "note": "global batch sharded evenly, no collective; time = max over ranks", "rows": rows}, indent=1), file=out)
+                          "note": "global batch sharded evenly, no collective; time = max over ranks", "reps_unit": REPS_UNIT, "rows": rows}, indent=1), file=out)
     if world > 1:
         dist.destroy_process_group()
 
