@@ -245,9 +245,14 @@ static int finish_step(Net &net, float alpha, int precision, cudaStream_t s)
             // one GPU: the conv bucket is the exposed end of the step and backward has just finished on the caller's
             // stream, so its update runs right there (no cross-stream hops); the side stream's FC work is joined after it
             HP_CUDA_TRY(cudaEventRecord(net.ev_tail, us));
-            if (int rc = sgd_apply_range(net, alpha, off[b], end[b] - off[b], s)) return rc;
-            if (precision == HP_PRECISION_TENSOR)
-                if (int rc = tc_refresh_bucket(net, b, s)) return rc;
+            static const bool unfused_conv = getenv("HP_SGD_UNFUSED") != nullptr;
+            if (precision == HP_PRECISION_TENSOR && !unfused_conv) {
+                if (int rc = tc_sgd_conv_images(net, alpha, s)) return rc;
+            } else {
+                if (int rc = sgd_apply_range(net, alpha, off[b], end[b] - off[b], s)) return rc;
+                if (precision == HP_PRECISION_TENSOR)
+                    if (int rc = tc_refresh_bucket(net, b, s)) return rc;
+            }
             HP_CUDA_TRY(cudaStreamWaitEvent(s, net.ev_tail, 0));
             net.tc_dirty = (precision != HP_PRECISION_TENSOR);
             return 0;
@@ -255,6 +260,11 @@ static int finish_step(Net &net, float alpha, int precision, cudaStream_t s)
             HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_bucket[b], 0));
         }
         if (b < 2) HP_CUDA_TRY(cudaStreamWaitEvent(us, net.ev_dx[b], 0));
+        static const bool unfused = getenv("HP_SGD_UNFUSED") != nullptr;   // A/B: separate SGD and shadow-refresh kernels
+        if (net.world == 1 && precision == HP_PRECISION_TENSOR && b < 2 && !unfused) {
+            if (int rc = tc_sgd_refresh_fc(net, b, alpha, us)) return rc;   // one pass over the bucket: update + both shadows
+            continue;
+        }
         if (int rc = sgd_apply_range(net, alpha, off[b], end[b] - off[b], us)) return rc;
         if (precision == HP_PRECISION_TENSOR)
             if (int rc = tc_refresh_bucket(net, b, us)) return rc;
@@ -389,6 +399,12 @@ static int create_resources(Net &n)
     }
     HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.d2h_stream, cudaStreamNonBlocking));
     HP_CUDA_TRY(cudaStreamCreateWithFlags(&n.aux_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        HP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        HP_CUDA_TRY(cudaStreamCreateWithPriority(&n.hi_stream, cudaStreamNonBlocking, hi));
+        for (int b = 0; b < 2; b++) HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_hi[b], cudaEventDisableTiming));
+    }
     for (int b = 0; b < 3; b++) {
         HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_fork[b], cudaEventDisableTiming));
         HP_CUDA_TRY(cudaEventCreateWithFlags(&n.ev_join[b], cudaEventDisableTiming));
@@ -502,6 +518,9 @@ int hp_destroy(hp_net *net)
     if (n.comm_stream) cudaStreamDestroy(n.comm_stream);
     if (n.d2h_stream) cudaStreamDestroy(n.d2h_stream);
     if (n.aux_stream) cudaStreamDestroy(n.aux_stream);
+    if (n.hi_stream) cudaStreamDestroy(n.hi_stream);
+    for (int b = 0; b < 2; b++)
+        if (n.ev_hi[b]) cudaEventDestroy(n.ev_hi[b]);
     for (int b = 0; b < 3; b++) {
         if (n.ev_fork[b]) cudaEventDestroy(n.ev_fork[b]);
         if (n.ev_join[b]) cudaEventDestroy(n.ev_join[b]);
@@ -884,11 +903,28 @@ int hp_apply_grads_device(hp_net *net, float alpha, void *stream)
 }
 
 // One step, eagerly: forward + backward on the caller's stream, the update tail pipelined on the side streams.
+// One GPU, tensor path: the chain forward -> backward runs on an internal HIGH-priority stream forked from the caller's (and
+// joined back at the end), so that its CTAs are dispatched ahead of the thousands of pending CTAs of the update tail that
+// overlaps it (the 200 KB GEMM CTAs otherwise wait for the update's grid to drain: measured 11 us on one GEMM).  Stream
+// priorities are recorded per kernel node when the step is captured, so the replayed graph keeps them.
 static int train_step_eager(Net &N, const float *x_dev, const float *t_dev, int64_t n, float alpha, float *mse_dev, int precision, cudaStream_t s)
 {
-    HP_CUDA_TRY(cudaEventRecord(N.ev_start, s));
-    if (int rc = grad_device(N, x_dev, t_dev, n, mse_dev, precision, s)) return rc;
-    return finish_step(N, alpha, precision, s);
+    static const bool no_hi = getenv("HP_NO_PRIORITY") != nullptr;   // A/B
+    const bool hi = N.world == 1 && precision == HP_PRECISION_TENSOR && !N.step_timing && !no_hi;
+    cudaStream_t m = s;
+    if (hi) {
+        HP_CUDA_TRY(cudaEventRecord(N.ev_hi[0], s));
+        HP_CUDA_TRY(cudaStreamWaitEvent(N.hi_stream, N.ev_hi[0], 0));
+        m = N.hi_stream;
+    }
+    HP_CUDA_TRY(cudaEventRecord(N.ev_start, m));
+    if (int rc = grad_device(N, x_dev, t_dev, n, mse_dev, precision, m)) return rc;
+    if (int rc = finish_step(N, alpha, precision, m)) return rc;
+    if (hi) {
+        HP_CUDA_TRY(cudaEventRecord(N.ev_hi[1], m));
+        HP_CUDA_TRY(cudaStreamWaitEvent(s, N.ev_hi[1], 0));
+    }
+    return 0;
 }
 
 int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, int64_t n, float alpha, float *mse_dev, int precision,
@@ -934,7 +970,7 @@ int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, i
         const cudaError_t ce = cudaStreamEndCapture(s, &graph);
         G.launches_per_step = N.launches - l0;
         N.launches = l0;
-        if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) {
+        if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiateWithFlags(&G.exec, graph, cudaGraphInstantiateFlagUseNodePriority) != cudaSuccess) {
             cudaGetLastError();
             if (graph) cudaGraphDestroy(graph);
             G.exec = nullptr;

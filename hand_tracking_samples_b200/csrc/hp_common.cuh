@@ -108,6 +108,8 @@ int tc_forward_u16(Net &net, const uint16_t *depth, float depth_scale, float dmi
 int tc_forward_decode(Net &net, const float *x, const uint16_t *x16, float depth_scale, float dmin, float dmax, int64_t n, float *y_out, float *dec_out,
                       cudaStream_t s);
 int tc_refresh_weights(Net &net, cudaStream_t s);
+int tc_sgd_refresh_fc(Net &net, int bucket, float alpha, cudaStream_t s);   // one GPU: SGD + both shadows of FC bucket 0 / 1 in one pass
+int tc_sgd_conv_images(Net &net, float alpha, cudaStream_t s);             // one GPU: SGD on the conv bucket + its 16-bit images
 int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s);   // 0: fc2 shadows, 1: fc1 shadows, 2: conv images
 int tc_init(Net &net);
 void tc_destroy(Net &net);
@@ -123,6 +125,8 @@ struct Net {
     cudaStream_t d2h_stream = nullptr;    // D2H copy stream of the host-buffer Eval; SGD / shadow-refresh stream of the training tail
     cudaStream_t aux_stream = nullptr;    // small-batch training: the bias-gradient reductions run here, beside the GEMM chain
     cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t hi_stream = nullptr;     // one GPU, tensor path: the step's forward -> backward chain (priority over the update tail's CTAs)
+    cudaEvent_t ev_hi[2] = {nullptr, nullptr};
     float *params = nullptr;              // FP32 master weights, .cnnb order
     float *grads = nullptr;               // FP32 gradient sums, .cnnb order
     Workspace ws;

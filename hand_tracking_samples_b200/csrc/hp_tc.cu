@@ -573,6 +573,35 @@ __global__ void __launch_bounds__(256) convert_rows_bf16(const float *__restrict
     }
 }
 
+// One GPU, tensor path: SGD on one FC weight matrix (w <- fma(-alpha, g, w), sgd_kernel's arithmetic) fused with the
+// rebuild of both of its 16-bit shadows -- transpose_to_act + convert_rows_bf16 above read the updated fp32 weights twice
+// more; here every weight and gradient is read once and the three results are written from registers / one smem tile.
+// 75 MB of HBM traffic per FC bucket instead of 113 MB, next to the backward kernels that share the bandwidth.
+// One 32x32 tile per CTA.  (A persistent two-CTAs-per-SM variant that leaves room for the GEMM CTAs beside it was tried:
+// the co-resident weight-gradient GEMM then ran 25 us instead of 9.  What works is priority: the step's main chain runs on
+// a high-priority stream, so its CTAs are dispatched ahead of the pending tiles of this kernel -- hp_api.cu.)
+template <bool HWC>
+__global__ void __launch_bounds__(256) sgd_refresh_fc(float *__restrict__ w, const float *__restrict__ g, float alpha, act_t *__restrict__ wt,
+                                                      __nv_bfloat16 *__restrict__ wb, int K, int N)
+{
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int kd = k0 + ty + 8 * i;
+        const int ks = HWC ? (kd & 63) * 36 + (kd >> 6) : kd;
+        const size_t o = (size_t)ks * N + n0 + tx;
+        const float v = fmaf(-alpha, g[o], w[o]);
+        w[o] = v;
+        wb[(size_t)kd * N + n0 + tx] = __float2bfloat16_rn(v);
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) wt[(size_t)(n0 + ty + 8 * i) * K + k0 + tx] = __float2half_rn(tile[tx][ty + 8 * i]);
+}
+
 // 16-bit src[n][C] -> bf16 dst[C][ldk] (k contiguous) with zero fill for n <= k < n_pad: the K-major operands of the
 // weight-gradient GEMMs (LFull::update, cnn.h:438-445, is the contraction over the batch).  Both operands of one GEMM
 // are transposed by one launch (blockIdx.z picks the job).
@@ -861,7 +890,7 @@ void tc_destroy(Net &net)
     if (!t) return;
     if (t->w1t) cudaFree(t->w1t);
     if (t->w2t) cudaFree(t->w2t);
-    void *tb[] = {t->w1b, t->w2b, t->dlog_bf, t->da1_bf, t->h1T, t->dlogT, t->p2T, t->da1T, t->e2, t->e2T, t->colT, t->w2kt, t->db2_partial};
+    void *tb[] = {t->w1b, t->w2b, t->dlog_bf, t->da1_bf, t->g2_sink, t->h1T, t->dlogT, t->p2T, t->da1T, t->e2, t->e2T, t->colT, t->w2kt, t->db2_partial};
     for (void *q : tb)
         if (q) cudaFree(q);
     if (t->b1_img) cudaFree(t->b1_img);
@@ -892,6 +921,20 @@ int tc_refresh_bucket(Net &net, int bucket, cudaStream_t s)
         if (int rc = tc_conv_refresh(net, s)) return rc;   // b1/b2 images and w2kt (the dL/dcol GEMM's B operand)
     }
     return 0;
+}
+
+// SGD + shadow refresh of FC bucket 0 (fc2) or 1 (fc1) in one pass over the weights; the bias follows as a plain SGD range
+int tc_sgd_refresh_fc(Net &net, int bucket, float alpha, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    if (bucket == 0) {
+        sgd_refresh_fc<false><<<dim3(FC2_OUT / 32, FC2_IN / 32), 256, 0, s>>>(net.params + OFF_F2W, net.grads + OFF_F2W, alpha, t->w2t, t->w2b, FC2_IN, FC2_OUT);
+        LAUNCH_CHECK(net);
+        return sgd_apply_range(net, alpha, OFF_F2B, N_PARAMS - OFF_F2B, s);
+    }
+    sgd_refresh_fc<true><<<dim3(FC1_OUT / 32, FC1_IN / 32), 256, 0, s>>>(net.params + OFF_F1W, net.grads + OFF_F1W, alpha, t->w1t, t->w1b, FC1_IN, FC1_OUT);
+    LAUNCH_CHECK(net);
+    return sgd_apply_range(net, alpha, OFF_F1B, OFF_F2W - OFF_F1B, s);
 }
 
 int tc_refresh_weights(Net &net, cudaStream_t s)
@@ -1011,6 +1054,7 @@ static int tc_train_ensure(Net &net)
     const int64_t cap = TRAIN_CAP;
     HP_CUDA_TRY(cudaMalloc((void **)&t->dlog_bf, (size_t)cap * N_OUT * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->da1_bf, (size_t)cap * FC1_OUT * 2));
+    HP_CUDA_TRY(cudaMalloc((void **)&t->g2_sink, (size_t)cap * FC1_IN * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->h1T, (size_t)FC1_OUT * cap * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->dlogT, (size_t)N_OUT * cap * 2));
     HP_CUDA_TRY(cudaMalloc((void **)&t->p2T, (size_t)FC1_IN * cap * 2));
@@ -1138,26 +1182,26 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
         loss_from_y<<<(unsigned)n, 256, 0, s>>>(w.y, t_dev, w.dlog, t->dlog_bf, mse);
         LAUNCH_CHECK(net);
     }
+    // Small batches: the weight-gradient branch of each FC layer (bias column sums, operand transposes, dW GEMM -- nothing
+    // downstream in backward reads it) leaves the chain for the side stream; the chain is then loss -> dX2 -> dX1 -> conv
+    // backward.  The bucket events are recorded where the branch ends; conv backward joins the side stream at its end.
     const bool side = side_reductions(n);
-    if (side) {
+    cudaStream_t wg = side ? net.aux_stream : s;
+    if (side)
         if (int rc = side_fork(net, 0, s)) return rc;
-        if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, net.aux_stream)) return rc;
-        if (int rc = side_done(net, 0)) return rc;
-    } else if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, s)) return rc;
-    transpose_bf16_pair<<<dim3(N_OUT / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->h1, t->h1T, FC1_OUT, 1}, TransposeJob{t->dlog_bf, t->dlogT, N_OUT, 0}, M,
-                                                                                 n_pad, (int)TRAIN_CAP);
+    if (int rc = fp32_colsum(net, w.dlog, n, FC2_OUT, G + OFF_F2B, accumulate, wg)) return rc;
+    transpose_bf16_pair<<<dim3(N_OUT / 32, (n_pad + 31) / 32, 2), 256, 0, wg>>>(TransposeJob{t->h1, t->h1T, FC1_OUT, 1}, TransposeJob{t->dlog_bf, t->dlogT, N_OUT, 0}, M,
+                                                                                  n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW2[2048][2304] = h1^T * dlog
     // 16 x 9 = 144 tiles of 128x256 are one wave on 148 SMs but two on the 132 left when SMs are reserved for the
     // data-parallel exchange CTAs: 128-wide tiles (288 of them) then waste a fifth of a wave instead of most of one
     const bool half_tiles = t->num_sms < 144;
     if (half_tiles) {
-        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128, false>(net, t->tm_h1T, t->tm_dlogT128, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_STORE_F32, 128, false>(net, t->tm_h1T, t->tm_dlogT128, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, wg)) return rc;
     } else
-    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256, false>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, s)) return rc;
-    if (side)
-        if (int rc = side_join(net, 0, s)) return rc;
-    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], s));
+    if (int rc = launch_gemm<TC_EPI_STORE_F32, 256, false>(net, t->tm_h1T, t->tm_dlogT, EpiArgs{nullptr, G + OFF_F2W, nullptr, nullptr, flags}, FC2_IN, FC2_OUT, n_pad, wg)) return rc;
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], wg));
     // da1 = (dlog * W2^T) .* (1 - h1^2)
     if (narrow) {
         if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_dlog, t->tm_w2b64, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
@@ -1166,35 +1210,36 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[0], s));
     // ---- fc1
-    if (side) {
+    if (side)
         if (int rc = side_fork(net, 1, s)) return rc;
-        if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, net.aux_stream)) return rc;
-        if (int rc = side_done(net, 1)) return rc;
-    } else if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, s)) return rc;
-    transpose_bf16_pair<<<dim3(FC1_IN / 32, (n_pad + 31) / 32, 2), 256, 0, s>>>(TransposeJob{t->p2, t->p2T, FC1_IN, 1}, TransposeJob{t->da1_bf, t->da1T, FC1_OUT, 0}, M,
-                                                                                  n_pad, (int)TRAIN_CAP);
+    if (int rc = fp32_colsum(net, w.da1, n, FC1_OUT, G + OFF_F1B, accumulate, wg)) return rc;
+    transpose_bf16_pair<<<dim3(FC1_IN / 32, (n_pad + 31) / 32, 2), 256, 0, wg>>>(TransposeJob{t->p2, t->p2T, FC1_IN, 1}, TransposeJob{t->da1_bf, t->da1T, FC1_OUT, 0}, M,
+                                                                                   n_pad, (int)TRAIN_CAP);
     LAUNCH_CHECK(net);
     // dW1[k'][2048] = p2^T * da1, rows un-permuted from HWC to the reference's CHW flatten on store
     if (half_tiles) {
         if (int rc = launch_gemm<TC_EPI_STORE_F32, 128, false>(net, t->tm_p2T, t->tm_da1T128, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW},
-                                                        FC1_IN, FC1_OUT, n_pad, s)) return rc;
+                                                        FC1_IN, FC1_OUT, n_pad, wg)) return rc;
     } else
     if (int rc = launch_gemm<TC_EPI_STORE_F32, 256, false>(net, t->tm_p2T, t->tm_da1T, EpiArgs{nullptr, G + OFF_F1W, nullptr, nullptr, flags | TC_FLAG_ROWS_HWC_TO_CHW}, FC1_IN,
-                                                    FC1_OUT, n_pad, s)) return rc;
-    if (side)
-        if (int rc = side_join(net, 1, s)) return rc;
-    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], s));
-    // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order
+                                                    FC1_OUT, n_pad, wg)) return rc;
+    HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], wg));
+    // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order (the epilogue's bf16 copy is not needed: it goes to a sink of
+    // its own -- dlog_bf, the sink before, may still be read by the side stream's transpose)
     if (narrow) {
-        if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->g2_sink, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     } else {
-        if (int rc = launch_gemm<TC_EPI_DTANH, 256, false>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->dlog_bf /*scratch bf16 sink*/, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
+        if (int rc = launch_gemm<TC_EPI_DTANH, 256, false>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->g2_sink, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[1], s));
     // ---- conv stages backward (winners-only weight gradients; FFMA)
     static const bool ffma_conv_bwd = getenv("HP_CONV_BWD_FFMA") != nullptr;   // A/B switch for the previous FFMA kernels
     if (ffma_conv_bwd) {
         if (int rc = tc_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
+        if (side) {   // the side stream's weight-gradient branch rejoins the chain here (the GEMM route joins it itself)
+            if (int rc = side_done(net, 2)) return rc;
+            if (int rc = side_join(net, 2, s)) return rc;
+        }
     } else {
         if (int rc = tc_conv_backward_gemm(net, x, n, w.g2, accumulate, s)) return rc;
     }

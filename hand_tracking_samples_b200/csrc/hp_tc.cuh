@@ -78,6 +78,7 @@ struct TcState {
     __nv_bfloat16 *w1b = nullptr;  // [2304 (k' HWC)][2048] = fc1.W as stored (B operand of the fc1 dX GEMM)
     __nv_bfloat16 *w2b = nullptr;  // [2048][2304] = fc2.W as stored
     // training activations (TRAIN_CAP samples per pass)
+    __nv_bfloat16 *g2_sink = nullptr;                               // [cap][2304]: unused bf16 copy of the fc1 dX epilogue
     __nv_bfloat16 *dlog_bf = nullptr, *da1_bf = nullptr;            // [cap][2304], [cap][2048]
     __nv_bfloat16 *h1T = nullptr, *dlogT = nullptr, *p2T = nullptr, *da1T = nullptr;  // [features][cap]: batch-contiguous (K-major for dW)
     // conv2 backward as GEMMs: dense error rows / its transpose / transposed im2col of p1, (n,pos) padded to TRAIN_CAP*144

@@ -472,6 +472,43 @@ __global__ void __launch_bounds__(256) build_conv_images(const float *__restrict
     build_conv_image_elem(blockIdx.x * 256 + threadIdx.x, params, b1, b2, w2kt);
 }
 
+// One GPU, tensor path: SGD on the conv bucket fused with the update of every 16-bit image derived from it (the scatter
+// form of build_conv_image_elem / build_conv2_tmem_image: a weight knows where its copies live; the images' structural
+// zeros never change).  One kernel at the exposed end of the step instead of three.
+__global__ void __launch_bounds__(256) sgd_conv_images(float *__restrict__ params, const float *__restrict__ grads, float alpha, uint8_t *__restrict__ b1,
+                                                       uint8_t *__restrict__ b2, __nv_bfloat16 *__restrict__ w2kt, __half *__restrict__ a2)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= OFF_F1W) return;
+    const float w = fmaf(-alpha, grads[i], params[i]);   // sgd_kernel's arithmetic
+    params[i] = w;
+    if (i < OFF_C1B) {
+        const int co = i / 25, tap = i - co * 25, ky = tap / 5, kx = tap - ky * 5;
+        const __half h = __float2half_rn(w);
+#pragma unroll
+        for (int pos = 0; pos < 16; pos++) {
+            const int blk = pos >> 2, sub = pos & 3, dy = 2 * (blk >> 1) + (sub >> 1), dx = 2 * (blk & 1) + (sub & 1);
+            const int nrow = pos * 16 + co, r = ky + dy, c = kx + dx;
+            reinterpret_cast<__half *>(b1 + nrow * 128 + ((r ^ (nrow & 7)) << 4))[c] = h;
+        }
+    } else if (i >= OFF_C2W && i < OFF_C2B) {
+        const int j = i - OFF_C2W;
+        const int co = j >> 8, ci = (j >> 4) & 15, tap = j & 15, ky = tap >> 2, kx = tap & 3;
+        const __half h = __float2half_rn(w);
+        reinterpret_cast<__half *>(b2)[((tap * 2 + (ci >> 3)) * 64 + co) * 8 + (ci & 7)] = h;
+        w2kt[(tap * 16 + ci) * C2_CO + co] = __float2bfloat16_rn(w);
+        a2[(2 * co + (kx >> 1)) * 128 + (ky * 2 + (kx & 1)) * 16 + ci] = h;
+    }
+}
+
+int tc_sgd_conv_images(Net &net, float alpha, cudaStream_t s)
+{
+    TcState *t = net.tc;
+    sgd_conv_images<<<(OFF_F1W + 255) / 256, 256, 0, s>>>(net.params, net.grads, alpha, t->b1_img, t->b2_img, t->w2kt, reinterpret_cast<__half *>(t->a2_img));
+    LAUNCH_CHECK(net);
+    return 0;
+}
+
 #ifdef HP_CONV_TRACE
 extern "C" __attribute__((visibility("default"))) int hp_debug_conv_trace(long long *out, int n)
 {
