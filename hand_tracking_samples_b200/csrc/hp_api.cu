@@ -1097,8 +1097,10 @@ int hp_dp_peer_init(hp_net *net, const void *all_handles, int rank, int world)
     Net &N = net->n;
     HP_CUDA_TRY(cudaSetDevice(N.device));
     if (N.peer && N.peer->ready) { set_error("peer exchange already initialised on this net; call hp_dp_shutdown first"); return HP_ERR_INVALID; }
-    // the exchange kernels run one 1024-thread CTA on each SM that the persistent tensor-core grids leave free
-    int reserve = 16;
+    // the exchange kernels run one 1024-thread CTA on each SM that the persistent tensor-core grids leave free.  32: with
+    // the step's chain at ~175 us (batch 256) the two FC exchanges are the critical path at 16 CTAs (70 us each, 2 GPUs:
+    // 232 us/step); at 32 they are hidden again (193 us/step; 24: 202, 48: 196, 64: 209 -- profiles/r2_dp_exchange.md)
+    int reserve = 32;
     if (const char *e = getenv("HP_DP_RESERVE_SMS")) reserve = atoi(e);
     if (int rc = peer_init(N, all_handles, rank, world, reserve)) return rc;
     drop_step_graph(N);
