@@ -86,6 +86,30 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     pass
 
+    def sample_now(self):
+        """One synchronous NVML sample from the calling thread (the main thread calls this right after it has queued the
+        timed steps, while the GPU is still executing them): the region has samples even if the polling thread was starved."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((time.perf_counter(), float(sm), float(mx), int(rs)))
+        except Exception:
+            pass
+
     def mark_begin(self):
         self.t_begin = time.perf_counter()
 
@@ -241,6 +265,9 @@ def main():
     for _ in range(K):
         net.eval_batch_device(x.data_ptr(), B, y.data_ptr(), precision=hp.PRECISION_TENSOR, stream=stream)
     e1.record()
+    for _ in range(3):          # the GPU is still working through the queued steps: these samples are under load
+        sampler.sample_now()
+        time.sleep(0.002)
     barrier()
     sampler.mark_end()
     launches = net.launch_count() - l0
