@@ -420,6 +420,37 @@ def test_minibatch256_step_vs_oracle_both_paths(net, p0):
         assert maxnorm_err(p[off:off + cnt], pw[off:off + cnt]) <= FP32_TOL, k
 
 
+def test_fused_updates_leave_the_16bit_shadows_equal_to_a_full_rebuild():
+    # The single-GPU tensor-path step updates the 16-bit operand copies inside its update kernels (sgd_refresh_fc: fp16
+    # W^T and bf16 W of an FC layer; sgd_conv_images: the conv weight images) instead of rebuilding them from the fp32
+    # master weights.  After a few steps -- the later ones replayed as a CUDA graph -- outputs and gradients must be
+    # bit-identical to what a full rebuild from the master weights gives (set_params marks every shadow stale).
+    import torch
+    n = 96
+    x = np.concatenate([synth.depthlike_crops(64, 301), synth.uniform_crops(32, 302)])
+    t = synth.heatmap_labels(n, 303)
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+    mse = torch.empty(n, device="cuda")
+    side = torch.cuda.Stream()
+    fresh = hp.PoseInitializerCNN("")
+    for _ in range(4):
+        fresh.train_batch_device(xd.data_ptr(), td.data_ptr(), n, 0.01 / n, mse.data_ptr(), precision=hp.PRECISION_TENSOR, stream=side.cuda_stream)
+    torch.cuda.synchronize()
+
+    def probe():
+        y = fresh.eval_batch(x[:32], precision=hp.PRECISION_TENSOR)
+        fresh.grad_batch_device(xd.data_ptr(), td.data_ptr(), n, mse.data_ptr(), precision=hp.PRECISION_TENSOR, stream=side.cuda_stream)
+        torch.cuda.synchronize()
+        return y, fresh.get_grads()
+
+    y_a, g_a = probe()
+    fresh.set_params(fresh.get_params())
+    y_b, g_b = probe()
+    assert np.array_equal(y_a, y_b)
+    assert np.array_equal(g_a, g_b)
+    assert not np.array_equal(fresh.get_params(), hp.PoseInitializerCNN("").get_params())   # the steps did move the weights
+
+
 def test_tensor_path_pool_winners_agree_with_fp32_path(net):
     import torch
     n = 16
