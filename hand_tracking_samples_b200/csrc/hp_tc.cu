@@ -29,7 +29,6 @@ namespace hp {
         HP_CUDA_TRY(cudaGetLastError()); \
     } while (0)
 
-constexpr int GEMM_CL = 4;           // CTAs per cluster of the small-batch GEMMs (share the A tile by TMA multicast)
 constexpr int64_t TC_CHUNK = 16384;  // crops per pass of the tensor-core path (activation workspace bound)
 
 // ---- GEMM tile configuration -----------------------------------------------------------
@@ -108,16 +107,10 @@ static int make_map_f16(CUtensorMap *m, const void *base, uint64_t rows, uint64_
 // C[M x N] = A[M x K] * Bt[N x K]^T  (+ fused epilogue); A, Bt bf16 K-major via TMA.
 // ============================================================================
 // OPS_F16: both operands are IEEE half (forward GEMMs); otherwise bf16 (backward GEMMs).
-// CL > 1 (narrow tiles at small batches): CL CTAs of a thread-block cluster work on CL neighbouring N tiles of the same M
-// tile and share its A tile -- each loads BM / CL of its rows and TMA-multicasts them into all CL shared memories (tmA then
-// has BM / CL-row boxes), and a stage is free again when the MMAs of all CL CTAs have consumed it (commit multicast onto
-// every CTA's empty barrier).  At 64-wide tiles a CTA otherwise pulls 128 rows of activations for 64 of weights through
-// its SM's L2 port, and that port is what bounds these GEMMs at batch 256.
-template <int EPI, int BN, bool OPS_F16, int CL = 1>
+template <int EPI, int BN, bool OPS_F16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs ea, int M, int N, int K)
 {
-    static_assert(CL == 1 || (BM % CL == 0 && (BM / CL) % 8 == 0), "A slices must be whole swizzle atoms");
     static_assert((EPI != TC_EPI_SOFTMAX_F32 && EPI != TC_EPI_SOFTMAX_DECODE) || BN == 256, "the fused chunked softmax needs whole 256-wide spans in one tile");
     constexpr int STAGES = stages_for(BN);
     constexpr int B_BYTES = BN * BK * 2;
@@ -138,14 +131,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m_tiles = (M + BM - 1) / BM;
     const int mn_tiles = m_tiles * n_tiles;
     const int kb_total = (K + BK - 1) / BK;     // a ragged last block reads zeros (TMA out-of-bounds fill)
-    const int ksplit = (CL == 1 && EPI == TC_EPI_STORE_F32 && ea.ksplit > 1) ? ea.ksplit : 1;
+    const int ksplit = (EPI == TC_EPI_STORE_F32 && ea.ksplit > 1) ? ea.ksplit : 1;
     const int kb_per = (kb_total + ksplit - 1) / ksplit;
     const int num_tiles = mn_tiles * ksplit;
-    // tile walk: CL == 1: tile = blockIdx.x, += gridDim.x.  CL > 1: the cluster walks groups of CL N tiles, CTA r takes the r-th
-    const uint32_t crank = CL > 1 ? ptx::cluster_ctarank() : 0;
-    const int tile0 = CL > 1 ? (int)(blockIdx.x / CL) * CL + (int)crank : (int)blockIdx.x;   // (n_tiles % CL == 0: a group never straddles M tiles)
-    const int tile_step = (int)gridDim.x;
-    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -154,7 +142,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], CL);
+            ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&tmem_full[a], 1);
@@ -165,7 +153,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
     ptx::tc_fence_before();
     __syncthreads();
-    if (CL > 1) ptx::cluster_sync();   // no peer may multicast into this CTA or arrive on its barriers before they exist
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -174,7 +161,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
                 const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
                 const int kb0 = split * kb_per, kb1 = (kb0 + kb_per < kb_total) ? kb0 + kb_per : kb_total;
@@ -182,9 +169,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     uint8_t *sa = smem + stage * STAGE_BYTES;
-                    if (CL > 1)
-                        ptx::tma_load_2d_multicast(sa + crank * (A_BYTES / CL), &tmA, &full_bar[stage], kb * BK, m_blk * BM + (int)crank * (BM / CL), CMASK);
-                    else
                     ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
                     ptx::tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -197,7 +181,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = tile0; tile < num_tiles; tile += tile_step, it++) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -218,8 +202,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ptx::umma_f16_c<true>(tmem_d, adesc + 2, bdesc + 2, idesc);
                     ptx::umma_f16_c<true>(tmem_d, adesc + 4, bdesc + 4, idesc);
                     ptx::umma_f16_c<true>(tmem_d, adesc + 6, bdesc + 6, idesc);
-                    if (CL > 1) ptx::umma_commit_multicast(&empty_bar[stage], CMASK);
-                    else ptx::umma_commit(&empty_bar[stage]);
+                    ptx::umma_commit(&empty_bar[stage]);
                     if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
                 }
                 __syncwarp();
@@ -230,7 +213,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== epilogue: thread <-> accumulator row =====
         const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
         int it = 0;
-        for (int tile = tile0; tile < num_tiles; tile += tile_step, it++) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
             const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
             const int as = it & 1;
@@ -547,7 +530,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (CL > 1) ptx::cluster_sync();   // peers' multicasts and barrier arrivals target this CTA's shared memory until they are done too
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
@@ -877,13 +859,6 @@ int tc_init(Net &net)
     if (int rc = make_map_f16(&t->tm_w2t, t->w2t, FC2_OUT, FC2_IN, 256)) return rc;
     if (int rc = make_map_f16(&t->tm_w1t64, t->w1t, FC1_OUT, FC1_IN, 64)) return rc;
     if (int rc = make_map_f16(&t->tm_w2t64, t->w2t, FC2_OUT, FC2_IN, 64)) return rc;
-#define HP_GEMM_ATTR_CL(EPI, BN, F16) \
-    HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, F16, GEMM_CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(BN)))
-    HP_GEMM_ATTR_CL(TC_EPI_TANH_ACT, 64, true);
-    HP_GEMM_ATTR_CL(TC_EPI_STORE_F32, 64, true);
-    HP_GEMM_ATTR_CL(TC_EPI_DTANH, 64, false);
-#undef HP_GEMM_ATTR_CL
-    if (const char *e = getenv("HP_GEMM_CLUSTER")) t->gemm_cluster = e[0] != '0';
 #define HP_GEMM_ATTR(EPI, BN, F16) \
     HP_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(BN)))
     HP_GEMM_ATTR(TC_EPI_TANH_ACT, 256, true);
@@ -986,8 +961,6 @@ static int tc_ensure(Net &net, int64_t n)
     HP_CUDA_TRY(cudaMemset(t->h1, 0, (size_t)cap * FC1_OUT * 2));
     if (int rc = make_map_f16(&t->tm_p2, t->p2, cap, FC1_IN, BM)) return rc;
     if (int rc = make_map_f16(&t->tm_h1, t->h1, cap, FC1_OUT, BM)) return rc;
-    if (int rc = make_map_f16(&t->tm_p2_q, t->p2, cap, FC1_IN, BM / GEMM_CL)) return rc;
-    if (int rc = make_map_f16(&t->tm_h1_q, t->h1, cap, FC1_OUT, BM / GEMM_CL)) return rc;
     t->cap = cap;
     return 0;
 }
@@ -1052,32 +1025,6 @@ int tc_forward_decode(Net &net, const float *x, const uint16_t *x16, float depth
     return tc_forward_impl(net, x, x16, depth_scale, dmin, dmax, n, y_out, dec_out, s);
 }
 
-// narrow GEMM on clusters of GEMM_CL CTAs that share the A tile by TMA multicast (tmA must have BM / GEMM_CL-row boxes)
-template <int EPI, int BN, bool OPS_F16>
-static int launch_gemm_cluster(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB, const EpiArgs &ea, int M, int N, int K, cudaStream_t s)
-{
-    TcState *t = net.tc;
-    const int tiles = ((M + BM - 1) / BM) * (N / BN);
-    int grid = tiles < t->num_sms ? tiles : t->num_sms;
-    grid -= grid % GEMM_CL;
-    if ((N / BN) % GEMM_CL != 0 || grid < GEMM_CL) { set_error("cluster GEMM: %d N tiles / grid %d not a multiple of %d", N / BN, grid, GEMM_CL); return 1; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = gemm_smem(BN);
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = GEMM_CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    HP_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BN, OPS_F16, GEMM_CL>, tmA, tmB, ea, M, N, K));
-    LAUNCH_CHECK(net);
-    return 0;
-}
-
 template <int EPI, int BN, bool OPS_F16>
 static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB, const EpiArgs &ea, int M, int N, int K, cudaStream_t s)
 {
@@ -1120,8 +1067,6 @@ static int tc_train_ensure(Net &net)
     HP_CUDA_TRY(cudaMemset(t->da1T, 0, (size_t)FC1_OUT * cap * 2));
     if (int rc = make_map_bf16(&t->tm_dlog, t->dlog_bf, cap, N_OUT, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_da1, t->da1_bf, cap, FC1_OUT, BM)) return rc;
-    if (int rc = make_map_bf16(&t->tm_dlog_q, t->dlog_bf, cap, N_OUT, BM / GEMM_CL)) return rc;
-    if (int rc = make_map_bf16(&t->tm_da1_q, t->da1_bf, cap, FC1_OUT, BM / GEMM_CL)) return rc;
     if (int rc = make_map_bf16(&t->tm_h1T, t->h1T, FC1_OUT, cap, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_p2T, t->p2T, FC1_IN, cap, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_dlogT, t->dlogT, N_OUT, cap, 256)) return rc;
@@ -1228,13 +1173,8 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     // small batches: 64-wide N tiles so that the GEMMs spread over the SMs (256-wide tiles give 2 x 8 CTAs at n = 256)
     const bool narrow = ((M + BM - 1) / BM) * (FC1_OUT / 256) < 74;
     if (narrow) {
-        if (t->gemm_cluster) {
-            if (int rc = launch_gemm_cluster<TC_EPI_TANH_ACT, 64, true>(net, t->tm_p2_q, t->tm_w1t64, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
-            if (int rc = launch_gemm_cluster<TC_EPI_STORE_F32, 64, true>(net, t->tm_h1_q, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, w.logits, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
-        } else {
         if (int rc = launch_gemm<TC_EPI_TANH_ACT, 64, true>(net, t->tm_p2, t->tm_w1t64, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
         if (int rc = launch_gemm<TC_EPI_STORE_F32, 64, true>(net, t->tm_h1, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, w.logits, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
-        }
         if (int rc = fp32_softmax_loss(net, w.logits, w.y, t_dev, w.dlog, t->dlog_bf, mse, n, s)) return rc;
     } else {
         if (int rc = launch_gemm<TC_EPI_TANH_ACT, 256, true>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
@@ -1264,9 +1204,6 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[0], wg));
     // da1 = (dlog * W2^T) .* (1 - h1^2)
     if (narrow) {
-        if (t->gemm_cluster) {
-            if (int rc = launch_gemm_cluster<TC_EPI_DTANH, 64, false>(net, t->tm_dlog_q, t->tm_w2b64, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
-        } else
         if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_dlog, t->tm_w2b64, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
     } else {
         if (int rc = launch_gemm<TC_EPI_DTANH, 256, false>(net, t->tm_dlog, t->tm_w2b, EpiArgs{nullptr, w.da1, t->da1_bf, t->h1, 0}, M, FC2_IN, FC2_OUT, s)) return rc;
@@ -1290,9 +1227,6 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order (the epilogue's bf16 copy is not needed: it goes to a sink of
     // its own -- dlog_bf, the sink before, may still be read by the side stream's transpose)
     if (narrow) {
-        if (t->gemm_cluster) {
-            if (int rc = launch_gemm_cluster<TC_EPI_DTANH, 64, false>(net, t->tm_da1_q, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->g2_sink, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
-        } else
         if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->g2_sink, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     } else {
         if (int rc = launch_gemm<TC_EPI_DTANH, 256, false>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->g2_sink, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;

@@ -86,8 +86,6 @@ struct TcState {
     float *db2_partial = nullptr;                                    // [cap][64] per-crop conv2 bias-gradient sums
     __nv_bfloat16 *w2kt = nullptr;                                   // [256 k = tap*16+ci][64 co] = conv2.W, K-major over co
     CUtensorMap tm_e2, tm_e2T, tm_colT, tm_w2kt;
-    CUtensorMap tm_p2_q, tm_h1_q, tm_dlog_q, tm_da1_q;   // the activation operands with BM/4-row boxes: A slices of the 4-CTA cluster GEMMs
-    bool gemm_cluster = true;                            // HP_GEMM_CLUSTER=0: plain narrow GEMMs at small batches (A/B runs)
     CUtensorMap tm_w1t64, tm_w2t64, tm_w1b64, tm_w2b64;   // the same weights with 64-row boxes (small-batch GEMMs)
     CUtensorMap tm_w1b, tm_w2b, tm_dlog, tm_da1, tm_h1T, tm_p2T, tm_dlogT, tm_da1T;
     CUtensorMap tm_dlogT128, tm_da1T128;                  // 128-row boxes: half-width weight-gradient tiles in data-parallel mode
