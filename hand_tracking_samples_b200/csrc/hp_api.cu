@@ -75,7 +75,7 @@ int ensure_workspace(Net &net, int64_t n)
     rc |= dev_alloc(w.g1, cap * P1_N);
     if (!w.w2p) rc |= dev_alloc(w.w2p, (size_t)C2_CO * C2_KDIM);
     if (!w.partial) {
-        w.partial_floats = (size_t)128 * C2_CO * C2_KDIM;  // conv2 split-K partials dominate
+        w.partial_floats = (size_t)2 * 512 * N_OUT;   // >= conv2 split-K partials (128 x 64 x 256); also the two split-K halves of the small-batch fc2 logits
         rc |= dev_alloc(w.partial, w.partial_floats);
     }
     if (rc) return HP_ERR_CUDA;

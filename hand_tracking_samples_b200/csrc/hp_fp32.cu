@@ -385,17 +385,19 @@ __global__ void __launch_bounds__(256) colsum_partial(const float *__restrict__ 
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ logits, float *__restrict__ y,
                                                       const float *__restrict__ t, float *__restrict__ dlog,
-                                                      float *__restrict__ mse, __nv_bfloat16 *__restrict__ dlog_bf = nullptr)
+                                                      float *__restrict__ mse, __nv_bfloat16 *__restrict__ dlog_bf = nullptr,
+                                                      const float *__restrict__ logits2 = nullptr)
 {
     const int64_t crop = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *lg = logits + crop * N_OUT;
+    const float *lg2 = logits2 ? logits2 + crop * N_OUT : nullptr;   // second split-K half of the logits (tensor path, small batches)
     float ev[8], es;
     // big span `warp`
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        ev[i] = exp_cr(lg[warp * 256 + i * 32 + lane]);
+        ev[i] = exp_cr(lg2 ? lg[warp * 256 + i * 32 + lane] + lg2[warp * 256 + i * 32 + lane] : lg[warp * 256 + i * 32 + lane]);
         sum += ev[i];
     }
 #pragma unroll
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float *__restrict__ 
 #pragma unroll
     for (int i = 0; i < 8; i++) ev[i] = ev[i] / sum;
     // small spans: element 2048 + tid, span = tid / 16
-    es = exp_cr(lg[2048 + tid]);
+    es = exp_cr(lg2 ? lg[2048 + tid] + lg2[2048 + tid] : lg[2048 + tid]);
     float ssum = es;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
@@ -1012,9 +1014,10 @@ int fp32_init_attributes()
     return 0;
 }
 
-int fp32_softmax_loss(Net &net, const float *logits, float *y, const float *t, float *dlog, __nv_bfloat16 *dlog_bf, float *mse, int64_t n, cudaStream_t s)
+int fp32_softmax_loss(Net &net, const float *logits, float *y, const float *t, float *dlog, __nv_bfloat16 *dlog_bf, float *mse, int64_t n, cudaStream_t s,
+                      const float *logits2)
 {
-    softmax_kernel<true><<<(unsigned)n, 256, 0, s>>>(logits, y, t, dlog, mse, dlog_bf);
+    softmax_kernel<true><<<(unsigned)n, 256, 0, s>>>(logits, y, t, dlog, mse, dlog_bf, logits2);
     LAUNCH_CHECK(net);
     return 0;
 }

@@ -464,7 +464,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ptx::tmem_ld32(taddr + c * 32, r);
                     ptx::tmem_ld_wait();
                     uint4 o[8];
-                    if (bias) {   // LFull::forward: Y = B + x*W (cnn.h:407), logits for the separate softmax / loss kernel
+                    if (bias && split == 0) {   // LFull::forward: Y = B + x*W (cnn.h:407), logits for the separate softmax / loss kernel (split-K: the bias goes into the first partial)
 #pragma unroll
                         for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) + bptr[c * 32 + j]);
                     }
@@ -1037,7 +1037,8 @@ static int launch_gemm(Net &net, const CUtensorMap &tmA, const CUtensorMap &tmB,
 }
 
 // hp_fp32.cu: softmax + loss + softmax backward from logits, optionally also emitting dlogits as bf16
-int fp32_softmax_loss(Net &net, const float *logits, float *y, const float *t, float *dlog, __nv_bfloat16 *dlog_bf, float *mse, int64_t n, cudaStream_t s);
+int fp32_softmax_loss(Net &net, const float *logits, float *y, const float *t, float *dlog, __nv_bfloat16 *dlog_bf, float *mse, int64_t n, cudaStream_t s,
+                      const float *logits2 = nullptr);
 
 // hp_fp32.cu
 int fp32_conv_stage(Net &net, const float *x, int64_t n, __nv_bfloat16 *p2_bf, cudaStream_t s);
@@ -1174,8 +1175,18 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     const bool narrow = ((M + BM - 1) / BM) * (FC1_OUT / 256) < 74;
     if (narrow) {
         if (int rc = launch_gemm<TC_EPI_TANH_ACT, 64, true>(net, t->tm_p2, t->tm_w1t64, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
+        // fc2 at 64-wide tiles is 2 x 36 CTAs, each bounded by what 192 KB of loads in flight deliver (profiles/r2_train_step.md);
+        // when the SMs allow it the K range is cut in two (144 CTAs) and the loss kernel adds the two partial logits
+        const int fc2_tiles = ((M + BM - 1) / BM) * (FC2_OUT / 64);
+        static const bool no_split2 = getenv("HP_FC2_SPLITK") && getenv("HP_FC2_SPLITK")[0] == '0';   // A/B
+        const bool split2 = !no_split2 && 2 * fc2_tiles <= t->num_sms && (size_t)2 * M * N_OUT <= w.partial_floats;
+        if (split2) {
+            if (int rc = launch_gemm<TC_EPI_STORE_F32, 64, true>(net, t->tm_h1, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, w.partial, nullptr, nullptr, 0, 2}, M, FC2_OUT, FC2_IN, s)) return rc;
+            if (int rc = fp32_softmax_loss(net, w.partial, w.y, t_dev, w.dlog, t->dlog_bf, mse, n, s, w.partial + (size_t)M * N_OUT)) return rc;
+        } else {
         if (int rc = launch_gemm<TC_EPI_STORE_F32, 64, true>(net, t->tm_h1, t->tm_w2t64, EpiArgs{net.params + OFF_F2B, w.logits, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
         if (int rc = fp32_softmax_loss(net, w.logits, w.y, t_dev, w.dlog, t->dlog_bf, mse, n, s)) return rc;
+        }
     } else {
         if (int rc = launch_gemm<TC_EPI_TANH_ACT, 256, true>(net, t->tm_p2, t->tm_w1t, EpiArgs{net.params + OFF_F1B, t->h1, nullptr, nullptr, 0}, M, FC1_OUT, FC1_IN, s)) return rc;
         if (int rc = launch_gemm<TC_EPI_SOFTMAX_F32, 256, true>(net, t->tm_h1, t->tm_w2t, EpiArgs{net.params + OFF_F2B, w.y, nullptr, nullptr, 0}, M, FC2_OUT, FC2_IN, s)) return rc;
