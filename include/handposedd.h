@@ -240,9 +240,14 @@ HP_API int hp_train_batch(hp_net *net, const float *x, const float *t, int64_t n
  * 128 bytes of label upload per sample instead of 9,216.  HOST buffers. */
 HP_API int hp_train_batch_points(hp_net *net, const float *x, const float *points, const float *vals, int64_t n, float alpha,
                                  float *mse_out, int precision);
-/* DEVICE buffers, caller's stream.  With data parallelism enabled (hp_dp_init)
- * the gradient sum is all-reduced over NCCL behind the backward pass before
- * the update. */
+/* DEVICE buffers, caller's stream: the step is ordered after the work already queued on `stream` and everything it
+ * launches (also on the library's internal side streams: weight-gradient branches, the update of each gradient bucket,
+ * the data-parallel exchange) has rejoined `stream` when the call returns -- the caller only ever synchronises `stream`.
+ * A call that repeats the previous one exactly (same buffers, n, alpha, precision and a non-legacy stream) is replayed as
+ * a CUDA graph captured on the second such call (HP_NO_GRAPH=1 disables); the result is bit-identical to the eager step.
+ * With data parallelism enabled the gradient sums are exchanged behind the backward pass before the update:
+ * hp_dp_peer_init -> one kernel per gradient bucket over NVLink peer memory (also graph-replayed), hp_dp_init -> NCCL
+ * all-reduce.  The gradient store afterwards holds this rank's (peer path) or the all-reduced (NCCL path) sums. */
 HP_API int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, int64_t n,
                                  float alpha, float *mse_dev, int precision, void *stream);
 /* Forward + backward WITHOUT the update: leaves sum_b g_b in the net's
