@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_dpR.sh N r1 r2 ... -- N-GPU data-parallel step time for several exchange CTA counts
+# usage: [HP_PEER_TMA=1] gpu_dpR.sh N r1 r2 ... -- N-GPU data-parallel step time for several exchange CTA counts
 N=$1; shift
 export HP_PEER_TIMEOUT_S=20
 p=29800
