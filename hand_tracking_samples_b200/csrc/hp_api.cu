@@ -80,6 +80,7 @@ int ensure_workspace(Net &net, int64_t n)
     }
     if (rc) return HP_ERR_CUDA;
     w.cap = cap;
+    net.alloc_epoch++;
     return 0;
 }
 
@@ -946,15 +947,20 @@ int hp_train_batch_device(hp_net *net, const float *x_dev, const float *t_dev, i
     const bool dp_ok = N.world == 1 || (N.peer && N.peer->ready);
     const bool eligible = !no_graph && !G.disabled && dp_ok && !N.profiling && !N.step_timing && n <= FP32_CHUNK && s != nullptr &&
                           !(precision == HP_PRECISION_TENSOR && N.tc_dirty);
-    const bool same = G.x == x_dev && G.t == t_dev && G.mse == mse_dev && G.n == n && G.alpha == alpha && G.precision == precision && G.stream == s;
+    // the key of a captured step: its arguments AND the generation of the device buffers it points into (an Eval with a
+    // larger batch in between may reallocate the workspace or the activation buffers)
+    const bool same = G.x == x_dev && G.t == t_dev && G.mse == mse_dev && G.n == n && G.alpha == alpha && G.precision == precision && G.stream == s &&
+                      G.alloc_epoch == N.alloc_epoch;
     if (!eligible || !same) {
         if (!same) {
             if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
             G.x = x_dev; G.t = t_dev; G.mse = mse_dev; G.n = n; G.alpha = alpha; G.precision = precision; G.stream = s;
             G.seen = 0;
         }
-        if (eligible) G.seen = 1;
-        return train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s);
+        const int rc = train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s);
+        G.alloc_epoch = N.alloc_epoch;   // what this step allocated is part of the key from here on
+        if (eligible && rc == 0) G.seen = 1;
+        return rc;
     }
     if (!G.exec) {
         if (G.seen < 1) { G.seen = 1; return train_step_eager(N, x_dev, t_dev, n, alpha, mse_dev, precision, s); }

@@ -161,11 +161,14 @@ struct Net {
         float alpha = 0.f;
         int precision = -1;
         cudaStream_t stream = nullptr;
+        uint64_t alloc_epoch = 0;     // Net::alloc_epoch the captured pointers belong to
         int seen = 0;                 // consecutive calls with this key
         cudaGraphExec_t exec = nullptr;
         int64_t launches_per_step = 0;
         bool disabled = false;        // HP_NO_GRAPH=1, or a capture failed once
     } step_graph;
+    uint64_t alloc_epoch = 0;         // bumped whenever a device buffer a training step touches is (re)allocated: a captured step graph
+                                      // holds raw pointers / tensor maps and must not outlive them
     int64_t last_n = 0;
     // per-stage timing (hp_profile): a pool of events, (stage, begin, end) triples
     bool profiling = false;

@@ -962,6 +962,7 @@ static int tc_ensure(Net &net, int64_t n)
     if (int rc = make_map_f16(&t->tm_p2, t->p2, cap, FC1_IN, BM)) return rc;
     if (int rc = make_map_f16(&t->tm_h1, t->h1, cap, FC1_OUT, BM)) return rc;
     t->cap = cap;
+    net.alloc_epoch++;
     return 0;
 }
 
@@ -1086,6 +1087,7 @@ static int tc_train_ensure(Net &net)
     if (int rc = make_map_bf16(&t->tm_e2, t->e2, ld, C2_CO, BM)) return rc;
     if (int rc = make_map_bf16(&t->tm_e2T, t->e2T, C2_CO, ld, 64)) return rc;
     if (int rc = make_map_bf16(&t->tm_colT, t->colT, C2_KDIM, ld, BM)) return rc;
+    net.alloc_epoch++;
     return 0;
 }
 

@@ -451,6 +451,29 @@ def test_fused_updates_leave_the_16bit_shadows_equal_to_a_full_rebuild():
     assert not np.array_equal(fresh.get_params(), hp.PoseInitializerCNN("").get_params())   # the steps did move the weights
 
 
+def test_step_graph_survives_buffer_reallocation_between_steps():
+    # A replayed training step holds raw device pointers and tensor maps.  An Eval with a larger batch between two
+    # steps reallocates the activation buffers (tensor path) and the workspace (FP32 path): the next step must notice
+    # (the graph is keyed on the allocation generation) and give the same weights as a net that never ran those Evals.
+    import torch
+    n = 96
+    x = np.concatenate([synth.depthlike_crops(64, 311), synth.uniform_crops(32, 312)])
+    t = synth.heatmap_labels(n, 313)
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+    side = torch.cuda.Stream()
+    big = synth.uniform_crops(700, 314)
+    for prec in (hp.PRECISION_TENSOR, hp.PRECISION_FP32):
+        a, b = hp.PoseInitializerCNN(""), hp.PoseInitializerCNN("")
+        for step in range(6):
+            for m in (a, b):
+                m.train_batch_device(xd.data_ptr(), td.data_ptr(), n, 0.01 / n, None, precision=prec, stream=side.cuda_stream)
+            torch.cuda.synchronize()
+            if step == 2:      # a's step graph exists by now (captured on the second call)
+                a.eval_batch(big, precision=hp.PRECISION_TENSOR)
+                a.eval_batch(big, precision=hp.PRECISION_FP32)
+        assert np.array_equal(a.get_params(), b.get_params()), prec
+
+
 def test_tensor_path_pool_winners_agree_with_fp32_path(net):
     import torch
     n = 16
