@@ -131,7 +131,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m_tiles = (M + BM - 1) / BM;
     const int mn_tiles = m_tiles * n_tiles;
     const int kb_total = (K + BK - 1) / BK;     // a ragged last block reads zeros (TMA out-of-bounds fill)
-    const int ksplit = (EPI == TC_EPI_STORE_F32 && ea.ksplit > 1) ? ea.ksplit : 1;
+    const int ksplit = ((EPI == TC_EPI_STORE_F32 || EPI == TC_EPI_DTANH) && ea.ksplit > 1) ? ea.ksplit : 1;   // DTANH: the factor (1 - h^2) is applied per partial (linear)
     const int kb_per = (kb_total + ksplit - 1) / ksplit;
     const int num_tiles = mn_tiles * ksplit;
 
@@ -477,7 +477,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int row = m_blk * BM + ew * 32 + lane;
                 const int rowc = row < M ? row : M - 1;   // clamp: rows past M are computed but never stored
                 const act_t *hrow = ea.H + (size_t)rowc * N + n_blk * BN;
-                uint8_t *gt32 = reinterpret_cast<uint8_t *>(out) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 4;
+                uint8_t *gt32 = reinterpret_cast<uint8_t *>(out) + ((size_t)split * M * N + (size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 4;
                 uint8_t *gt16 = reinterpret_cast<uint8_t *>(ea.out2) + ((size_t)(m_blk * BM + ew * 32) * N + n_blk * BN) * 2;
                 int fb = 0;
 #pragma unroll 1
@@ -519,8 +519,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             ob[h * 4 + q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
-                    flush(fb & 1, ob, gt16 + c * 128, (size_t)N * 2);
-                    fb++;
+                    if (ea.out2) {   // (null with split-K: a bf16 copy of a partial is of no use)
+                        flush(fb & 1, ob, gt16 + c * 128, (size_t)N * 2);
+                        fb++;
+                    }
                 }
             }
             ptx::tc_fence_before();
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(256) transpose_bf16_pair(TransposeJob j0, Tran
 // the next multiple of 64 that the last K block of the split-K GEMM reads.
 __global__ void __launch_bounds__(256) conv2_bwd_operands(const float *__restrict__ g2_hwc, const uint8_t *__restrict__ idx2, const float *__restrict__ p1,
                                                           __nv_bfloat16 *__restrict__ E, __nv_bfloat16 *__restrict__ ET, __nv_bfloat16 *__restrict__ colT,
-                                                          float *__restrict__ db_partial, int n, int64_t ld)
+                                                          float *__restrict__ db_partial, int n, int64_t ld, const float *__restrict__ g2_hwc_b = nullptr)
 {
     // Shared-memory layouts chosen so that every phase reads conflict-free (the first version of this kernel spent its
     // time in 5- to 9-way conflicted loads): the gradient transposed to [co][37], the dense error as bf16 [pos][66]
@@ -663,7 +665,11 @@ __global__ void __launch_bounds__(256) conv2_bwd_operands(const float *__restric
     const int64_t crop = blockIdx.x;
     const int t = threadIdx.x;
     for (int i = t; i < P2_N / 4; i += 256) {
-        const float4 v = reinterpret_cast<const float4 *>(g2_hwc + crop * P2_N)[i];   // HWC: index pp*64 + co
+        float4 v = reinterpret_cast<const float4 *>(g2_hwc + crop * P2_N)[i];   // HWC: index pp*64 + co
+        if (g2_hwc_b) {   // the fc1 dX GEMM ran as two K ranges: the gradient is the sum of its two partial products
+            const float4 u = reinterpret_cast<const float4 *>(g2_hwc_b + crop * P2_N)[i];
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
         const int pp = i >> 4, co0 = (i & 15) * 4;
         sgT[(co0 + 0) * GP + pp] = v.x;
         sgT[(co0 + 1) * GP + pp] = v.y;
@@ -1118,14 +1124,14 @@ static int side_join(Net &net, int i, cudaStream_t s)
     return 0;
 }
 
-static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s)
+static int tc_conv_backward_gemm(Net &net, const float *x, int64_t n, const float *g2_hwc, bool accumulate, cudaStream_t s, const float *g2_hwc_b = nullptr)
 {
     TcState *t = net.tc;
     Workspace &w = net.ws;
     float *G = net.grads;
     const int64_t ld = TRAIN_CAP * C2_POS;
     const int R = (int)(n * C2_POS);
-    conv2_bwd_operands<<<(unsigned)n, 256, 0, s>>>(g2_hwc, w.idx2, w.p1, t->e2, t->e2T, t->colT, t->db2_partial, (int)n, ld);
+    conv2_bwd_operands<<<(unsigned)n, 256, 0, s>>>(g2_hwc, w.idx2, w.p1, t->e2, t->e2T, t->colT, t->db2_partial, (int)n, ld, g2_hwc_b);
     LAUNCH_CHECK(net);
     const bool side = side_reductions(n);
     if (side) {
@@ -1239,14 +1245,24 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[1], wg));
     // g2 = (da1 * W1^T) .* (1 - p2^2), columns in HWC order (the epilogue's bf16 copy is not needed: it goes to a sink of
     // its own -- dlog_bf, the sink before, may still be read by the side stream's transpose)
-    if (narrow) {
+    // like fc2 forward: at 64-wide tiles this GEMM is 2 x 36 latency-bound CTAs; in two K ranges (144 CTAs) each writes
+    // (1 - p2^2) x its partial product and conv2_bwd_operands, the only reader, adds the two
+    static const bool ffma_conv_bwd = getenv("HP_CONV_BWD_FFMA") != nullptr;   // A/B switch for the previous FFMA kernels
+    static const bool no_dx_split = getenv("HP_DX1_SPLITK") && getenv("HP_DX1_SPLITK")[0] == '0';   // A/B
+    const int dx1_tiles = ((M + BM - 1) / BM) * (FC1_IN / 64);
+    const bool dx1_split = narrow && !ffma_conv_bwd && !no_dx_split && 2 * dx1_tiles <= t->num_sms && (size_t)2 * M * FC1_IN <= w.partial_floats;
+    const float *g2a = w.g2, *g2b = nullptr;
+    if (dx1_split) {
+        if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.partial, nullptr, t->p2, 0, 2}, M, FC1_IN, FC1_OUT, s)) return rc;
+        g2a = w.partial;
+        g2b = w.partial + (size_t)M * FC1_IN;
+    } else if (narrow) {
         if (int rc = launch_gemm<TC_EPI_DTANH, 64, false>(net, t->tm_da1, t->tm_w1b64, EpiArgs{nullptr, w.g2, t->g2_sink, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     } else {
         if (int rc = launch_gemm<TC_EPI_DTANH, 256, false>(net, t->tm_da1, t->tm_w1b, EpiArgs{nullptr, w.g2, t->g2_sink, t->p2, 0}, M, FC1_IN, FC1_OUT, s)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_dx[1], s));
     // ---- conv stages backward (winners-only weight gradients; FFMA)
-    static const bool ffma_conv_bwd = getenv("HP_CONV_BWD_FFMA") != nullptr;   // A/B switch for the previous FFMA kernels
     if (ffma_conv_bwd) {
         if (int rc = tc_conv_backward(net, x, n, w.g2, accumulate, s)) return rc;
         if (side) {   // the side stream's weight-gradient branch rejoins the chain here (the GEMM route joins it itself)
@@ -1254,7 +1270,7 @@ int tc_train_grad(Net &net, const float *x, const float *t_dev, int64_t n, float
             if (int rc = side_join(net, 2, s)) return rc;
         }
     } else {
-        if (int rc = tc_conv_backward_gemm(net, x, n, w.g2, accumulate, s)) return rc;
+        if (int rc = tc_conv_backward_gemm(net, x, n, g2a, accumulate, s, g2b)) return rc;
     }
     HP_CUDA_TRY(cudaEventRecord(net.ev_bucket[2], s));
     return 0;
